@@ -1,0 +1,80 @@
+"""CPU oracle for the critic-ensemble targets (REDQ / TQC).  TEST INFRASTRUCTURE ONLY.
+
+Same rules as ``oracle/pe_oracle.py``: a restatement of the reference arithmetic, pinned by the
+fixtures under ``tests/golden/`` that were generated from the unmodified reference; imported
+only by tests, ``smoke()`` and the CPU-baseline legs of ``bench.py``.
+"""
+import numpy as np
+import torch
+
+from .pe_oracle import mlp_forward
+
+
+def subset_indices_batchwise(ensemble_size, sample_number, rng=np.random):
+    """EnsembleQValue.value batch-wise branch, mirl/values/ensemble_value.py:84-86."""
+    return rng.choice(ensemble_size, sample_number, replace=False)
+
+
+def subset_indices_rowwise(ensemble_size, batch_size, sample_number, rng=np.random):
+    """sample_from_ensemble(replace=False), mirl/values/ensemble_value.py:20-31.
+    Returns ``[sample_number, B]`` member indices (distinct within a column)."""
+    if sample_number == 1:
+        return rng.choice(ensemble_size, batch_size * sample_number).reshape(1, batch_size)
+    indices = [rng.choice(ensemble_size - i, (batch_size,)) for i in range(sample_number)]
+    indices = np.stack(indices)
+    for i in range(sample_number - 1, 0, -1):
+        for j in range(i, sample_number):
+            indices[j] = (indices[j] + indices[i - 1] + 1) % (ensemble_size + 1 - i)
+    return indices
+
+
+def reduce_members(sampled, mode):
+    """ensemble_value.py:91-96 (min / mean / max over the member dim, -3)."""
+    if mode == "min":
+        return torch.min(sampled, dim=-3)[0]
+    if mode == "mean":
+        return torch.mean(sampled, dim=-3)
+    if mode == "max":
+        return torch.max(sampled, dim=-3)[0]
+    raise NotImplementedError(mode)
+
+
+def ensemble_q(W, b, obs, act, activation="relu"):
+    """EnsembleQValue forward, ensemble_value.py:59-63,75-77: ``cat[obs,act]`` -> MLP ->
+    ``[E,B,1]``.  Evaluates every member, like the reference."""
+    return mlp_forward(W, b, torch.cat([obs, act], dim=-1), activation)
+
+
+def redq_value(W, b, obs, act, member_idx=None, row_idx=None, mode="min", activation="relu"):
+    """EnsembleQValue.value for a drawn subset.  ``member_idx [n]`` = batch-wise draw
+    (ensemble_value.py:84-86); ``row_idx [n,B]`` = per-row draw (:10-34); neither = all
+    members (:89-90)."""
+    q = ensemble_q(W, b, obs, act, activation)
+    if member_idx is not None:
+        q = q[..., torch.as_tensor(np.asarray(member_idx), dtype=torch.long), :, :]
+    elif row_idx is not None:
+        row_idx = torch.as_tensor(np.asarray(row_idx), dtype=torch.long)
+        ar = torch.arange(q.shape[1]).expand_as(row_idx)
+        q = q[row_idx, ar]
+    return reduce_members(q, mode)
+
+
+def td_target(value, rewards, terminals, log_prob, alpha, discount=0.99):
+    """SACAgent.compute_q_target arithmetic, mirl/agents/sac_agent.py:80-85 (also
+    tqc_agent.py:54-56 when ``value`` holds atoms ``[B,K]``)."""
+    return rewards + (1.0 - terminals) * discount * (value - alpha * log_prob)
+
+
+def tqc_atoms(W, b, obs, act, number_drop=None, percentage_drop=None, activation="relu"):
+    """TQCQValue.value(return_atoms=True), mirl/values/distributional_value.py:59-93 and
+    ``_drop_atoms`` :32-57.  Returns ``value [B,1]`` and kept atoms ``[B, E*Q - drop]``."""
+    atoms = mlp_forward(W, b, torch.cat([obs, act], dim=-1), activation)   # [E,B,Q]
+    atoms = atoms.transpose(-3, -2)
+    atoms = atoms.reshape(atoms.shape[:-2] + (-1,))                          # [B,E*Q]
+    n_atom = atoms.shape[-1]
+    if number_drop is None:
+        number_drop = 0 if percentage_drop is None else round(n_atom * percentage_drop / 100)
+    if number_drop > 0:
+        atoms, _ = torch.sort(atoms, dim=-1)
+        atoms = atoms[..., :-number_drop]
+    return torch.mean(atoms, dim=-1, keepdim=True), atoms

@@ -1,0 +1,275 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference on CPU.
+
+Container-only: needs ``/root/reference`` (imported through ``oracle/ref_shim.py``; reference
+sources are never copied).  Run:  ``python -m tests.golden.gen_golden``  from the repo root.
+The fixtures store only the reference's outputs (+ the NumPy/torch RNG draws it consumed);
+weights and inputs are rebuilt from seeds by ``tests/golden/cases.py``.
+"""
+import json
+import os
+import tempfile
+
+import numpy as np
+import torch
+
+from oracle import ref_shim
+from tests.golden import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LOSS_VEC7 = [0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4]
+LOSS_VEC10 = [0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4, 0.05, 0.8, 0.6]
+
+
+def T(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def proj(t, seed):
+    """Checksum of a tensor: norm and a projection on a fixed random direction (fp64)."""
+    a = t.detach().double().numpy()
+    r = np.random.RandomState(seed).standard_normal(a.shape)
+    return np.array([np.sqrt((a * a).sum()), (a * r).sum()])
+
+
+def build_pe(cfg, seed, env="cheetah"):
+    from mirl.agents.mbpo.pe_model import PEModel
+    p = cases.pe_params(seed, cfg)
+    m = PEModel(ref_shim.FakeEnv(env), known=["done"], ensemble_size=cfg["E"],
+                elite_number=cfg["elites"], hidden_layers=list(cfg["hidden"]),
+                activation=cfg["act"], connection="simple", reward_coef=1, bound_reg_coef=2e-2,
+                weight_decay=list(cases.WEIGHT_DECAY)[:len(cfg["hidden"]) + 1])
+    sd = {k: T(v) for k, v in cases.pe_state_dict(p).items()}
+    m.load_state_dict(sd)
+    return m, p
+
+
+def gen_forward():
+    m, _ = build_pe(cases.MBPO, 11)
+    o, a = cases.rollout_inputs(12, 200)
+    with torch.no_grad():
+        def run(model, o, a):
+            x = torch.cat([model.obs_processor.process(o), model.action_processor.process(a)], -1)
+            from mirl.torch_modules.mlp import MLP
+            out = MLP.forward(model.module, x)
+            return model.module._get_mean_logstd(out)
+        mean, ls = run(m, T(o), T(a))
+        m64 = m.double()
+        mean64, ls64 = run(m64, T(o).double(), T(a).double())
+    np.savez(os.path.join(HERE, "pe_forward_mbpo.npz"), mean=mean.numpy(), logstd=ls.numpy(),
+             mean64=mean64.numpy(), logstd64=ls64.numpy())
+
+
+def gen_step():
+    for env, seed in (("cheetah", 21), ("hopper", 22), ("walker2d", 23), ("mb_ant", 24),
+                      ("mb_humanoid", 25), ("inverted_pendulum", 26)):
+        m, _ = build_pe(cases.MBPO, 11, env)
+        m.remember_loss(LOSS_VEC7)
+        B = 1000
+        o, a = cases.rollout_inputs(seed, B, env=env)
+        np.random.seed(seed); torch.manual_seed(seed)
+        with torch.no_grad():
+            no, r, d, _ = m.step(T(o), T(a))
+        # replay of what step() consumed from the two global generators (pe_model.py:169,176)
+        np.random.seed(seed); torch.manual_seed(seed)
+        idx = np.random.choice(m.elite_indices, B)
+        eps = torch.randn(B, cases.OBS + 1)
+        np.savez(os.path.join(HERE, "pe_step_%s.npz" % env), idx=idx.astype(np.int64),
+                 eps=eps.numpy(), next_obs=no.numpy(), reward=r.numpy(), done=d.numpy(),
+                 elite_indices=np.asarray(m.elite_indices, dtype=np.int64))
+    # elite_indices=None before the first training (pe_model.py:167-168)
+    m, _ = build_pe(cases.MBPO, 11)
+    o, a = cases.rollout_inputs(27, 64)
+    np.random.seed(27); torch.manual_seed(27)
+    with torch.no_grad():
+        no, r, d, _ = m.step(T(o), T(a))
+    np.random.seed(27); torch.manual_seed(27)
+    idx = np.random.choice(list(np.arange(7)), 64)
+    eps = torch.randn(64, cases.OBS + 1)
+    np.savez(os.path.join(HERE, "pe_step_noelite.npz"), idx=idx.astype(np.int64), eps=eps.numpy(),
+             next_obs=no.numpy(), reward=r.numpy(), done=d.numpy())
+
+
+def gen_dist():
+    from mirl.agents.mbpo.mopo_collector import MOPOCollector
+    m, _ = build_pe(cases.MOPO, 31, "hopper")
+    m.remember_loss(LOSS_VEC10)
+    B = 128
+    o, a = cases.rollout_inputs(32, B, env="hopper")
+    np.random.seed(32); torch.manual_seed(32)
+    with torch.no_grad():
+        no, r, d, info = m.step(T(o), T(a), return_distribution=True)
+    np.random.seed(32); torch.manual_seed(32)
+    idx = np.random.choice(m.elite_indices, B)
+    eps = torch.randn(B, cases.OBS + 1)
+    out = {k: v.numpy() for k, v in info.items()}
+    means, stds = info["ensemble_next_obs_mean"], info["ensemble_next_obs_std"]
+    # MOPOCollector.add_sample penalty arithmetic (mopo_collector.py:42-53), via the class
+    class _Pool:
+        def add_samples(self, s): self.s = s
+    for kind in ("total_var", "max_var"):
+        pool = _Pool()
+        c = MOPOCollector(m, None, None, pool, penalty_coef=1.0, penalty_type=kind)
+        from mirl.utils.logger import logger
+        logger.set_log_level(logger.ERROR) if hasattr(logger, "set_log_level") else None
+        stop = torch.zeros(B, 1)
+        with torch.no_grad():
+            try:
+                c.add_sample(stop, T(o), T(a), no, r, d, info, 0, 0)
+                out["penalized_reward_" + kind] = pool.s["rewards"]
+            except Exception as e:            # logger side effects; fall back to the formulae
+                print("add_sample failed (%s); using formulae" % e)
+                if kind == "max_var":
+                    pen = torch.max(torch.norm(stds, dim=-1, keepdim=True), dim=0)[0]
+                else:
+                    pen = torch.sum(torch.mean(stds ** 2, 0) + torch.var(means, 0), -1, keepdim=True)
+                out["penalized_reward_" + kind] = (r - pen).numpy()
+    np.savez(os.path.join(HERE, "pe_step_dist_mopo.npz"), idx=idx.astype(np.int64),
+             eps=eps.numpy(), next_obs=no.numpy(), reward=r.numpy(), done=d.numpy(),
+             elite_indices=np.asarray(m.elite_indices, dtype=np.int64), **out)
+
+
+def named_trainables(m):
+    return [(n, p) for n, p in m.named_parameters() if p.requires_grad]
+
+
+def gen_loss():
+    res = {}
+    m, _ = build_pe(cases.MBPO, 11)
+    names = [n for n, _ in named_trainables(m)]
+    for tag, ignore in (("keep", False), ("ignore", True)):
+        bt = {k: T(v) for k, v in cases.train_batch(41, 7, 256).items()}
+        m.zero_grad()
+        loss, el = m.compute_loss(bt["observations"], bt["actions"], bt["deltas"], bt["rewards"],
+                                  bt["terminals"], ignore)
+        loss.backward()
+        res["loss_" + tag] = loss.detach().numpy()
+        res["ensemble_loss_" + tag] = el.detach().numpy()
+        res["grad_proj_" + tag] = np.stack([proj(p.grad, 1000 + i)
+                                            for i, (_, p) in enumerate(named_trainables(m))])
+    bs = {k: T(v) for k, v in cases.train_batch(42, 7, 500, shared=True).items()}
+    with torch.no_grad():
+        loss, el = m.compute_loss(bs["observations"], bs["actions"], bs["deltas"], bs["rewards"],
+                                  bs["terminals"])          # eval default ignore_terminal_state=True
+    res["loss_shared"] = loss.numpy(); res["ensemble_loss_shared"] = el.numpy()
+    np.savez(os.path.join(HERE, "pe_loss_mbpo.npz"), names=np.array(names), **res)
+
+    # small config: full gradients
+    m, _ = build_pe(cases.SMALL, 51)
+    bt = {k: T(v) for k, v in cases.train_batch(52, 3, 64).items()}
+    m.zero_grad()
+    loss, el = m.compute_loss(bt["observations"], bt["actions"], bt["deltas"], bt["rewards"],
+                              bt["terminals"], False)
+    loss.backward()
+    out = {"loss": loss.detach().numpy(), "ensemble_loss": el.detach().numpy()}
+    for n, p in named_trainables(m):
+        out["grad/" + n] = p.grad.numpy()
+    np.savez(os.path.join(HERE, "pe_loss_small.npz"), **out)
+
+
+def gen_train():
+    from mirl.agents.mbpo.pe_model_trainer import PEModelTrainer
+    from mirl.utils.logger import logger
+    tmp = tempfile.mkdtemp()
+    logger.set_snapshot_dir(tmp)
+    for tag, cfg, seed, B, steps in (("mbpo", cases.MBPO, 11, 256, 10), ("small", cases.SMALL, 51, 64, 10)):
+        m, _ = build_pe(cfg, seed)
+        tr = PEModelTrainer(ref_shim.FakeEnv(), m, lr=1e-3, tb_log_freq=-1, silent=True,
+                            ignore_terminal_state=False)
+        out = {"loss": [], "ensemble_loss": []}
+        for s in range(steps):
+            bt = {k: T(v) for k, v in cases.train_batch(600 + s, cfg["E"], B).items()}
+            diag = tr.train_from_torch_batch(bt)
+            out["loss"].append(diag["train_loss"])
+            out["ensemble_loss"].append([diag["mt/net_%d/train_loss" % i] for i in range(cfg["E"])])
+            if s + 1 in (1, steps):
+                nt = named_trainables(m)
+                out["param_proj_%d" % (s + 1)] = np.stack([proj(p, 2000 + i) for i, (_, p) in enumerate(nt)])
+                st = tr.optimizer.state
+                out["m_proj_%d" % (s + 1)] = np.stack([proj(st[p]["exp_avg"], 3000 + i) for i, (_, p) in enumerate(nt)])
+                out["v_proj_%d" % (s + 1)] = np.stack([proj(st[p]["exp_avg_sq"], 4000 + i) for i, (_, p) in enumerate(nt)])
+                if tag == "small":
+                    for n, p in nt:
+                        out["param_%d/%s" % (s + 1, n)] = p.detach().numpy().copy()
+        out["loss"] = np.array(out["loss"], dtype=np.float64)
+        out["ensemble_loss"] = np.array(out["ensemble_loss"], dtype=np.float64)
+        out["names"] = np.array([n for n, _ in named_trainables(m)])
+        np.savez(os.path.join(HERE, "pe_train_%s.npz" % tag), **out)
+
+
+def gen_critics():
+    from mirl.values.ensemble_value import EnsembleQValue, sample_from_ensemble
+    from mirl.values.distributional_value import TQCQValue
+    env = ref_shim.FakeEnv()
+    c = cases.REDQ
+    q = EnsembleQValue(env, ensemble_size=c["E"], hidden_layers=list(c["hidden"]), activation=c["act"])
+    W, b = cases.mlp_params(71, c["E"], [23] + c["hidden"] + [c["out"]])
+    q.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(W, b).items()})
+    x = cases.critic_inputs(72, 256)
+    o, a = T(x["obs"]), T(x["act"])
+    out = {}
+    with torch.no_grad():
+        np.random.seed(73)
+        out["bw_min"] = q.value(o, a, sample_number=2, batchwise_sample=True, mode="min")[0].numpy()
+        np.random.seed(73)
+        out["bw_idx"] = np.random.choice(c["E"], 2, replace=False)
+        np.random.seed(74)
+        out["row_min"] = q.value(o, a, sample_number=2, batchwise_sample=False, mode="min")[0].numpy()
+        np.random.seed(74)
+        idx = [np.random.choice(c["E"] - i, (256,)) for i in range(2)]
+        out["row_raw_draws"] = np.stack(idx)
+        np.random.seed(75)
+        out["row3_max"] = q.value(o, a, sample_number=3, batchwise_sample=False, mode="max")[0].numpy()
+        out["all_mean"] = q.value(o, a, sample_number=None, mode="mean")[0].numpy()
+        out["all_min"] = q.value(o, a, sample_number=10, mode="min")[0].numpy()
+        out["ensemble"] = q.value(o, a, only_return_ensemble=True)[1]["ensemble_value"].numpy()
+        # SACAgent.compute_q_target arithmetic (sac_agent.py:80-85) on the batch-wise value
+        alpha, disc = 0.2, 0.99
+        out["td_target"] = (T(x["rewards"]) + (1. - T(x["terminals"])) * disc *
+                            (T(out["bw_min"]) - alpha * T(x["log_prob"]))).numpy()
+    np.savez(os.path.join(HERE, "redq.npz"), **out)
+
+    c = cases.TQC
+    q = TQCQValue(env, ensemble_size=c["E"], number_head=c["out"], hidden_layers=list(c["hidden"]),
+                  activation=c["act"])
+    W, b = cases.mlp_params(81, c["E"], [23] + c["hidden"] + [c["out"]])
+    q.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(W, b).items()})
+    x = cases.critic_inputs(82, 256)
+    o, a = T(x["obs"]), T(x["act"])
+    out = {}
+    with torch.no_grad():
+        v, info = q.value(o, a, percentage_drop=8, return_atoms=True)
+        out["value_drop8pct"], out["atoms_drop8pct"] = v.numpy(), info["value_atoms"].numpy()
+        v, info = q.value(o, a, number_drop=0, return_atoms=True, return_ensemble=True)
+        out["value_drop0"], out["atoms_drop0"] = v.numpy(), info["value_atoms"].numpy()
+        out["ensemble"] = q.value(o, a, only_return_ensemble=True)[1]["ensemble_atoms"].numpy()
+        alpha, disc = 0.2, 0.99
+        out["atoms_target"] = (T(x["rewards"]) + (1. - T(x["terminals"])) * disc *
+                               (T(out["atoms_drop8pct"]) - alpha * T(x["log_prob"]))).numpy()
+    np.savez(os.path.join(HERE, "tqc.npz"), **out)
+
+
+def gen_keys():
+    from mirl.values.ensemble_value import EnsembleQValue
+    from mirl.values.distributional_value import TQCQValue
+    m, _ = build_pe(cases.MBPO, 11)
+    env = ref_shim.FakeEnv()
+    q = EnsembleQValue(env, ensemble_size=10, hidden_layers=[256, 256], activation="relu")
+    t = TQCQValue(env, ensemble_size=5, number_head=25, hidden_layers=[512] * 3, activation="relu")
+    out = {n: {k: list(v.shape) for k, v in mod.state_dict().items()}
+           for n, mod in (("PEModel", m), ("EnsembleQValue", q), ("TQCQValue", t))}
+    out["PEModel.parameters"] = [n for n, _ in m.named_parameters()]
+    with open(os.path.join(HERE, "state_dict_keys.json"), "w") as f:
+        json.dump(out, f, indent=0)
+
+
+def main():
+    ref_shim.install()
+    torch.set_num_threads(1)        # bitwise-stable reductions for the fixtures
+    gen_forward(); gen_step(); gen_dist(); gen_loss(); gen_train(); gen_critics(); gen_keys()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith((".npz", ".json")):
+            print("%8d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))
+
+
+if __name__ == "__main__":
+    main()
