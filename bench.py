@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- MBPO ensemble rollout throughput (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one model rollout of HORIZON steps over ROWS start states per GPU (HalfCheetah-shaped
+synthetic data: obs 17, act 6, 7 members / 5 elites, 4x200 swish), i.e. ROWS*HORIZON transitions
+per GPU per step; actions are pre-generated U(-1,1) (the reference's own
+``COMPOCollector(random_sample=True)`` mode), the done function is cheetah's.  Work per GPU is
+fixed as N grows ("scaling": "weak"); at N > 1 every rank also all-gathers the transitions it
+generated into a replicated pool buffer (NCCL), inside the timed region.
+
+``value``   transitions/s, inputs resident in HBM, CUDA-event timed, max over ranks.
+``e2e``     same metric through the public API (``B200PEModel.step``) from pinned HOST buffers:
+            H2D of start states / actions / member indices and D2H of the generated
+            transitions are inside the timed region, as are the NumPy member draw and the
+            torch noise draw the reference also performs.
+``roofline`` the rollout kernel alone (events inside the C ABI), algorithmic FLOPs / launch.
+``cpu_baseline`` the CPU oracle (restatement of the reference's op sequence: all E members for
+            every row) on this box's host cores, bounded sample.
+``--impl reference`` times only that CPU arm (the reference itself is Python and cannot travel
+            to the GPU box; the oracle is pinned to it by tests/golden).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS = int(os.environ.get("MB_BENCH_ROWS", 1_000_000))       # start states per GPU per step
+HORIZON = int(os.environ.get("MB_BENCH_HORIZON", 5))
+CPU_SAMPLE_ROWS = int(os.environ.get("MB_BENCH_CPU_ROWS", 50_000))
+FLOP_PER_TRANSITION = 263_600     # one member: 2*(23*200 + 3*200*200 + 200*36), SURVEY.md 8(d)
+BYTES_PER_TRANSITION = 241        # obs 68 + act 24 + noise 72 + idx 1 in; next_obs 68 + r 4 + d 4 out
+METRIC = "mbpo_rollout_transitions_per_s"
+LOSS_VEC7 = [0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tensor": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"], "src": "measured (sustained)"}
+    return {"tensor": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(device):
+    from tests.golden import cases
+    from tests.helpers_gpu import make_pe_model
+    m, p = make_pe_model(cases.MBPO, 11, "cheetah", device=device)
+    m.remember_loss(LOSS_VEC7)
+    return m, p
+
+
+def cpu_arm(steps, warmup, threads=None):
+    """Reference CPU path (oracle restatement, kind 'port'): PEModel.step over a bounded sample."""
+    from oracle import pe_oracle as po
+    from tests.golden import cases
+    from tests.util import T, to_torch
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    p = to_torch(cases.pe_params(11, cases.MBPO))
+    _, elites = po.rank_elites(LOSS_VEC7, 7, 5)
+    B = CPU_SAMPLE_ROWS
+    o, a = cases.rollout_inputs(3, B)
+    o, a = T(o), T(a)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            idx = torch.from_numpy(np.random.choice(elites, B))      # pe_model.py:169
+            eps = torch.randn(B, 18)                                 # pe_model.py:176
+            po.rollout_step(p, o, a, idx, eps, "cheetah")
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return {"value": B / sec, "unit": "transitions/s", "cores": threads, "kind": "port",
+            "sample": "%d steps of PEModel.step restatement (all 7 members, fp32 torch CPU) over "
+                      "%d states, %.2f s/step" % (steps, B, sec)}, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    base, sec = cpu_arm(steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "transitions/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    return {"workload": "MBPO model rollout sweep point: %d start states/GPU x horizon %d, 7 members / "
+                        "5 elites, 4x200 swish, obs17/act6, cheetah done" % (ROWS, HORIZON),
+            "rows_per_gpu": ROWS, "horizon": HORIZON, "ensemble": 7, "elites": 5,
+            "parallelism": "rows sharded over %d GPU(s); transitions all-gathered" % n,
+            "l2_policy": "inputs larger than L2 (%.0f MB of obs/act/noise per step)" %
+                         (ROWS * HORIZON * (24 + 72 + 1) / 1e6 + ROWS * 68 / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from mirl_b200 import _lib
+    L = _lib.lib()
+    model, _ = build_model(dev)
+    kernel = model._resolve_kernel()
+    B, H, O, A, D = ROWS, HORIZON, 17, 6, 18
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    obs0 = torch.randn(B, O, device=dev, generator=gen)
+    acts = torch.rand(H, B, A, device=dev, generator=gen) * 2 - 1
+    noise = torch.randn(H, B, D, device=dev, generator=gen)
+    rs = np.random.RandomState(99 + rank)
+    idx_host = rs.choice(model.elite_indices, (H, B)).astype(np.uint8)
+    idx = torch.from_numpy(idx_host).to(dev)
+    # replicated pool the generated transitions are gathered into (o, a, o', r, d = 42 floats)
+    trans = torch.empty(H, B, 2 * O + A + 2, device=dev)
+    pool = torch.empty(world, H, B, 2 * O + A + 2, device=dev) if world > 1 else None
+
+    def device_step():
+        o = obs0
+        for h in range(H):
+            no, r, d, _ = model.step(o, acts[h], indices=idx[h], noise=noise[h])
+            t = trans[h]
+            t[:, :O] = o; t[:, O:O + A] = acts[h]; t[:, O + A:2 * O + A] = no
+            t[:, 2 * O + A:2 * O + A + 1] = r; t[:, 2 * O + A + 1:] = d
+            o = no
+        if world > 1:
+            dist.all_gather_into_tensor(pool.view(world, -1), trans.view(-1))
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(device_step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * B * H / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API from pinned host buffers ------------------------------
+    h_obs0 = obs0.cpu().pin_memory()
+    h_acts = acts.cpu().pin_memory()
+    h_out = torch.empty(H, B, O + 2).pin_memory()
+    np.random.seed(4321 + rank)
+    torch.manual_seed(4321 + rank)
+
+    def e2e_step():
+        o = h_obs0.to(dev, non_blocking=True)
+        for h in range(H):
+            a = h_acts[h].to(dev, non_blocking=True)
+            no, r, d, _ = model.step(o, a)          # draws indices (NumPy, host) and noise (torch)
+            h_out[h].copy_(torch.cat([no, r, d], dim=1), non_blocking=True)
+            o = no
+        torch.cuda.current_stream().synchronize()   # the caller owns the transitions now
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_ms = timed(e2e_step, e2e_steps, 3) / e2e_steps
+    e2e = {"value": world * B * H / (e2e_ms * 1e-3), "unit": "transitions/s",
+           "h2d_bytes_per_step": B * O * 4 + H * B * (A * 4 + 1),
+           "d2h_bytes_per_step": H * B * (O + 2) * 4, "ms_per_step": e2e_ms}
+
+    # ---- roofline of the dominant kernel (events inside the C ABI around that kernel only) -------
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        L.mb_profile_enable(1)
+        ks = []
+        for it in range(6):
+            model.step(obs0, acts[it % H], indices=idx[it % H], noise=noise[it % H])
+            ms = _lib.ctypes.c_float(0)
+            _lib.check(L.mb_profile_last_ms(_lib.ctypes.byref(ms)))
+            if it >= 2:
+                ks.append(ms.value)
+        L.mb_profile_enable(0)
+        kms = float(np.mean(ks))
+        achieved = FLOP_PER_TRANSITION * B / (kms * 1e-3) / 1e12
+        roof = {"kernel": "k_pe_rollout_%s" % kernel, "bound": "tensor", "achieved": achieved,
+                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
+                "peak_source": pk["src"], "kernel_ms": kms, "launch_rows": B,
+                "hbm_gbs_algorithmic": BYTES_PER_TRANSITION * B / (kms * 1e-3) / 1e9,
+                "traffic": None}
+        prof = os.path.join(ROOT, "profiles", "rollout_traffic.json")
+        if os.path.exists(prof):
+            with open(prof) as f:
+                roof["traffic"] = json.load(f).get(roof["kernel"])
+
+    if rank == 0:
+        base, _ = cpu_arm(3, 1)
+        launches_per_step = H * 4 + (1 if world > 1 else 0) * 0
+        line = {"metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(workload_config(world), kernel=kernel),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "roofline": roof, "cpu_baseline": base}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,191 @@
+/* mirl_b200 -- C ABI of the B200-native probabilistic-ensemble hot path.
+ *
+ * Drop-in boundary for ONE path of QiZhou1997/MIRL: the ensemble MLP behind
+ *   PEModel.step / PEModel.compute_loss        (mirl/agents/mbpo/pe_model.py:252-307)
+ *   PEModelTrainer.train_from_torch_batch      (mirl/agents/mbpo/pe_model_trainer.py:85-106)
+ *   EnsembleQValue.value / TQCQValue.value     (mirl/values/ensemble_value.py:65-107,
+ *                                               mirl/values/distributional_value.py:59-93)
+ * The reference has no FFI of its own (pure Python); these are the entry points its Python
+ * classes bind through ctypes.  Rules of the ABI:
+ *   - extern "C", plain pointers and sizes; no torch / C++ types;
+ *   - every data pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - all tensors are fp32, row-major, last dimension contiguous (the reference's layout);
+ *   - no internal allocation, no device synchronisation: work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), outputs and workspace are caller-owned;
+ *   - returns 0 on success, a negative MB_E* code otherwise; mb_last_error() has the text;
+ *   - not thread-safe per handle/argument set (the reference is single-threaded).
+ */
+#ifndef MIRL_B200_H
+#define MIRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+#define MB_MAX_LAYERS 8
+
+enum { MB_OK = 0, MB_EINVAL = -1, MB_ECUDA = -2, MB_EWORKSPACE = -3, MB_EUNSUPPORTED = -4 };
+
+/* mirl/torch_modules/utils.py:138-149 get_activation (the two the path's configs use) */
+enum { MB_ACT_SWISH = 0, MB_ACT_RELU = 1 };
+
+/* mirl/environments/reward_done_functions/<name>.py done_function */
+enum {
+    MB_DONE_CHEETAH = 0, MB_DONE_HOPPER = 1, MB_DONE_WALKER2D = 2, MB_DONE_MB_ANT = 3,
+    MB_DONE_MB_HUMANOID = 4, MB_DONE_INVERTED_PENDULUM = 5
+};
+
+/* mirl/agents/mbpo/mopo_collector.py:45-52 penalty_type */
+enum { MB_PENALTY_NONE = 0, MB_PENALTY_TOTAL_VAR = 1, MB_PENALTY_MAX_VAR = 2 };
+
+/* mirl/values/ensemble_value.py:91-96 mode */
+enum { MB_REDUCE_MIN = 0, MB_REDUCE_MEAN = 1, MB_REDUCE_MAX = 2 };
+
+/* kernel family for the rollout step: hand-written SIMT fp32 FFMA, or tcgen05 (bf16x3 split
+ * operands, fp32 TMEM accumulators).  Both are sm_100a CUDA; there is no CPU path. */
+enum { MB_KERNEL_SIMT = 0, MB_KERNEL_TCGEN05 = 1 };
+
+/* Shape of an ensemble MLP (mirl/torch_modules/mlp.py:63-99, linear.py:114-133).
+ * Parameters live in ONE packed fp32 blob; mb_mlp_*_offset give float offsets:
+ *   for l in [0,L):  W_l [E][sizes[l]][sizes[l+1]]   then   b_l [E][sizes[l+1]]
+ *   then (probabilistic models only)  max_logstd [E][D], min_logstd [E][D], D = sizes[L]/2
+ * every segment starts on a multiple of 4 floats. */
+typedef struct {
+    int32_t ensemble_size;              /* E */
+    int32_t num_layers;                 /* L linear layers, 1..MB_MAX_LAYERS */
+    int32_t sizes[MB_MAX_LAYERS + 1];   /* in, hidden..., out */
+    int32_t activation;                 /* MB_ACT_*; applied after every layer but the last */
+} mb_mlp_desc;
+
+int64_t mb_mlp_weight_offset(const mb_mlp_desc* d, int layer);
+int64_t mb_mlp_bias_offset(const mb_mlp_desc* d, int layer);
+int64_t mb_mlp_logstd_offset(const mb_mlp_desc* d, int which /*0 max, 1 min*/);
+int64_t mb_mlp_param_count(const mb_mlp_desc* d, int probabilistic);
+
+/* A probabilistic-ensemble dynamics model (PEModel, pe_model.py:191-232).
+ * norm = [obs_mean O | obs_std O | act_mean A | act_std A | delta_mean O | delta_std O]
+ * (Normalizer mean/std, mirl/processors/normalizer.py:6-28; epsilon 1e-6 is applied inside). */
+typedef struct {
+    mb_mlp_desc mlp;          /* sizes[0] = O + A, sizes[L] = 2*(O+1) */
+    int32_t obs_dim;          /* O */
+    int32_t act_dim;          /* A */
+    const float* params;      /* packed blob, mb_mlp_param_count(&mlp, 1) floats */
+    const float* norm;        /* 4*O + 2*A floats */
+    const void* tc_pack;      /* mb_pe_tc_pack output, or NULL (required by MB_KERNEL_TCGEN05) */
+} mb_pe_model;
+
+int mb_abi_version(void);
+const char* mb_last_error(void);
+
+/* ---- (1) rollout step: PEModel.step (pe_model.py:252-283 over base_model.py:54-76) ------
+ * member_idx[B] (uint8) = np.random.choice(elite_indices, B) drawn by the caller exactly like
+ * pe_model.py:169; noise[B][O+1] = the torch.randn_like draw of pe_model.py:176.
+ * Writes next_obs[B][O], reward[B][1], done[B][1] (float 0/1). */
+size_t mb_pe_rollout_workspace_bytes(const mb_pe_model* m, int64_t B);
+int mb_pe_rollout_step(const mb_pe_model* m, int kernel, const float* obs, const float* act,
+                       const uint8_t* member_idx, const float* noise, int64_t B, int done_kind,
+                       float* next_obs, float* reward, float* done,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* PEModel.step(return_distribution=True) + MOPOCollector penalty (mopo_collector.py:42-53).
+ * elites_host[n_elite]: elite member ids in RANK order (pe_model.py:234-237).
+ * info tensors are [n_elite][B][.] in that order; any of them may be NULL.
+ * penalized_reward (optional) = reward - penalty_coef * penalty. */
+int mb_pe_rollout_step_dist(const mb_pe_model* m, const float* obs, const float* act,
+                            const uint8_t* member_idx, const float* noise, int64_t B,
+                            int done_kind, const int32_t* elites_host, int n_elite,
+                            float* next_obs, float* reward, float* done,
+                            float* delta_mean, float* delta_std, float* next_obs_mean,
+                            float* reward_mean, float* reward_std,
+                            int penalty_kind, float penalty_coef, float* penalty,
+                            float* penalized_reward, void* stream);
+
+/* ---- ensemble forward: per-member Gaussian mean / log-std (pe_model.py:110-151) -----------
+ * x is obs/act already split: obs[.][O], act[.][A]; per_member=0 -> inputs [B][.] shared by
+ * all members, 1 -> [E][B][.].  normalize!=0 applies the obs/action Normalizers.
+ * mean, logstd: [E][B][O+1] (logstd after the soft max/min clamp). */
+int mb_pe_forward(const mb_pe_model* m, const float* obs, const float* act, int per_member,
+                  int normalize, int64_t B, float* mean, float* logstd, void* stream);
+
+/* ---- (2) model loss / training step -------------------------------------------------------
+ * PEModel.compute_loss (pe_model.py:285-307 -> :71-108): ensemble_loss[E] and loss[1] on a
+ * per-member [E][B][.] or shared [B][.] batch; no gradients (eval_with_dataset,
+ * pe_model_trainer.py:108-121). */
+typedef struct {
+    float weight_decay[MB_MAX_LAYERS];  /* per-layer L2 coefficients (mlp.py:170-178) */
+    float bound_reg_coef;               /* pe_model.py:34,81 */
+    float reward_coef;                  /* pe_model.py:33,93 */
+    int32_t ignore_terminal_state;      /* pe_model.py:85-89 */
+    float lr, beta1, beta2, eps;        /* torch.optim.Adam, pe_model_trainer.py:47-51 */
+} mb_train_cfg;
+
+int mb_pe_loss(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs,
+               const float* act, const float* delta, const float* reward, const float* done,
+               int per_member, int64_t B, float* ensemble_loss, float* loss, void* stream);
+
+/* One PEModelTrainer.train_from_torch_batch (pe_model_trainer.py:85-106): forward, Gaussian
+ * NLL + log-std bound + L2, backward, Adam -- for the members [member_begin, member_end) only
+ * (member-sharded training: each rank passes its own slice; the others are untouched).
+ * params/exp_avg/exp_avg_sq: packed blobs (same layout), updated in place.
+ * step = 1-based Adam step count AFTER this update.  Batch tensors are [E][B][.].
+ * ensemble_loss[E] (entries of this slice written), loss_terms[3] += {sum_e loss_e, l2, bound}
+ * over this slice (zeroed by the call). */
+size_t mb_pe_train_workspace_bytes(const mb_pe_model* m, int64_t B);
+int mb_pe_train_step(const mb_pe_model* m, const mb_train_cfg* cfg, float* params,
+                     float* exp_avg, float* exp_avg_sq, int64_t step,
+                     const float* obs, const float* act, const float* delta,
+                     const float* reward, const float* done, int64_t B,
+                     int member_begin, int member_end,
+                     float* ensemble_loss, float* loss_terms,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* gradients only (same maths as the training step, no Adam); grads is a packed blob.
+ * Exposed for parity tests of loss.backward(). */
+int mb_pe_loss_grads(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs,
+                     const float* act, const float* delta, const float* reward,
+                     const float* done, int64_t B, float* grads, float* ensemble_loss,
+                     float* loss_terms, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (3) critic-ensemble targets ----------------------------------------------------------
+ * Plain ensemble forward [E][B][out] (EnsembleQValue / TQCQValue `only_return_ensemble`). */
+int mb_critic_forward(const mb_mlp_desc* d, const float* params, const float* obs,
+                      const float* act, int obs_dim, int act_dim, int64_t B, float* out,
+                      void* stream);
+
+/* EnsembleQValue.value (ensemble_value.py:65-107) with the subset reduced on the fly, fused with
+ * SACAgent.compute_q_target (sac_agent.py:80-85) when td != 0:
+ *   batch-wise subset: members_host[n_sub] (np.random.choice(E, n, replace=False), :84-86);
+ *   per-row subset:    row_members[n_sub][B] uint8 device (sample_from_ensemble, :10-34);
+ *   both NULL:         all members.
+ * Only the drawn members are evaluated.  value[B][1];  with td:
+ *   value = reward + (1 - terminal) * discount * (reduce - alpha * log_prob). */
+int mb_critic_redq_target(const mb_mlp_desc* d, const float* params, const float* obs,
+                          const float* act, int obs_dim, int act_dim, int64_t B,
+                          const int32_t* members_host, const uint8_t* row_members, int n_sub,
+                          int mode, int td, const float* reward, const float* terminal,
+                          const float* log_prob, float alpha, float discount, float* value,
+                          void* stream);
+
+/* TQCQValue.value(return_atoms=True) (distributional_value.py:32-93) fused with
+ * TQCAgent.compute_q_target (tqc_agent.py:41-57) when td != 0.  atoms[B][E*Q - n_drop] ascending
+ * (unsorted member-major order when n_drop == 0, like the reference); value[B][1] = mean of the
+ * kept atoms BEFORE the TD transform (what TQCQValue.value returns). */
+int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float* obs,
+                         const float* act, int obs_dim, int act_dim, int64_t B, int n_drop,
+                         int td, const float* reward, const float* terminal,
+                         const float* log_prob, float alpha, float discount,
+                         float* value, float* atoms, void* stream);
+
+/* ---- tcgen05 operand pack: bf16 hi/lo split of every member's weights in the UMMA
+ * shared-memory layout the rollout kernel streams (rebuild after the weights change). */
+size_t mb_pe_tc_pack_bytes(const mb_pe_model* m);
+int mb_pe_tc_pack(const mb_pe_model* m, void* pack, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIRL_B200_H */

@@ -1,0 +1,25 @@
+"""mirl_b200 -- B200-native (sm_100a) kernels behind MIRL's probabilistic-ensemble module API.
+
+Public classes mirror the reference's (same constructor arguments, methods and return values):
+
+====================  ===========================================  ============================
+here                  reference class                              reference file
+====================  ===========================================  ============================
+B200PEModel           PEModel                                      mirl/agents/mbpo/pe_model.py
+B200PEModelTrainer    PEModelTrainer                               mirl/agents/mbpo/pe_model_trainer.py
+B200MBPOCollector     MBPOCollector                                mirl/agents/mbpo/mbpo_collector.py
+B200MOPOCollector     MOPOCollector                                mirl/agents/mbpo/mopo_collector.py
+B200EnsembleQValue    EnsembleQValue                               mirl/values/ensemble_value.py
+B200TQCQValue         TQCQValue                                    mirl/values/distributional_value.py
+====================  ===========================================  ============================
+
+All computation goes through ``libmirl_b200.so`` (``include/mirl_b200.h``); there is no PyTorch
+or CPU fallback -- calls raise if the library is missing or the tensors are not on a CUDA device.
+"""
+from .pe_model import B200PEModel                      # noqa: F401
+from .pe_model_trainer import B200PEModelTrainer       # noqa: F401
+from .values import B200EnsembleQValue, B200TQCQValue  # noqa: F401
+from .collectors import B200MBPOCollector, B200MOPOCollector  # noqa: F401
+
+__all__ = ["B200PEModel", "B200PEModelTrainer", "B200EnsembleQValue", "B200TQCQValue",
+           "B200MBPOCollector", "B200MOPOCollector"]

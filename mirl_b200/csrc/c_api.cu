@@ -1,0 +1,281 @@
+// extern "C" surface of libmirl_b200.so (declared in include/mirl_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "pe_kernels.h"
+#include "simt_mlp.cuh"
+
+namespace mb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int validate_desc(const mb_mlp_desc* d, const char* who) {
+    MB_CHECK_ARG(d != nullptr, "%s: null mlp descriptor", who);
+    MB_CHECK_ARG(d->num_layers >= 1 && d->num_layers <= MB_MAX_LAYERS, "%s: num_layers %d outside [1,%d]",
+                 who, d->num_layers, MB_MAX_LAYERS);
+    MB_CHECK_ARG(d->ensemble_size >= 1 && d->ensemble_size <= 32, "%s: ensemble_size %d outside [1,32]", who,
+                 d->ensemble_size);
+    for (int l = 0; l <= d->num_layers; ++l)
+        MB_CHECK_ARG(d->sizes[l] >= 1 && d->sizes[l] <= SimtTile32::MAXW, "%s: layer width %d outside [1,%d]",
+                     who, d->sizes[l], SimtTile32::MAXW);
+    MB_CHECK_ARG(d->activation == MB_ACT_SWISH || d->activation == MB_ACT_RELU, "%s: unknown activation %d",
+                 who, d->activation);
+    return MB_OK;
+}
+
+int validate_model(const mb_pe_model* m, const char* who) {
+    MB_CHECK_ARG(m != nullptr, "%s: null model", who);
+    int rc = validate_desc(&m->mlp, who);
+    if (rc) return rc;
+    const mb_mlp_desc& d = m->mlp;
+    MB_CHECK_ARG(m->obs_dim >= 1 && m->act_dim >= 1, "%s: bad obs/act dims", who);
+    MB_CHECK_ARG(d.sizes[0] == m->obs_dim + m->act_dim, "%s: mlp input %d != obs+act %d", who, d.sizes[0],
+                 m->obs_dim + m->act_dim);
+    MB_CHECK_ARG(d.sizes[d.num_layers] == 2 * (m->obs_dim + 1), "%s: mlp output %d != 2*(obs+1) %d", who,
+                 d.sizes[d.num_layers], 2 * (m->obs_dim + 1));
+    MB_CHECK_ARG(m->obs_dim + 1 <= 64, "%s: obs_dim %d too large (max 63)", who, m->obs_dim);
+    for (int l = 0; l <= d.num_layers; ++l)
+        MB_CHECK_ARG(d.sizes[l] <= SimtTile64::MAXW, "%s: model layer width %d > %d", who, d.sizes[l],
+                     SimtTile64::MAXW);
+    MB_CHECK_ARG(m->params != nullptr && m->norm != nullptr, "%s: null params/norm", who);
+    return MB_OK;
+}
+
+static PeDev to_dev(const mb_pe_model* m) {
+    PeDev d;
+    d.mlp = m->mlp;
+    d.O = m->obs_dim;
+    d.A = m->act_dim;
+    d.params = m->params;
+    d.norm = m->norm;
+    return d;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+int mb_abi_version(void) { return MB_ABI_VERSION; }
+const char* mb_last_error(void) { return g_err; }
+
+int64_t mb_mlp_weight_offset(const mb_mlp_desc* d, int layer) { return w_offset(*d, layer); }
+int64_t mb_mlp_bias_offset(const mb_mlp_desc* d, int layer) { return b_offset(*d, layer); }
+int64_t mb_mlp_logstd_offset(const mb_mlp_desc* d, int which) { return logstd_offset(*d, which); }
+int64_t mb_mlp_param_count(const mb_mlp_desc* d, int probabilistic) {
+    return param_count(*d, probabilistic != 0);
+}
+
+size_t mb_pe_rollout_workspace_bytes(const mb_pe_model* m, int64_t B) {
+    (void)m;
+    return bucket_workspace_bytes(B < 1 ? 1 : B, 64);
+}
+
+int mb_pe_rollout_step(const mb_pe_model* m, int kernel, const float* obs, const float* act,
+                       const uint8_t* member_idx, const float* noise, int64_t B, int done_kind,
+                       float* next_obs, float* reward, float* done, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    int rc = validate_model(m, "mb_pe_rollout_step");
+    if (rc) return rc;
+    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "mb_pe_rollout_step: B %lld out of range", (long long)B);
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(obs && act && member_idx && noise && next_obs && reward && done,
+                 "mb_pe_rollout_step: null tensor");
+    MB_CHECK_ARG(done_kind >= MB_DONE_CHEETAH && done_kind <= MB_DONE_INVERTED_PENDULUM,
+                 "mb_pe_rollout_step: unknown done_kind %d", done_kind);
+    if (workspace == nullptr || workspace_bytes < mb_pe_rollout_workspace_bytes(m, B)) {
+        set_error("mb_pe_rollout_step: workspace %zu < %zu bytes", workspace_bytes,
+                  mb_pe_rollout_workspace_bytes(m, B));
+        return MB_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (kernel == MB_KERNEL_SIMT)
+        return launch_pe_rollout_simt(to_dev(m), obs, act, member_idx, noise, B, done_kind, next_obs, reward,
+                                      done, workspace, s);
+    if (kernel == MB_KERNEL_TCGEN05) {
+        MB_CHECK_ARG(m->tc_pack != nullptr, "mb_pe_rollout_step: MB_KERNEL_TCGEN05 needs tc_pack");
+        return launch_pe_rollout_tc(to_dev(m), m->tc_pack, obs, act, member_idx, noise, B, done_kind, next_obs,
+                                    reward, done, workspace, s);
+    }
+    set_error("mb_pe_rollout_step: unknown kernel family %d", kernel);
+    return MB_EINVAL;
+}
+
+int mb_pe_rollout_step_dist(const mb_pe_model* m, const float* obs, const float* act,
+                            const uint8_t* member_idx, const float* noise, int64_t B, int done_kind,
+                            const int32_t* elites_host, int n_elite, float* next_obs, float* reward,
+                            float* done, float* delta_mean, float* delta_std, float* next_obs_mean,
+                            float* reward_mean, float* reward_std, int penalty_kind,
+                            float penalty_coef, float* penalty, float* penalized_reward,
+                            void* stream) {
+    int rc = validate_model(m, "mb_pe_rollout_step_dist");
+    if (rc) return rc;
+    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "mb_pe_rollout_step_dist: B out of range");
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(obs && act && member_idx && noise && next_obs && reward && done,
+                 "mb_pe_rollout_step_dist: null tensor");
+    MB_CHECK_ARG(elites_host && n_elite >= 1 && n_elite <= m->mlp.ensemble_size,
+                 "mb_pe_rollout_step_dist: bad elite list");
+    for (int i = 0; i < n_elite; ++i)
+        MB_CHECK_ARG(elites_host[i] >= 0 && elites_host[i] < m->mlp.ensemble_size,
+                     "mb_pe_rollout_step_dist: elite id %d out of range", elites_host[i]);
+    MB_CHECK_ARG(penalty_kind >= MB_PENALTY_NONE && penalty_kind <= MB_PENALTY_MAX_VAR,
+                 "mb_pe_rollout_step_dist: unknown penalty kind %d", penalty_kind);
+    return launch_pe_rollout_dist_simt(to_dev(m), elites_host, n_elite, obs, act, member_idx, noise, B,
+                                       done_kind, next_obs, reward, done, delta_mean, delta_std,
+                                       next_obs_mean, reward_mean, reward_std, penalty_kind, penalty_coef,
+                                       penalty, penalized_reward, (cudaStream_t)stream);
+}
+
+int mb_pe_forward(const mb_pe_model* m, const float* obs, const float* act, int per_member,
+                  int normalize, int64_t B, float* mean, float* logstd, void* stream) {
+    int rc = validate_model(m, "mb_pe_forward");
+    if (rc) return rc;
+    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "mb_pe_forward: B out of range");
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(obs && act && mean && logstd, "mb_pe_forward: null tensor");
+    return launch_pe_forward_simt(to_dev(m), obs, act, per_member, normalize, B, mean, logstd, nullptr,
+                                  nullptr, nullptr, 0, 1.f, nullptr, (cudaStream_t)stream);
+}
+
+int mb_pe_loss(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs, const float* act,
+               const float* delta, const float* reward, const float* done, int per_member, int64_t B,
+               float* ensemble_loss, float* loss, void* stream) {
+    int rc = validate_model(m, "mb_pe_loss");
+    if (rc) return rc;
+    MB_CHECK_ARG(cfg != nullptr, "mb_pe_loss: null cfg");
+    MB_CHECK_ARG(B >= 1 && B < (int64_t)1 << 31, "mb_pe_loss: B out of range");
+    MB_CHECK_ARG(obs && act && delta && reward && ensemble_loss, "mb_pe_loss: null tensor");
+    MB_CHECK_ARG(!cfg->ignore_terminal_state || done, "mb_pe_loss: ignore_terminal_state needs done");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(ensemble_loss, 0, sizeof(float) * m->mlp.ensemble_size, s);
+    (void)loss;   // the scalar loss (sum + L2 + bound) is assembled by the host wrapper
+    return launch_pe_forward_simt(to_dev(m), obs, act, per_member, 1, B, nullptr, nullptr, delta, reward,
+                                  done, cfg->ignore_terminal_state, cfg->reward_coef, ensemble_loss, s);
+}
+
+size_t mb_pe_train_workspace_bytes(const mb_pe_model* m, int64_t B) {
+    return train_workspace_bytes(m->mlp, B < 1 ? 1 : B);
+}
+
+static int train_common(const char* who, const mb_pe_model* m, const mb_train_cfg* cfg, float* params,
+                        float* exp_avg, float* exp_avg_sq, int64_t step, const float* obs,
+                        const float* act, const float* delta, const float* reward, const float* done,
+                        int64_t B, int e0, int e1, float* grads, float* ensemble_loss,
+                        float* loss_terms, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate_model(m, who);
+    if (rc) return rc;
+    MB_CHECK_ARG(cfg != nullptr, "%s: null cfg", who);
+    MB_CHECK_ARG(m->mlp.activation == MB_ACT_SWISH, "%s: only swish models are trainable", who);
+    MB_CHECK_ARG(B >= 1 && B < (int64_t)1 << 24, "%s: B %lld out of range", who, (long long)B);
+    MB_CHECK_ARG(0 <= e0 && e0 < e1 && e1 <= m->mlp.ensemble_size, "%s: member slice [%d,%d) invalid", who, e0,
+                 e1);
+    MB_CHECK_ARG(obs && act && delta && reward && ensemble_loss && loss_terms, "%s: null tensor", who);
+    MB_CHECK_ARG(!cfg->ignore_terminal_state || done, "%s: ignore_terminal_state needs done", who);
+    if (workspace == nullptr || workspace_bytes < mb_pe_train_workspace_bytes(m, B)) {
+        set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, mb_pe_train_workspace_bytes(m, B));
+        return MB_EWORKSPACE;
+    }
+    return launch_pe_train(to_dev(m), *cfg, params, exp_avg, exp_avg_sq, step, obs, act, delta, reward, done,
+                           B, e0, e1, grads, ensemble_loss, loss_terms, workspace, (cudaStream_t)stream);
+}
+
+int mb_pe_train_step(const mb_pe_model* m, const mb_train_cfg* cfg, float* params, float* exp_avg,
+                     float* exp_avg_sq, int64_t step, const float* obs, const float* act,
+                     const float* delta, const float* reward, const float* done, int64_t B,
+                     int member_begin, int member_end, float* ensemble_loss, float* loss_terms,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    MB_CHECK_ARG(params && exp_avg && exp_avg_sq, "mb_pe_train_step: null optimiser state");
+    MB_CHECK_ARG(m && params == m->params, "mb_pe_train_step: params must be the model's blob");
+    MB_CHECK_ARG(step >= 1, "mb_pe_train_step: step must be >= 1");
+    return train_common("mb_pe_train_step", m, cfg, params, exp_avg, exp_avg_sq, step, obs, act, delta,
+                        reward, done, B, member_begin, member_end, nullptr, ensemble_loss, loss_terms,
+                        workspace, workspace_bytes, stream);
+}
+
+int mb_pe_loss_grads(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs, const float* act,
+                     const float* delta, const float* reward, const float* done, int64_t B,
+                     float* grads, float* ensemble_loss, float* loss_terms, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    MB_CHECK_ARG(grads != nullptr, "mb_pe_loss_grads: null grads");
+    return train_common("mb_pe_loss_grads", m, cfg, nullptr, nullptr, nullptr, 1, obs, act, delta, reward,
+                        done, B, 0, m ? m->mlp.ensemble_size : 0, grads, ensemble_loss, loss_terms, workspace,
+                        workspace_bytes, stream);
+}
+
+static int check_critic(const char* who, const mb_mlp_desc* d, const float* params, const float* obs,
+                        const float* act, int O, int A, int64_t B) {
+    int rc = validate_desc(d, who);
+    if (rc) return rc;
+    MB_CHECK_ARG(O >= 1 && A >= 0 && d->sizes[0] == O + A, "%s: mlp input %d != obs+act %d", who, d->sizes[0],
+                 O + A);
+    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "%s: B out of range", who);
+    MB_CHECK_ARG(params && obs && act, "%s: null tensor", who);
+    return MB_OK;
+}
+
+int mb_critic_forward(const mb_mlp_desc* d, const float* params, const float* obs, const float* act,
+                      int obs_dim, int act_dim, int64_t B, float* out, void* stream) {
+    int rc = check_critic("mb_critic_forward", d, params, obs, act, obs_dim, act_dim, B);
+    if (rc) return rc;
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(out != nullptr, "mb_critic_forward: null out");
+    return launch_critic_forward(*d, params, obs, act, obs_dim, act_dim, B, out, (cudaStream_t)stream);
+}
+
+int mb_critic_redq_target(const mb_mlp_desc* d, const float* params, const float* obs, const float* act,
+                          int obs_dim, int act_dim, int64_t B, const int32_t* members_host,
+                          const uint8_t* row_members, int n_sub, int mode, int td, const float* reward,
+                          const float* terminal, const float* log_prob, float alpha, float discount,
+                          float* value, void* stream) {
+    int rc = check_critic("mb_critic_redq_target", d, params, obs, act, obs_dim, act_dim, B);
+    if (rc) return rc;
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(value != nullptr, "mb_critic_redq_target: null value");
+    MB_CHECK_ARG(d->sizes[d->num_layers] == 1, "mb_critic_redq_target: critic output must be 1");
+    MB_CHECK_ARG(mode >= MB_REDUCE_MIN && mode <= MB_REDUCE_MAX, "mb_critic_redq_target: unknown mode %d", mode);
+    MB_CHECK_ARG(!(members_host && row_members), "mb_critic_redq_target: pass one of members_host/row_members");
+    if (members_host || row_members)
+        MB_CHECK_ARG(n_sub >= 1 && n_sub <= d->ensemble_size, "mb_critic_redq_target: n_sub %d out of range", n_sub);
+    if (members_host)
+        for (int i = 0; i < n_sub; ++i)
+            MB_CHECK_ARG(members_host[i] >= 0 && members_host[i] < d->ensemble_size,
+                         "mb_critic_redq_target: member id %d out of range", members_host[i]);
+    MB_CHECK_ARG(!td || (reward && terminal && log_prob), "mb_critic_redq_target: td needs reward/terminal/log_prob");
+    return launch_critic_redq(*d, params, obs, act, obs_dim, act_dim, B, members_host, row_members, n_sub, mode,
+                              td, reward, terminal, log_prob, alpha, discount, value, (cudaStream_t)stream);
+}
+
+int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float* obs, const float* act,
+                         int obs_dim, int act_dim, int64_t B, int n_drop, int td, const float* reward,
+                         const float* terminal, const float* log_prob, float alpha, float discount,
+                         float* value, float* atoms, void* stream) {
+    int rc = check_critic("mb_critic_tqc_target", d, params, obs, act, obs_dim, act_dim, B);
+    if (rc) return rc;
+    if (B == 0) return MB_OK;
+    const int NA = d->ensemble_size * d->sizes[d->num_layers];
+    MB_CHECK_ARG(n_drop >= 0 && n_drop < NA, "mb_critic_tqc_target: n_drop %d outside [0,%d)", n_drop, NA);
+    MB_CHECK_ARG(NA <= 512, "mb_critic_tqc_target: %d atoms per row unsupported (max 512)", NA);
+    MB_CHECK_ARG(!td || (reward && terminal && log_prob), "mb_critic_tqc_target: td needs reward/terminal/log_prob");
+    return launch_critic_tqc(*d, params, obs, act, obs_dim, act_dim, B, n_drop, td, reward, terminal, log_prob,
+                             alpha, discount, value, atoms, (cudaStream_t)stream);
+}
+
+size_t mb_pe_tc_pack_bytes(const mb_pe_model* m) { return m ? tc_pack_bytes(m->mlp) : 0; }
+
+int mb_pe_tc_pack(const mb_pe_model* m, void* pack, void* stream) {
+    int rc = validate_model(m, "mb_pe_tc_pack");
+    if (rc) return rc;
+    MB_CHECK_ARG(pack != nullptr, "mb_pe_tc_pack: null pack");
+    return launch_tc_pack(to_dev(m), pack, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Internal launcher interface between the C ABI (c_api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mirl_b200.h"
+
+namespace mb {
+
+// Device-side view of mb_pe_model (passed by value as a kernel parameter).
+struct PeDev {
+    mb_mlp_desc mlp;
+    int O, A;
+    const float* params;
+    const float* norm;
+};
+
+// Rows grouped by drawn member: perm[start .. start+count) are the rows of tile t = tiles[t]
+// (x = member, y = start, z = count).  *ntiles is computed on the device (no host sync).
+struct BucketPlan {
+    int* perm;
+    int4* tiles;
+    int* ntiles;
+    int max_tiles;
+};
+size_t bucket_workspace_bytes(int64_t B, int TM);
+BucketPlan bucket_rows(const uint8_t* idx, int64_t B, int E, int TM, void* ws, cudaStream_t s);
+
+// ---- SIMT fp32 family (pe_simt.cu)
+int launch_pe_rollout_simt(const PeDev& m, const float* obs, const float* act, const uint8_t* idx,
+                           const float* noise, int64_t B, int done_kind, float* next_obs,
+                           float* reward, float* done, void* ws, cudaStream_t s);
+int launch_pe_forward_simt(const PeDev& m, const float* obs, const float* act, int per_member,
+                           int normalize, int64_t B, float* mean, float* logstd, const float* delta,
+                           const float* reward, const float* done, int ignore_terminal,
+                           float reward_coef, float* ensemble_loss, cudaStream_t s);
+int launch_pe_rollout_dist_simt(const PeDev& m, const int32_t* elites, int n_elite, const float* obs,
+                                const float* act, const uint8_t* idx, const float* noise, int64_t B,
+                                int done_kind, float* next_obs, float* reward, float* done,
+                                float* delta_mean, float* delta_std, float* next_obs_mean,
+                                float* reward_mean, float* reward_std, int penalty_kind,
+                                float penalty_coef, float* penalty, float* penalized_reward,
+                                cudaStream_t s);
+
+// ---- tcgen05 family (pe_tc.cu)
+size_t tc_pack_bytes(const mb_mlp_desc& d);
+int launch_tc_pack(const PeDev& m, void* pack, cudaStream_t s);
+int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, const float* act,
+                         const uint8_t* idx, const float* noise, int64_t B, int done_kind,
+                         float* next_obs, float* reward, float* done, void* ws, cudaStream_t s);
+
+// ---- model training (pe_train.cu)
+size_t train_workspace_bytes(const mb_mlp_desc& d, int64_t B);
+int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, float* exp_avg,
+                    float* exp_avg_sq, int64_t step, const float* obs, const float* act,
+                    const float* delta, const float* reward, const float* done, int64_t B,
+                    int e0, int e1, float* grads_out, float* ensemble_loss, float* loss_terms,
+                    void* ws, cudaStream_t s);
+
+// ---- critic targets (critic.cu)
+int launch_critic_forward(const mb_mlp_desc& d, const float* params, const float* obs,
+                          const float* act, int O, int A, int64_t B, float* out, cudaStream_t s);
+int launch_critic_redq(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
+                       int O, int A, int64_t B, const int32_t* members, const uint8_t* row_members,
+                       int n_sub, int mode, int td, const float* reward, const float* terminal,
+                       const float* log_prob, float alpha, float discount, float* value,
+                       cudaStream_t s);
+int launch_critic_tqc(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
+                      int O, int A, int64_t B, int n_drop, int td, const float* reward,
+                      const float* terminal, const float* log_prob, float alpha, float discount,
+                      float* value, float* atoms, cudaStream_t s);
+
+}  // namespace mb

@@ -1,0 +1,354 @@
+// Model-training step of the probabilistic ensemble, SIMT fp32 family.
+//
+// One PEModelTrainer.train_from_torch_batch (mirl/agents/mbpo/pe_model_trainer.py:85-106):
+//   forward  (PEModel.compute_loss, pe_model.py:285-307 -> :71-143)  -> k_train_fwd
+//   loss.backward()  (autograd over ~60 ATen ops, 9 GEMMs)            -> k_train_gemm<DW|DX>
+//   torch.optim.Adam.step() over 84 tensors (pe_model_trainer.py:47-51,99) -> k_adam
+// Gradient formulae: SURVEY.md Appendix A.3 (validated against autograd, see
+// tests/test_oracle_golden.py::test_analytic_gradients_match_autograd_of_reference).
+// Members are independent (the loss is a plain sum over members, pe_model.py:95-96), so a call
+// may cover any member slice [e0, e1) -- that is the multi-GPU partition; no collective.
+#include "common.cuh"
+#include "simt_mlp.cuh"
+#include "pe_kernels.h"
+
+namespace mb {
+
+struct TrainWs {
+    float* x0;                     // [E][B][IN] normalised inputs
+    float* z[MB_MAX_LAYERS];       // [E][B][sizes[l+1]] pre-activations, l < L-1
+    float* gA;                     // [E][B][maxW] dL/dz ping
+    float* gB;                     // [E][B][maxW] dL/dz pong
+    float* grads;                  // packed blob
+};
+
+static int max_width(const mb_mlp_desc& d) {
+    int w = 0;
+    for (int l = 0; l <= d.num_layers; ++l) w = d.sizes[l] > w ? d.sizes[l] : w;
+    return w;
+}
+
+size_t train_workspace_bytes(const mb_mlp_desc& d, int64_t B) {
+    const int64_t E = d.ensemble_size;
+    int64_t f = round_up4(E * B * d.sizes[0]);
+    for (int l = 0; l + 1 < d.num_layers; ++l) f += round_up4(E * B * d.sizes[l + 1]);
+    f += 2 * round_up4(E * B * max_width(d));
+    f += param_count(d, true);
+    return (size_t)f * sizeof(float) + 256;
+}
+
+static TrainWs carve(const mb_mlp_desc& d, int64_t B, void* ws) {
+    TrainWs w;
+    const int64_t E = d.ensemble_size;
+    float* p = reinterpret_cast<float*>(ws);
+    w.x0 = p; p += round_up4(E * B * d.sizes[0]);
+    for (int l = 0; l < MB_MAX_LAYERS; ++l) w.z[l] = nullptr;
+    for (int l = 0; l + 1 < d.num_layers; ++l) { w.z[l] = p; p += round_up4(E * B * d.sizes[l + 1]); }
+    w.gA = p; p += round_up4(E * B * max_width(d));
+    w.gB = p; p += round_up4(E * B * max_width(d));
+    w.grads = p;
+    return w;
+}
+
+struct ZPtrs { float* p[MB_MAX_LAYERS]; };
+
+// ---- forward + loss + dL/d(out) ------------------------------------------------------------
+// grid = (row tiles, members of the slice); batch tensors are [E][B][.]
+__global__ void __launch_bounds__(kSimtThreads, 1)
+k_train_fwd(PeDev m, mb_train_cfg cfg, int e0, const float* __restrict__ obs,
+            const float* __restrict__ act, const float* __restrict__ delta,
+            const float* __restrict__ reward, const float* __restrict__ done_in, int64_t B,
+            float* __restrict__ x0s, ZPtrs zs, float* __restrict__ gout, float* __restrict__ grads,
+            float* __restrict__ ensemble_loss, float* __restrict__ loss_terms) {
+    using Tile = SimtTile64;
+    extern __shared__ __align__(16) float smem[];
+    float* buf0 = smem;
+    float* buf1 = buf0 + Tile::kActFloats;
+    float* wbuf = buf1 + Tile::kActFloats;
+    __shared__ float red[kSimtThreads / 32];
+    __shared__ float gmx[64], gmn[64];
+    const int O = m.O, A = m.A, D = O + 1, IN = O + A, IN4 = (IN + 3) & ~3;
+    const int L = m.mlp.num_layers;
+    const int e = e0 + blockIdx.y;
+    const int64_t row0 = (int64_t)blockIdx.x * Tile::TM;
+    const int cnt = (int)min((int64_t)Tile::TM, B - row0);
+    const int64_t mrow = (int64_t)e * B;
+    const float* nrm = m.norm;
+    const float* dmean = nrm + 2 * O + 2 * A;
+    const float* dstd = dmean + O;
+    const float* mxp = m.params + logstd_offset(m.mlp, 0) + e * D;
+    const float* mnp = m.params + logstd_offset(m.mlp, 1) + e * D;
+
+    // stage normalised inputs (Normalizer.process, normalizer.py:17-18) and keep a copy for dW_0
+    for (int t = threadIdx.x; t < Tile::TM * IN4; t += kSimtThreads) {
+        const int i = t / IN4, j = t - i * IN4;
+        float v = 0.f;
+        if (i < cnt && j < IN) {
+            const int64_t r = mrow + row0 + i;
+            if (j < O) v = (obs[r * O + j] - nrm[j]) / (nrm[O + j] + kNormEps);
+            else v = (act[r * A + (j - O)] - nrm[2 * O + (j - O)]) / (nrm[2 * O + A + (j - O)] + kNormEps);
+            x0s[r * IN + j] = v;
+        }
+        buf0[i * Tile::AS + j] = v;
+    }
+    if (threadIdx.x < 64) { gmx[threadIdx.x] = 0.f; gmn[threadIdx.x] = 0.f; }
+    __syncthreads();
+
+    float* zsave[MB_MAX_LAYERS];
+    for (int l = 0; l < L; ++l)
+        zsave[l] = (l + 1 < L) ? zs.p[l] + (mrow + row0) * m.mlp.sizes[l + 1] : nullptr;
+    const float* res = Tile::forward(m.mlp, m.params, e, buf0, buf1, wbuf, zsave, cnt);
+
+    const float invB = 1.f / (float)B;
+    float part = 0.f;
+    for (int t = threadIdx.x; t < cnt * D; t += kSimtThreads) {
+        const int i = t / D, j = t - i * D;
+        const int64_t r = mrow + row0 + i;
+        const float mu = res[i * Tile::AS + j], raw = res[i * Tile::AS + D + j];
+        const float mx = mxp[j], mn = mnp[j];
+        const float a = mx - raw;
+        const float ls1 = mx - softplusf_(a);
+        const float c = ls1 - mn;
+        const float ls = mn + softplusf_(c);
+        float tgt, coef;
+        if (j < O) { tgt = (delta[r * O + j] - dmean[j]) / (dstd[j] + kNormEps); coef = 1.f; }
+        else { tgt = reward[r]; coef = cfg.reward_coef; }
+        const float mask = cfg.ignore_terminal_state ? 1.f - done_in[r] : 1.f;
+        const float inv_var = expf(-2.f * ls);
+        const float diff = tgt - mu;
+        const float w = mask * coef * invB;
+        part += w * 0.5f * (kLog2Pi + 2.f * ls + diff * diff * inv_var);
+        const float g_ls = w * (1.f - diff * diff * inv_var);
+        const float sa = softplus_gradf_(a), sb = softplus_gradf_(c);
+        gout[r * (2 * D) + j] = -w * diff * inv_var;
+        gout[r * (2 * D) + D + j] = g_ls * sb * sa;
+        atomicAdd(&gmx[j], g_ls * sb * (1.f - sa));
+        atomicAdd(&gmn[j], g_ls * (1.f - sb));
+    }
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kSimtThreads / 32; ++w) s += red[w];
+        atomicAdd(ensemble_loss + e, s);
+        atomicAdd(loss_terms + 0, s);
+    }
+    if (threadIdx.x < D) {
+        const int j = threadIdx.x;
+        float gx = gmx[j], gn = gmn[j];
+        if (blockIdx.x == 0) {   // bound regulariser, once per member (pe_model.py:81,105-108)
+            gx += cfg.bound_reg_coef;
+            gn -= cfg.bound_reg_coef;
+            atomicAdd(loss_terms + 2, cfg.bound_reg_coef * (mxp[j] - mnp[j]));
+        }
+        atomicAdd(grads + logstd_offset(m.mlp, 0) + e * D + j, gx);
+        atomicAdd(grads + logstd_offset(m.mlp, 1) + e * D + j, gn);
+    }
+}
+
+// ---- backward GEMMs ------------------------------------------------------------------------
+// DW: dW[k][n] = sum_b h[b][k] * g[b][n] + wd * W[k][n];  db[n] = sum_b g[b][n]
+// DX: gprev[b][k] = (sum_n g[b][n] * W[k][n]) * swish'(z[b][k])
+constexpr int kGT = 64;    // output tile edge
+constexpr int kGR = 16;    // reduction chunk
+constexpr int kGLD = kGT + 4;
+
+template <bool DX>
+__global__ void __launch_bounds__(256)
+k_train_gemm(int e0, int64_t B, int K, int N, const float* __restrict__ hin /*x0 or z_{l-1}*/,
+             int hin_is_z, const float* __restrict__ g, const float* __restrict__ W, float wd,
+             const float* __restrict__ zprev, float* __restrict__ out, float* __restrict__ dbias,
+             float* __restrict__ loss_terms) {
+    __shared__ __align__(16) float As[kGR][kGLD];
+    __shared__ __align__(16) float Bs[kGR][kGLD];
+    __shared__ float red[8];
+    const int e = e0 + blockIdx.z;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int M = DX ? (int)B : K;        // output rows
+    const int NN = DX ? K : N;            // output cols
+    const int R = DX ? N : (int)B;        // reduction length
+    const int m0 = blockIdx.y * kGT, n0 = blockIdx.x * kGT;
+    const float* ge = g + (int64_t)e * B * N;
+    const float* he = DX ? nullptr : hin + (int64_t)e * B * K;
+    const float* We = W + (int64_t)e * K * N;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+
+    for (int r0 = 0; r0 < R; r0 += kGR) {
+        if (DX) {
+            // As[r][m] = g[m0+m][r0+r] ; Bs[r][n] = W[n0+n][r0+r]   (reduction index contiguous)
+            const int mm = tid >> 2, rq = (tid & 3) * 4;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int r = rq + c;
+                const bool rin = r0 + r < R;
+                As[r][mm] = (rin && m0 + mm < M) ? ge[(int64_t)(m0 + mm) * N + r0 + r] : 0.f;
+                Bs[r][mm] = (rin && n0 + mm < NN) ? We[(int64_t)(n0 + mm) * N + r0 + r] : 0.f;
+            }
+        } else {
+            // As[r][m] = h[r0+r][m0+m] ; Bs[r][n] = g[r0+r][n0+n]   (output index contiguous)
+            const int r = tid >> 4, cq = (tid & 15) * 4;
+            const bool rin = r0 + r < R;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float a = 0.f;
+                if (rin && m0 + cq + c < M) {
+                    a = he[(int64_t)(r0 + r) * K + m0 + cq + c];
+                    if (hin_is_z) a = swishf_(a);
+                }
+                As[r][cq + c] = a;
+                Bs[r][cq + c] = (rin && n0 + cq + c < NN) ? ge[(int64_t)(r0 + r) * N + n0 + cq + c] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kGR; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[r][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (!DX && blockIdx.y == 0 && tid < kGT) {
+#pragma unroll
+            for (int r = 0; r < kGR; ++r) bsum += Bs[r][tid];
+        }
+        __syncthreads();
+    }
+    float l2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int mi = m0 + ty * 4 + i;
+        if (mi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nj = n0 + tx * 4 + j;
+            if (nj >= NN) continue;
+            if (DX) {
+                const float z = zprev[((int64_t)e * B + mi) * K + nj];
+                const float sg = sigmoidf_(z);
+                out[((int64_t)e * B + mi) * K + nj] = acc[i][j] * (sg * (1.f + z * (1.f - sg)));
+            } else {
+                const float w = We[(int64_t)mi * N + nj];
+                out[(int64_t)e * K * N + (int64_t)mi * N + nj] = acc[i][j] + wd * w;
+                l2 += 0.5f * wd * w * w;
+            }
+        }
+    }
+    if (!DX) {
+        if (blockIdx.y == 0 && tid < kGT && n0 + tid < N) dbias[(int64_t)e * N + n0 + tid] = bsum;
+        for (int o = 16; o; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+        if ((tid & 31) == 0) red[tid >> 5] = l2;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            atomicAdd(loss_terms + 1, s);
+        }
+    }
+}
+
+// ---- Adam (torch.optim.Adam defaults, no weight decay / amsgrad) ----------------------------
+struct AdamSegs { int n; int64_t off[2 * MB_MAX_LAYERS + 2]; int64_t len[2 * MB_MAX_LAYERS + 2]; };
+
+__global__ void k_adam(AdamSegs segs, float* __restrict__ p, float* __restrict__ m1,
+                       float* __restrict__ m2, const float* __restrict__ g, float beta1,
+                       float beta2, float eps, float step_size, float bc2_sqrt) {
+    const int s = blockIdx.y;
+    const int64_t off = segs.off[s], len = segs.len[s];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = off + i;
+        const float gr = g[k];
+        const float a = m1[k] * beta1 + gr * (1.f - beta1);
+        const float v = m2[k] * beta2 + (gr * gr) * (1.f - beta2);
+        m1[k] = a;
+        m2[k] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        p[k] = p[k] - step_size * (a / denom);
+    }
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e)); return MB_ECUDA; }
+    return MB_OK;
+}
+
+int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, float* exp_avg,
+                    float* exp_avg_sq, int64_t step, const float* obs, const float* act,
+                    const float* delta, const float* reward, const float* done, int64_t B,
+                    int e0, int e1, float* grads_out, float* ensemble_loss, float* loss_terms,
+                    void* ws, cudaStream_t s) {
+    using Tile = SimtTile64;
+    const mb_mlp_desc& d = m.mlp;
+    const int L = d.num_layers, E = d.ensemble_size, D = d.sizes[L] / 2, ne = e1 - e0;
+    TrainWs w = carve(d, B, ws);
+    float* grads = grads_out ? grads_out : w.grads;
+
+    // zero the atomically accumulated outputs of this slice
+    cudaMemsetAsync(ensemble_loss + e0, 0, sizeof(float) * ne, s);
+    cudaMemsetAsync(loss_terms, 0, sizeof(float) * 3, s);
+    cudaMemsetAsync(grads + logstd_offset(d, 0) + (int64_t)e0 * D, 0, sizeof(float) * ne * D, s);
+    cudaMemsetAsync(grads + logstd_offset(d, 1) + (int64_t)e0 * D, 0, sizeof(float) * ne * D, s);
+
+    int rc = set_smem(k_train_fwd, Tile::kSmemBytes);
+    if (rc) return rc;
+    ZPtrs zs;
+    for (int l = 0; l < MB_MAX_LAYERS; ++l) zs.p[l] = w.z[l];
+    float* gcur = w.gA;
+    float* gnext = w.gB;
+    dim3 gf((unsigned)((B + Tile::TM - 1) / Tile::TM), (unsigned)ne);
+    k_train_fwd<<<gf, kSimtThreads, Tile::kSmemBytes, s>>>(m, cfg, e0, obs, act, delta, reward, done, B,
+                                                           w.x0, zs, gcur, grads, ensemble_loss,
+                                                           loss_terms);
+    MB_CUDA_LAUNCH_CHECK("k_train_fwd");
+    for (int l = L - 1; l >= 0; --l) {
+        const int K = d.sizes[l], N = d.sizes[l + 1];
+        const float* Wl = m.params + w_offset(d, l);
+        dim3 gw((unsigned)((N + kGT - 1) / kGT), (unsigned)((K + kGT - 1) / kGT), (unsigned)ne);
+        k_train_gemm<false><<<gw, 256, 0, s>>>(e0, B, K, N, l == 0 ? w.x0 : w.z[l - 1], l > 0, gcur, Wl,
+                                               cfg.weight_decay[l], nullptr, grads + w_offset(d, l),
+                                               grads + b_offset(d, l), loss_terms);
+        MB_CUDA_LAUNCH_CHECK("k_train_gemm<DW>");
+        if (l > 0) {
+            dim3 gx((unsigned)((K + kGT - 1) / kGT), (unsigned)((B + kGT - 1) / kGT), (unsigned)ne);
+            k_train_gemm<true><<<gx, 256, 0, s>>>(e0, B, K, N, nullptr, 0, gcur, Wl, 0.f, w.z[l - 1], gnext,
+                                                  nullptr, nullptr);
+            MB_CUDA_LAUNCH_CHECK("k_train_gemm<DX>");
+            float* t = gcur; gcur = gnext; gnext = t;
+        }
+    }
+    if (params != nullptr) {
+        AdamSegs segs;
+        segs.n = 0;
+        int64_t maxlen = 0;
+        for (int l = 0; l < L; ++l) {
+            const int64_t wn = (int64_t)d.sizes[l] * d.sizes[l + 1], bn = d.sizes[l + 1];
+            segs.off[segs.n] = w_offset(d, l) + e0 * wn; segs.len[segs.n++] = ne * wn;
+            segs.off[segs.n] = b_offset(d, l) + e0 * bn; segs.len[segs.n++] = ne * bn;
+            maxlen = wn * ne > maxlen ? wn * ne : maxlen;
+        }
+        segs.off[segs.n] = logstd_offset(d, 0) + (int64_t)e0 * D; segs.len[segs.n++] = (int64_t)ne * D;
+        segs.off[segs.n] = logstd_offset(d, 1) + (int64_t)e0 * D; segs.len[segs.n++] = (int64_t)ne * D;
+        const double bc1 = 1.0 - pow((double)cfg.beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)cfg.beta2, (double)step);
+        const int64_t nb = (maxlen + 255) / 256;
+        dim3 ga((unsigned)(nb < 1184 ? nb : 1184), (unsigned)segs.n);
+        k_adam<<<ga, 256, 0, s>>>(segs, params, exp_avg, exp_avg_sq, grads, cfg.beta1, cfg.beta2, cfg.eps,
+                                  (float)(cfg.lr / bc1), (float)sqrt(bc2));
+        MB_CUDA_LAUNCH_CHECK("k_adam");
+    }
+    (void)E;
+    return MB_OK;
+}
+
+}  // namespace mb

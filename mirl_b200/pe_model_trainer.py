@@ -1,0 +1,299 @@
+"""B200PEModelTrainer -- drop-in for ``PEModelTrainer``
+(mirl/agents/mbpo/pe_model_trainer.py:18-306).
+
+``train_from_torch_batch`` is ONE call into the fused CUDA training step (forward + Gaussian
+NLL + log-std bound + L2 + backward + Adam, ``mb_pe_train_step``) instead of ~4 500 ATen ops
+(SURVEY.md 2.1).  ``sufficiently_train`` keeps the reference's control flow (bootstrap indices,
+periodic hold-out evaluation, per-member early stopping, best-snapshot restore, elite ranking)
+and its NumPy RNG consumption order, but keeps the dataset, the bootstrap index table and the
+per-member "best" snapshots in device memory instead of NumPy fancy-indexing + H2D every step
+(:268-270) and ``torch.save`` per improved member (:249,256).
+
+Member-sharded training (``members=(e0, e1)``): members are independent (pe_model.py:95-96), so
+each rank trains its slice with no collective in the step; ``mirl_b200.dist.all_gather_members``
+exchanges the trained slices afterwards.
+"""
+import ctypes
+import os
+import os.path as osp
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .compat import Component, logger, snapshot_dir
+
+
+def split_dataset(dataset, valid_ratio, max_valid=5000):
+    """mirl/pools/utils.py:60-79 (same ``np.random.permutation`` consumption)."""
+    n_sample = len(next(iter(dataset.values())))
+    valid_length = int(np.ceil(min(max_valid, valid_ratio * n_sample)))
+    train_length = n_sample - valid_length
+    indices = np.random.permutation(n_sample)
+    train_indices, valid_indices = indices[:train_length], indices[-valid_length:]
+    train = {k: v[train_indices] for k, v in dataset.items()}
+    valid = {k: v[valid_indices] for k, v in dataset.items()}
+    return train, valid, train_length, valid_length
+
+
+_FIELDS = ("observations", "actions", "deltas", "rewards", "terminals")
+
+
+class B200PEModelTrainer(Component):
+    def __init__(self, env, model, lr=1e-3, max_step_per_train=4000, init_model_train_step=int(5e4),
+                 load_best=True, valid_ratio=0.2, max_valid=2000, resample=True, batch_size=256,
+                 report_freq=100, max_not_improve=20, silent=False, load_dataset_dir=None,
+                 tb_log_freq=100, optimizer_class="Adam", optimizer_kwargs={}, load_dir=None,
+                 save_dir=None, ignore_terminal_state=False, members=None, snapshot_to_disk=False):
+        if optimizer_class not in ("Adam", torch.optim.Adam):
+            raise NotImplementedError("the fused training step implements torch.optim.Adam only")
+        extra = set(optimizer_kwargs) - {"betas", "eps"}
+        if extra or optimizer_kwargs.get("weight_decay", 0) or optimizer_kwargs.get("amsgrad", False):
+            raise NotImplementedError("Adam options %s" % sorted(extra))
+        self.env = env
+        self.model = model
+        self.lr = lr
+        self.optimizer_kwargs = dict(optimizer_kwargs)
+        self.betas = tuple(optimizer_kwargs.get("betas", (0.9, 0.999)))
+        self.eps = optimizer_kwargs.get("eps", 1e-8)
+        flat = model.module.flat
+        self.exp_avg = torch.zeros_like(flat.data)
+        self.exp_avg_sq = torch.zeros_like(flat.data)
+        self.statistics = OrderedDict()
+        self.learn_reward, self.learn_done = model.learn_reward, model.learn_done
+        self.num_train_steps = 0
+        self.max_step_per_train = max_step_per_train
+        self.init_model_train_step = int(init_model_train_step)
+        self.load_best = load_best
+        self.tb_log_freq = tb_log_freq
+        self.ignore_terminal_state = ignore_terminal_state
+        self.valid_ratio, self.max_valid, self.resample = valid_ratio, max_valid, resample
+        self.batch_size, self.report_freq = batch_size, report_freq
+        self.max_not_improve, self.silent = max_not_improve, silent
+        self.load_dataset_dir = load_dataset_dir
+        self.load_dir = osp.expanduser(load_dir) if load_dir is not None else None
+        self.save_dir = osp.expanduser(save_dir) if save_dir is not None else None
+        self.members = tuple(members) if members is not None else (0, model.ensemble_size)
+        self.snapshot_to_disk = snapshot_to_disk
+        self._ws = None
+        self._loss_terms = None
+        self._ensemble_loss = None
+        self._best = None
+
+    # ---- fused step ------------------------------------------------------------------------------
+    def _state_to(self, dev):
+        if self.exp_avg.device != dev:
+            self.exp_avg, self.exp_avg_sq = self.exp_avg.to(dev), self.exp_avg_sq.to(dev)
+        if self._ensemble_loss is None or self._ensemble_loss.device != dev:
+            self._ensemble_loss = torch.zeros(self.model.ensemble_size, device=dev)
+            self._loss_terms = torch.zeros(3, device=dev)
+
+    def train_step_async(self, batch):
+        """Enqueue one fused training step; returns device tensors
+        ``(ensemble_loss [E], loss_terms [3] = sum_e loss_e, l2, bound)`` without synchronising
+        (the reference syncs twice per step, pe_model_trainer.py:101-104)."""
+        model, L = self.model, _lib.lib()
+        dev = model.device
+        self._state_to(dev)
+        t = {k: _lib.f32(batch[k], dev) for k in _FIELDS}
+        o = t["observations"]
+        assert o.dim() == 3 and o.shape[0] == model.ensemble_size, \
+            "training batches are per-member [E,B,.] (pe_model_trainer.py:268-270)"
+        B = o.shape[1]
+        m = model._c_model(None)
+        cfg = model.train_cfg(self.ignore_terminal_state, self.lr, self.betas, self.eps)
+        need = L.mb_pe_train_workspace_bytes(ctypes.byref(m), B)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self.num_train_steps += 1
+        e0, e1 = self.members
+        _lib.check(L.mb_pe_train_step(
+            ctypes.byref(m), ctypes.byref(cfg), _lib.ptr(model.module.flat.data),
+            _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.num_train_steps,
+            _lib.ptr(o), _lib.ptr(t["actions"]), _lib.ptr(t["deltas"]), _lib.ptr(t["rewards"]),
+            _lib.ptr(t["terminals"]), B, e0, e1, _lib.ptr(self._ensemble_loss),
+            _lib.ptr(self._loss_terms), _lib.ptr(self._ws), self._ws.numel(), _lib.stream()))
+        model.module.mark_weights_changed()
+        return self._ensemble_loss, self._loss_terms
+
+    def train_from_torch_batch(self, batch):
+        """pe_model_trainer.py:85-106 (same diagnostics keys; synchronises like the reference)."""
+        ensemble_loss, terms = self.train_step_async(batch)
+        return self._train_diagnostics(ensemble_loss, terms)
+
+    def _train_diagnostics(self, ensemble_loss, terms):
+        el = ensemble_loss.cpu().numpy()
+        diagnostics = OrderedDict()
+        e0, e1 = self.members
+        for i in range(e0, e1):
+            diagnostics["mt/net_%d/train_loss" % i] = el[i]
+        diagnostics["train_loss"] = float(terms.sum().item())
+        return diagnostics
+
+    def eval_with_dataset(self, dataset):
+        """pe_model_trainer.py:108-121: whole hold-out set, shared by all members."""
+        dev = self.model.device
+        d = {k: (v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v), device=dev).float())
+             for k, v in dataset.items() if k in _FIELDS}
+        loss, ensemble_loss = self.model.compute_loss(d["observations"], d["actions"], d["deltas"],
+                                                      d["rewards"], d["terminals"])
+        el = ensemble_loss.cpu().numpy()
+        diagnostics = OrderedDict()
+        for i, l in enumerate(el):
+            diagnostics["mt/net_%d/eval_loss" % i] = l
+        diagnostics["eval_loss"] = loss.item()
+        return diagnostics, list(el)
+
+    # ---- dataset handling ------------------------------------------------------------------------
+    def set_mean_std(self, mean_std_dict=None):
+        """pe_model_trainer.py:123-136."""
+        model = self.model
+        if mean_std_dict is None:
+            mean_std_dict = self.mean_std_dict
+        else:
+            self.mean_std_dict = mean_std_dict
+        model.obs_processor.set_mean_std_np(*mean_std_dict["observations"])
+        model.action_processor.set_mean_std_np(*mean_std_dict["actions"])
+        model.delta_processor.set_mean_std_np(*mean_std_dict["deltas"])
+
+    def train_with_pool(self, pool):
+        """pe_model_trainer.py:138-170."""
+        max_step = self.max_step_per_train
+        temp = pool.get_unprocessed_data("compute_delta", ["observations", "next_observations"])
+        deltas = temp["next_observations"] - temp["observations"]
+        pool.update_single_extra_field("deltas", deltas)
+        pool.update_process_flag("compute_delta", len(deltas))
+        self.set_mean_std(pool.get_mean_std())
+        max_step = self.init_model_train_step if self.num_train_steps == 0 else int(max_step)
+        if self.load_dir is not None:
+            if not self.model.load(self.load_dir) and logger is not None:
+                logger.log("Can not load a model from %s" % self.load_dir)
+        results = self.sufficiently_train(
+            pool, max_step, valid_ratio=self.valid_ratio, max_valid=self.max_valid,
+            resample=self.resample, batch_size=self.batch_size, report_freq=self.report_freq,
+            max_not_improve=self.max_not_improve, load_best=self.load_best, silent=self.silent,
+            load_dataset_dir=self.load_dataset_dir)
+        if self.save_dir is not None:
+            os.makedirs(self.save_dir, exist_ok=True)
+            self.model.save(self.save_dir)
+        return results
+
+    def split_dataset(self, pool, valid_ratio, max_valid, resample):
+        """pe_model_trainer.py:172-182 (permutation, then the bootstrap index table)."""
+        E = self.model.ensemble_size
+        dataset = pool.get_data()
+        (self.train_dataset, self.eval_dataset,
+         self.train_length, self.eval_length) = split_dataset(dataset, valid_ratio, max_valid)
+        if resample:
+            self.ensemble_index = np.random.randint(self.train_length, size=(E, self.train_length))
+        else:
+            self.ensemble_index = np.tile(np.arange(self.train_length)[None], (E, 1))
+
+    def save_dataset(self, save_dir=None):
+        save_dic = {k: getattr(self, k) for k in ("train_dataset", "eval_dataset", "train_length",
+                                                  "eval_length", "ensemble_index", "mean_std_dict")}
+        np.save(osp.join(save_dir or snapshot_dir(), "pe_model_dataset.npy"), save_dic,
+                allow_pickle=True)
+
+    def load_dataset(self, load_dir=None):
+        path = osp.join(load_dir or snapshot_dir(), "pe_model_dataset.npy")
+        self.__dict__.update(np.load(path, allow_pickle=True).item())
+
+    # ---- device-resident early-stopping snapshots -------------------------------------------------
+    def _snapshot_member(self, i):
+        mod = self.model.module
+        if self.snapshot_to_disk:
+            self.model.save(net_id=i)
+        if self._best is None or self._best.shape != mod.flat.shape or self._best.device != mod.flat.device:
+            self._best = mod.flat.data.clone()
+        for a, b in mod.member_slices(i, i + 1):
+            self._best[a:b].copy_(mod.flat.data[a:b])
+
+    def _restore_member(self, i):
+        """``model.load(net_id=i)`` (pe_model_trainer.py:282-284).  Like the reference's
+        substring match 'net{i}' over state-dict keys, the log-std bounds are restored too."""
+        mod = self.model.module
+        for a, b in mod.member_slices(i, i + 1):
+            mod.flat.data[a:b].copy_(self._best[a:b])
+        mod.mark_weights_changed()
+
+    def sufficiently_train(self, pool=None, max_step=2000, valid_ratio=0.2, max_valid=5000,
+                           resample=True, batch_size=256, report_freq=100, max_not_improve=20,
+                           load_best=True, silent=False, load_dataset_dir=None):
+        """pe_model_trainer.py:212-293."""
+        model = self.model
+        dev = model.device
+        if pool is not None:
+            self.split_dataset(pool, valid_ratio, max_valid, resample)
+        else:
+            assert load_dataset_dir is not None
+            self.load_dataset(load_dataset_dir)
+            self.set_mean_std()
+        train = {k: torch.as_tensor(np.asarray(v), device=dev).float()
+                 for k, v in self.train_dataset.items() if k in _FIELDS}
+        evald = {k: torch.as_tensor(np.asarray(v), device=dev).float()
+                 for k, v in self.eval_dataset.items() if k in _FIELDS}
+        index = torch.as_tensor(self.ensemble_index, device=dev)
+        train_length = self.train_length
+        e0, e1 = self.members
+        total_train_step = 0
+        eval_stat, eval_loss, last = OrderedDict(), None, None
+        continue_training = True
+        while True:
+            for j in range(0, train_length, batch_size):
+                if total_train_step % report_freq == 0:
+                    eval_stat, eval_loss = self.eval_with_dataset(evald)
+                    if total_train_step == 0:
+                        min_loss = eval_loss
+                        not_improve = []
+                        for i, _ in enumerate(eval_loss):
+                            self._snapshot_member(i)
+                            not_improve.append(0)
+                    else:
+                        for i, l in enumerate(eval_loss):
+                            if l < min_loss[i]:
+                                min_loss[i] = l
+                                not_improve[i] = 0
+                                self._snapshot_member(i)
+                            else:
+                                not_improve[i] += 1
+                    continue_training = False
+                    for i, n in enumerate(not_improve):
+                        eval_stat["mt/net_%d/not_improve" % i] = n
+                        if e0 <= i < e1 and (max_not_improve < 0 or n < max_not_improve):
+                            continue_training = True
+                if total_train_step >= max_step:
+                    continue_training = False
+                if not continue_training:
+                    break
+                ind = index[:, j:j + batch_size]
+                batch = {k: v[ind] for k, v in train.items()}
+                last = self.train_step_async(batch)
+                total_train_step += 1
+            if not continue_training:
+                break
+        if load_best:
+            for i in range(e0, e1):
+                self._restore_member(i)
+        eval_stat, eval_loss = self.eval_with_dataset(evald)
+        model.remember_loss(eval_loss)
+        if last is not None:
+            self.statistics.update(self._train_diagnostics(*last))
+        self.statistics.update(eval_stat)
+        self.statistics["train_step"] = total_train_step
+        self.min_loss = eval_loss
+        return self.statistics
+
+    def get_diagnostics(self):
+        return self.statistics
+
+    def end_epoch(self, epoch):
+        pass
+
+    @property
+    def networks(self):
+        return [self.model]
+
+    def get_snapshot(self):
+        return dict(model=self.model)

@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed reference fixtures
+and the CPU oracle on the same seeded inputs.  Tolerance of record: tests/util.py RTOL = 1e-3
+(|err| <= 1e-3*|ref| + 1e-3*mean|ref|); done masks and member indices bit-exact (done flips are
+tolerated only inside a 1e-3 guard band around a threshold and are counted)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import critic_oracle as co
+from oracle import pe_oracle as po
+from tests.golden import cases
+from tests.helpers_gpu import done_guard_mismatches, make_critic, make_pe_model
+from tests.util import T, assert_close, golden, norm_rel, proj, to_torch
+
+pytestmark = pytest.mark.gpu
+LOSS_VEC7 = [0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4]
+LOSS_VEC10 = [0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4, 0.05, 0.8, 0.6]
+KERNELS = ["simt", "tcgen05"]
+
+
+def _kernel_or_skip(m, kernel):
+    if kernel == "tcgen05" and not m._tc_supported():
+        pytest.skip("tcgen05 kernel not built for this shape")
+
+
+def test_forward_matches_reference_fixture():
+    g = golden("pe_forward_mbpo.npz")
+    m, _ = make_pe_model(cases.MBPO, 11)
+    o, a = cases.rollout_inputs(12, 200)
+    mean, ls = m.predict_distribution(T(o, "cuda"), T(a, "cuda"))
+    assert_close(mean, g["mean"], what="mean")
+    assert_close(ls, g["logstd"], what="logstd")
+    # SIMT fp32 is the same arithmetic class as the reference: report the margin too
+    assert norm_rel(mean, g["mean64"]) < 1e-5
+
+
+def test_forward_per_member_inputs_match_oracle():
+    m, p = make_pe_model(cases.MBPO, 11)
+    bt = cases.train_batch(41, 7, 129)
+    pt = to_torch(p)
+    x = torch.cat([po.normalize(T(bt["observations"]), pt["obs_mean"], pt["obs_std"]),
+                   po.normalize(T(bt["actions"]), pt["act_mean"], pt["act_std"])], -1)
+    ref_mean, ref_ls = po.mean_logstd(po.mlp_forward(pt["W"], pt["b"], x), pt["max_logstd"], pt["min_logstd"])
+    mean, ls = m.predict_distribution(T(bt["observations"], "cuda"), T(bt["actions"], "cuda"))
+    assert_close(mean, ref_mean, what="mean")
+    assert_close(ls, ref_ls, what="logstd")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("env", po.DONE_KINDS)
+def test_rollout_step_matches_reference_fixture(env, kernel):
+    g = golden("pe_step_%s.npz" % env)
+    seed = 21 + po.DONE_KINDS.index(env)
+    m, _ = make_pe_model(cases.MBPO, 11, env, kernel=kernel)
+    _kernel_or_skip(m, kernel)
+    m.remember_loss(LOSS_VEC7)
+    assert list(m.elite_indices) == list(g["elite_indices"])
+    o, a = cases.rollout_inputs(seed, 1000, env=env)
+    # replay of the reference's RNG consumption: same seeds -> same member indices
+    np.random.seed(seed)
+    idx = np.random.choice(m.elite_indices, 1000)
+    assert np.array_equal(idx, g["idx"])
+    no, r, d, info = m.step(T(o, "cuda"), T(a, "cuda"), indices=idx, noise=T(g["eps"], "cuda"))
+    assert info == {}
+    assert_close(no, g["next_obs"], what="next_obs")
+    assert_close(r, g["reward"], what="reward")
+    outside, inside = done_guard_mismatches(env, g["next_obs"], g["done"], d.cpu().numpy())
+    assert outside == 0, "%d done flags differ outside the guard band (%d inside)" % (outside, inside)
+    assert inside <= 2
+    if env == "cheetah":
+        assert float(d.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_rollout_step_without_elites_draws_like_reference(kernel):
+    g = golden("pe_step_noelite.npz")
+    m, _ = make_pe_model(cases.MBPO, 11, kernel=kernel)
+    _kernel_or_skip(m, kernel)
+    o, a = cases.rollout_inputs(27, 64)
+    np.random.seed(27)                      # step() draws np.random.choice(arange(E), B) itself
+    no, r, d, _ = m.step(T(o, "cuda"), T(a, "cuda"), noise=T(g["eps"], "cuda"))
+    assert_close(no, g["next_obs"], what="next_obs")
+    assert_close(r, g["reward"], what="reward")
+
+
+def test_return_distribution_and_mopo_penalty():
+    g = golden("pe_step_dist_mopo.npz")
+    m, _ = make_pe_model(cases.MOPO, 31, "hopper")
+    m.remember_loss(LOSS_VEC10)
+    assert list(m.elite_indices) == list(g["elite_indices"])
+    o, a = cases.rollout_inputs(32, 128, env="hopper")
+    for kind in ("total_var", "max_var"):
+        no, r, d, info = m.step(T(o, "cuda"), T(a, "cuda"), return_distribution=True, indices=g["idx"],
+                                noise=T(g["eps"], "cuda"), penalty_type=kind)
+        for k in ("ensemble_delta_mean", "ensemble_delta_std", "ensemble_next_obs_mean",
+                  "ensemble_next_obs_std", "ensemble_reward_mean", "ensemble_reward_std"):
+            assert_close(info[k], g[k], what=k)
+        assert_close(no, g["next_obs"], what="next_obs")
+        assert_close(r, g["reward"], what="reward")
+        assert_close(info["penalized_reward"], g["penalized_reward_" + kind], what="penalized " + kind)
+        outside, _ = done_guard_mismatches("hopper", g["next_obs"], g["done"], d.cpu().numpy())
+        assert outside == 0
+    assert list(info.keys())[:6] == ["ensemble_delta_mean", "ensemble_next_obs_mean", "ensemble_delta_std",
+                                     "ensemble_next_obs_std", "ensemble_reward_mean", "ensemble_reward_std"]
+
+
+def _batch(seed, E, B, shared=False, device="cuda"):
+    return {k: T(v, device) for k, v in cases.train_batch(seed, E, B, shared=shared).items()}
+
+
+def test_compute_loss_matches_reference_fixture():
+    g = golden("pe_loss_mbpo.npz")
+    m, _ = make_pe_model(cases.MBPO, 11)
+    bt = _batch(41, 7, 256)
+    for tag, ignore in (("keep", False), ("ignore", True)):
+        loss, el = m.compute_loss(bt["observations"], bt["actions"], bt["deltas"], bt["rewards"],
+                                  bt["terminals"], ignore)
+        assert_close(loss, g["loss_" + tag], what="loss " + tag)
+        assert_close(el, g["ensemble_loss_" + tag], what="ensemble_loss " + tag)
+    bs = _batch(42, 7, 500, shared=True)
+    loss, el = m.compute_loss(bs["observations"], bs["actions"], bs["deltas"], bs["rewards"], bs["terminals"])
+    assert_close(el, g["ensemble_loss_shared"], what="shared ensemble_loss")
+    assert_close(loss, g["loss_shared"], what="shared loss")
+
+
+def _grads(m, bt, ignore):
+    from mirl_b200 import _lib
+    L = _lib.lib()
+    cm = m._c_model(None)
+    cfg = m.train_cfg(ignore)
+    B = bt["observations"].shape[1]
+    ws = torch.empty(L.mb_pe_train_workspace_bytes(ctypes.byref(cm), B), dtype=torch.uint8, device="cuda")
+    grads = torch.zeros_like(m.module.flat.data)
+    el = torch.zeros(m.ensemble_size, device="cuda")
+    terms = torch.zeros(3, device="cuda")
+    _lib.check(L.mb_pe_loss_grads(ctypes.byref(cm), ctypes.byref(cfg), _lib.ptr(bt["observations"]),
+                                  _lib.ptr(bt["actions"]), _lib.ptr(bt["deltas"]), _lib.ptr(bt["rewards"]),
+                                  _lib.ptr(bt["terminals"]), B, _lib.ptr(grads), _lib.ptr(el), _lib.ptr(terms),
+                                  _lib.ptr(ws), ws.numel(), _lib.stream()))
+    torch.cuda.synchronize()
+    return grads, el, terms
+
+
+def test_gradients_match_reference_autograd():
+    g = golden("pe_loss_small.npz")
+    m, _ = make_pe_model(cases.SMALL, 51)
+    grads, el, terms = _grads(m, _batch(52, 3, 64), False)
+    assert_close(terms.sum(), g["loss"], what="loss")
+    ref_sd = m.module.reference_state_dict("module.", flat=grads)
+    for k in g.files:
+        if k.startswith("grad/"):
+            assert norm_rel(ref_sd[k[5:]], g[k]) < 1e-3, k
+    g = golden("pe_loss_mbpo.npz")
+    m, _ = make_pe_model(cases.MBPO, 11)
+    for tag, ignore in (("keep", False), ("ignore", True)):
+        grads, el, terms = _grads(m, _batch(41, 7, 256), ignore)
+        assert_close(el, g["ensemble_loss_" + tag], what="ensemble_loss")
+        assert_close(terms.sum(), g["loss_" + tag], what="loss")
+        sd = m.module.reference_state_dict("module.", flat=grads)
+        for i, name in enumerate(g["names"]):
+            got, ref = proj(sd[str(name)], 1000 + i), g["grad_proj_" + tag][i]
+            assert abs(got[0] - ref[0]) <= 1e-3 * ref[0] + 1e-9, (name, got, ref)     # norm
+            assert abs(got[1] - ref[1]) <= 1e-3 * ref[0] + 1e-9, (name, got, ref)     # projection
+
+
+@pytest.mark.parametrize("tag,cfg,seed,B", [("small", cases.SMALL, 51, 64), ("mbpo", cases.MBPO, 11, 256)])
+def test_fused_train_steps_match_reference_adam(tag, cfg, seed, B):
+    import mirl_b200
+    from tests.helpers_gpu import FakeEnv
+    g = golden("pe_train_%s.npz" % tag)
+    m, _ = make_pe_model(cfg, seed)
+    tr = mirl_b200.B200PEModelTrainer(FakeEnv(), m, lr=1e-3, tb_log_freq=-1, silent=True,
+                                      ignore_terminal_state=False)
+    for s in range(10):
+        diag = tr.train_from_torch_batch(_batch(600 + s, cfg["E"], B))
+        assert_close(np.array(diag["train_loss"]), g["loss"][s], what="loss step %d" % s)
+        el = np.array([diag["mt/net_%d/train_loss" % i] for i in range(cfg["E"])])
+        assert_close(el, g["ensemble_loss"][s], what="ensemble_loss step %d" % s)
+        if s + 1 in (1, 10):
+            sd = m.state_dict()
+            msd = m.module.reference_state_dict("module.", flat=tr.exp_avg)
+            vsd = m.module.reference_state_dict("module.", flat=tr.exp_avg_sq)
+            for i, name in enumerate(g["names"]):
+                name = str(name)
+                got, ref = proj(sd[name], 2000 + i), g["param_proj_%d" % (s + 1)][i]
+                # Adam's early steps are sign-like: absolute tolerance ~ lr * sqrt(numel)
+                tol = 1e-3 * (s + 1) * 0.05 * np.sqrt(sd[name].numel()) + 1e-4 * ref[0]
+                assert abs(got[0] - ref[0]) <= tol, (name, got, ref)
+                gm, rm = proj(msd[name], 3000 + i), g["m_proj_%d" % (s + 1)][i]
+                assert abs(gm[0] - rm[0]) <= 2e-3 * rm[0] + 1e-9, ("exp_avg", name, gm, rm)
+                gv, rv = proj(vsd[name], 4000 + i), g["v_proj_%d" % (s + 1)][i]
+                assert abs(gv[0] - rv[0]) <= 4e-3 * rv[0] + 1e-12, ("exp_avg_sq", name, gv, rv)
+            if tag == "small":
+                for k in g.files:
+                    if k.startswith("param_%d/" % (s + 1)):
+                        err = np.abs(sd[k.split("/", 1)[1]].cpu().numpy() - g[k]).max()
+                        assert err < 5e-4, (k, err)
+
+
+def test_redq_target_matches_reference_fixture():
+    g = golden("redq.npz")
+    q, _ = make_critic("redq", 71)
+    x = cases.critic_inputs(72, 256)
+    o, a = T(x["obs"], "cuda"), T(x["act"], "cuda")
+    _, info = q.value(o, a, only_return_ensemble=True)
+    assert_close(info["ensemble_value"], g["ensemble"], what="ensemble")
+    np.random.seed(73)
+    v, _ = q.value(o, a, sample_number=2, batchwise_sample=True, mode="min")
+    assert_close(v, g["bw_min"], what="batch-wise min")
+    np.random.seed(74)
+    v, _ = q.value(o, a, sample_number=2, batchwise_sample=False, mode="min")
+    assert_close(v, g["row_min"], what="per-row min")
+    np.random.seed(75)
+    v, _ = q.value(o, a, sample_number=3, batchwise_sample=False, mode="max")
+    assert_close(v, g["row3_max"], what="per-row max")
+    assert_close(q.value(o, a, sample_number=None, mode="mean")[0], g["all_mean"], what="mean")
+    assert_close(q.value(o, a, sample_number=10, mode="min")[0], g["all_min"], what="min")
+    np.random.seed(73)
+    y = q.q_target(o, a, T(x["rewards"], "cuda"), T(x["terminals"], "cuda"), T(x["log_prob"], "cuda"),
+                   alpha=0.2, discount=0.99, sample_number=2, batchwise_sample=True)
+    assert_close(y, g["td_target"], what="td target")
+
+
+def test_tqc_target_matches_reference_fixture():
+    g = golden("tqc.npz")
+    q, _ = make_critic("tqc", 81)
+    x = cases.critic_inputs(82, 256)
+    o, a = T(x["obs"], "cuda"), T(x["act"], "cuda")
+    _, info = q.value(o, a, only_return_ensemble=True)
+    assert_close(info["ensemble_atoms"], g["ensemble"], what="ensemble atoms")
+    v, info = q.value(o, a, percentage_drop=8, return_atoms=True)
+    assert info["value_atoms"].shape == (256, 115)
+    assert_close(info["value_atoms"], g["atoms_drop8pct"], what="kept atoms")
+    assert_close(v, g["value_drop8pct"], what="value")
+    at = info["value_atoms"]
+    assert bool((at[:, 1:] >= at[:, :-1]).all())                 # ascending
+    v, info = q.value(o, a, number_drop=0, return_atoms=True)
+    assert_close(info["value_atoms"], g["atoms_drop0"], what="atoms drop 0")
+    y = q.atoms_target(o, a, T(x["rewards"], "cuda"), T(x["terminals"], "cuda"), T(x["log_prob"], "cuda"),
+                       alpha=0.2, discount=0.99, percentage_drop=8)
+    assert_close(y, g["atoms_target"], what="atoms target")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("B", [1, 63, 64, 65, 127, 128, 129, 257, 4099])
+def test_rollout_ragged_batches_match_oracle(B, kernel):
+    m, p = make_pe_model(cases.MBPO, 11, "hopper", kernel=kernel)
+    _kernel_or_skip(m, kernel)
+    m.remember_loss(LOSS_VEC7)
+    o, a = cases.rollout_inputs(100 + B, B, env="hopper")
+    rs = np.random.RandomState(B)
+    idx = rs.choice(m.elite_indices, B)
+    eps = rs.standard_normal((B, 18)).astype(np.float32)
+    no, r, d, _ = m.step(T(o, "cuda"), T(a, "cuda"), indices=idx, noise=T(eps, "cuda"))
+    rno, rr, rd = po.rollout_step(to_torch(p), T(o), T(a), torch.from_numpy(idx), T(eps), "hopper")
+    assert_close(no, rno, what="next_obs")
+    assert_close(r, rr, what="reward")
+    outside, _ = done_guard_mismatches("hopper", rno.numpy(), rd.numpy(), d.cpu().numpy())
+    assert outside == 0
+
+
+def test_rollout_empty_batch():
+    m, _ = make_pe_model(cases.MBPO, 11)
+    no, r, d, _ = m.step(torch.zeros(0, 17, device="cuda"), torch.zeros(0, 6, device="cuda"))
+    assert no.shape == (0, 17) and r.shape == (0, 1) and d.shape == (0, 1)
+
+
+@pytest.mark.parametrize("E,elites", [(2, 2), (5, 3), (10, 7), (20, 15)])
+def test_ensemble_sizes_match_oracle(E, elites):
+    cfg = dict(E=E, elites=elites, hidden=[200, 200, 200, 200], act="swish")
+    m, p = make_pe_model(cfg, 200 + E, kernel="simt")
+    m.remember_loss(list(np.random.RandomState(E).uniform(size=E)))
+    B = 300
+    o, a = cases.rollout_inputs(300 + E, B)
+    rs = np.random.RandomState(E)
+    idx = rs.choice(m.elite_indices, B)
+    eps = rs.standard_normal((B, 18)).astype(np.float32)
+    no, r, d, _ = m.step(T(o, "cuda"), T(a, "cuda"), indices=idx, noise=T(eps, "cuda"))
+    rno, rr, _ = po.rollout_step(to_torch(p), T(o), T(a), torch.from_numpy(idx), T(eps))
+    assert_close(no, rno, what="next_obs")
+    assert_close(r, rr, what="reward")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_full_size_properties(kernel):
+    """BASELINE.json full size (1e6 states): size-independent properties instead of an oracle
+    pass -- (a) rows are independent: a permuted batch gives the permuted result bit-for-bit;
+    (b) zero noise reproduces obs + recover(mean of the drawn member) from the all-member
+    forward kernel; (c) cheetah never terminates."""
+    m, _ = make_pe_model(cases.MBPO, 11, kernel=kernel)
+    _kernel_or_skip(m, kernel)
+    m.remember_loss(LOSS_VEC7)
+    B = 1_000_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    o = torch.randn(B, 17, device="cuda", generator=g)
+    a = torch.rand(B, 6, device="cuda", generator=g) * 2 - 1
+    eps = torch.randn(B, 18, device="cuda", generator=g)
+    idx = torch.from_numpy(np.random.RandomState(5).choice(m.elite_indices, B)).cuda()
+    no, r, d, _ = m.step(o, a, indices=idx, noise=eps)
+    perm = torch.randperm(B, device="cuda", generator=g)
+    no2, r2, d2, _ = m.step(o[perm], a[perm], indices=idx[perm], noise=eps[perm])
+    assert torch.equal(no[perm], no2) and torch.equal(r[perm], r2) and torch.equal(d[perm], d2)
+    assert float(d.sum()) == 0.0
+    n = 20000
+    no0, r0, _, _ = m.step(o[:n], a[:n], indices=idx[:n], noise=torch.zeros(n, 18, device="cuda"))
+    mean, _ = m.predict_distribution(o[:n], a[:n])
+    sel = mean[idx[:n].long(), torch.arange(n, device="cuda")]
+    ref = o[:n] + m.delta_processor.recover(sel[:, :17])
+    assert_close(no0, ref, what="zero-noise next_obs")
+    assert_close(r0, sel[:, 17:], what="zero-noise reward")
