@@ -185,6 +185,13 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
 size_t mb_pe_tc_pack_bytes(const mb_pe_model* m);
 int mb_pe_tc_pack(const mb_pe_model* m, void* pack, void* stream);
 
+/* ---- instrumentation for bench.py's roofline leg (not used on the product path) ---------------
+ * When enabled, mb_pe_rollout_step brackets its dominant kernel (the fused MLP kernel, not the
+ * bucketing pre-pass) with CUDA events on `stream`; mb_profile_last_ms waits for the end event
+ * and returns the elapsed milliseconds of the last bracketed launch. */
+int mb_profile_enable(int on);
+int mb_profile_last_ms(float* ms);
+
 #ifdef __cplusplus
 }
 #endif

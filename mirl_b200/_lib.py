@@ -69,6 +69,8 @@ SIGNATURES = {
                                      c_int, P, P, P, c_float, c_float, P, P, P]),
     "mb_pe_tc_pack_bytes": (c_size_t, [POINTER(PeModel)]),
     "mb_pe_tc_pack": (c_int, [POINTER(PeModel), P, P]),
+    "mb_profile_enable": (c_int, [c_int]),
+    "mb_profile_last_ms": (c_int, [POINTER(c_float)]),
 }
 
 _lib = None

@@ -48,6 +48,15 @@ int validate_model(const mb_pe_model* m, const char* who) {
     return MB_OK;
 }
 
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+void prof_begin(cudaStream_t s) {
+    if (g_prof_on) cudaEventRecord(g_prof_ev[0], s);
+}
+void prof_end(cudaStream_t s) {
+    if (g_prof_on) cudaEventRecord(g_prof_ev[1], s);
+}
+
 static PeDev to_dev(const mb_pe_model* m) {
     PeDev d;
     d.mlp = m->mlp;
@@ -267,6 +276,25 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
     MB_CHECK_ARG(!td || (reward && terminal && log_prob), "mb_critic_tqc_target: td needs reward/terminal/log_prob");
     return launch_critic_tqc(*d, params, obs, act, obs_dim, act_dim, B, n_drop, td, reward, terminal, log_prob,
                              alpha, discount, value, atoms, (cudaStream_t)stream);
+}
+
+int mb_profile_enable(int on) {
+    if (on && g_prof_ev[0] == nullptr) {
+        if (cudaEventCreate(&g_prof_ev[0]) != cudaSuccess || cudaEventCreate(&g_prof_ev[1]) != cudaSuccess) {
+            set_error("mb_profile_enable: cudaEventCreate failed");
+            return MB_ECUDA;
+        }
+    }
+    g_prof_on = on != 0;
+    return MB_OK;
+}
+
+int mb_profile_last_ms(float* ms) {
+    MB_CHECK_ARG(ms != nullptr && g_prof_ev[0] != nullptr, "mb_profile_last_ms: profiling was never enabled");
+    cudaError_t e = cudaEventSynchronize(g_prof_ev[1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms, g_prof_ev[0], g_prof_ev[1]);
+    if (e != cudaSuccess) { set_error("mb_profile_last_ms: %s", cudaGetErrorString(e)); return MB_ECUDA; }
+    return MB_OK;
 }
 
 size_t mb_pe_tc_pack_bytes(const mb_pe_model* m) { return m ? tc_pack_bytes(m->mlp) : 0; }

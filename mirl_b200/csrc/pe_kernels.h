@@ -25,6 +25,10 @@ struct BucketPlan {
 size_t bucket_workspace_bytes(int64_t B, int TM);
 BucketPlan bucket_rows(const uint8_t* idx, int64_t B, int E, int TM, void* ws, cudaStream_t s);
 
+// bench instrumentation (c_api.cu): events around the dominant rollout kernel when enabled
+void prof_begin(cudaStream_t s);
+void prof_end(cudaStream_t s);
+
 // ---- SIMT fp32 family (pe_simt.cu)
 int launch_pe_rollout_simt(const PeDev& m, const float* obs, const float* act, const uint8_t* idx,
                            const float* noise, int64_t B, int done_kind, float* next_obs,

@@ -409,8 +409,10 @@ int launch_pe_rollout_simt(const PeDev& m, const float* obs, const float* act, c
     int rc = set_smem(k_pe_rollout_simt, smem);
     if (rc) return rc;
     const int grid = (int)min((int64_t)p.max_tiles, (int64_t)sm_count() * 4);
+    prof_begin(s);
     k_pe_rollout_simt<<<grid, kSimtThreads, smem, s>>>(m, obs, act, noise, p.perm, p.tiles, p.ntiles,
                                                        done_kind, next_obs, reward, done);
+    prof_end(s);
     MB_CUDA_LAUNCH_CHECK("k_pe_rollout_simt");
     return MB_OK;
 }
