@@ -19,7 +19,8 @@ REDUCE = {"min": 0, "mean": 1, "max": 2}
 KERNEL = {"simt": 0, "tcgen05": 1}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmirl_b200.so")
+# MIRL_B200_LIB: alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("MIRL_B200_LIB") or os.path.join(_HERE, "libmirl_b200.so")
 
 
 class MlpDesc(Structure):

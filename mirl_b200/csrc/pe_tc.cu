@@ -20,13 +20,14 @@
 // the accumulator from TMEM (tcgen05.ld), apply swish, split to bf16 hi/lo and write the next
 // layer's A operand straight into shared memory in UMMA layout.
 //
-// Pipeline (704 threads, 1 CTA/SM, persistent over tiles):
+// Pipeline (576 threads, 1 CTA/SM, persistent over tiles):
 //   warps 0-3   head: last-layer epilogue (clamp, sample, de-normalise, done) of tile t while the
 //               other warps already run tile t+1
-//   warps 4-19  epilogue: warp w owns TMEM lanes 32*(w%4).. and the 16-column blocks ks = c (mod 4),
-//               c = (w-4)/4; class c == 3 (warps 16-19) additionally stages the next tile's inputs
-//   warp  20    weight producer (one elected lane)
-//   warp  21    MMA issuer (warp-uniform control flow, one elected lane issues) + TMEM allocation
+//   warps 4-15  epilogue, 3 classes x 4 TMEM lane quarters: warp w owns TMEM lanes 32*(w%4).. and the
+//               16-column blocks ks = c (mod 3), c = (w-4)/4; the last class (warps 12-15) additionally
+//               stages the next tile's inputs.  (2, 4 and 5 classes were measured slower.)
+//   warp  16    weight producer (one elected lane)
+//   warp  17    MMA issuer (warp-uniform control flow, one elected lane issues) + TMEM allocation
 // The epilogue of layer l publishes its output per 16-column block (= one k-step of layer l+1)
 // on a_ready[ks]; the MMA warp starts layer l+1 on block 0 while the epilogue is still working
 // on the later blocks, accumulating into the OTHER of two TMEM accumulators.
@@ -47,14 +48,18 @@ namespace mb {
 // warp may touch is warp%4; both the head group and the epilogue group start at a multiple of 4.
 constexpr int kTcHeadWarp0 = 0;        // warps 0-3
 constexpr int kTcEpiWarp0 = 4;         // warps 4-19
-constexpr int kTcEpiWarps = 16;        // 4 TMEM lane quarters x 4 column-block classes
-constexpr int kTcStageClass = 3;       // epilogue class that also stages the next tile's inputs
+#ifndef MB_TC_CLASSES
+#define MB_TC_CLASSES 3
+#endif
+constexpr int kTcClasses = MB_TC_CLASSES;   // column-block classes (warps per TMEM lane quarter)
+constexpr int kTcEpiWarps = 4 * kTcClasses;
+constexpr int kTcStageClass = kTcClasses - 1;   // epilogue class that also stages the next tile's inputs
 constexpr int kTcProdWarp = kTcEpiWarp0 + kTcEpiWarps;
 constexpr int kTcMmaWarp = kTcProdWarp + 1;
 constexpr int kTcThreads = (kTcMmaWarp + 1) * 32;
 constexpr int kTcTM = 128;            // rows per tile (UMMA M)
 constexpr int kTcMaxKs = 16;          // k-steps per layer supported (HP <= 256)
-constexpr int kTcMaxStages = 6;
+constexpr int kTcMaxStages = 3;       // ring slots (two k-steps each)
 constexpr int kTcSmemLimit = 227 * 1024;
 // x with x*sigmoid(x) == 1: the "ones" column of the next layer's A operand
 constexpr float kSwishOne = 1.2784645427610738f;
@@ -111,7 +116,7 @@ static TcShape tc_shape(const mb_mlp_desc& d) {
     if (s.HP > 256 || s.K0P > 32 || s.HP < 64 || d.sizes[s.L] / 2 > 32) return s;
     s.nks0 = s.K0P / 16;
     s.nksh = s.HP / 16;
-    s.slot = 64 * s.HP;
+    s.slot = 2 * 64 * s.HP;            // one ring slot = two k-steps
     s.const_off = tc_layer_off(s, s.L);
     s.member_bytes = s.const_off + 64 * 4;
     s.stages = kTcMaxStages;
@@ -346,7 +351,8 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     auto d_full = [&](int i) { return bar0 + 8u * (2 * kTcMaxStages + kTcMaxKs + i); };
     const uint32_t h_free = bar0 + 8u * (2 * kTcMaxStages + kTcMaxKs + 2);   // head has read its accumulator
     const uint32_t d_last = bar0 + 8u * (2 * kTcMaxStages + kTcMaxKs + 3);   // last-layer accumulator complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcMaxStages + kTcMaxKs + 4);
+    const uint32_t x_ready = bar0 + 8u * (2 * kTcMaxStages + kTcMaxKs + 4);  // layer-0 A operand staged
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcMaxStages + kTcMaxKs + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ long long tl[4][40];          // debug timeline (MB_TC_DEBUG & 8), CTA 0 only
@@ -359,7 +365,8 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < s.stages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
-        for (int i = 0; i < kTcMaxKs; ++i) mbar_init(a_ready(i), 4);
+        for (int i = 0; i < kTcMaxKs; ++i) mbar_init(a_ready(i), kTcEpiWarps);   // one arrival per warp per round
+        mbar_init(x_ready, 4);
         mbar_init(d_full(0), 1);
         mbar_init(d_full(1), 1);
         mbar_init(h_free, 4);
@@ -434,8 +441,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             if (warp == kTcEpiWarp0 + 4 * kTcStageClass) TL(ti_dbg, 39);
             if (!(dbg & 16)) fence_proxy_async();
             __syncwarp();
-            if (lane == 0)
-                for (int ks = 0; ks < s.nks0; ++ks) mbar_arrive(a_ready(ks));
+            if (lane == 0) mbar_arrive(x_ready);
         };
 
         int xrow_next = -1;
@@ -453,25 +459,36 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 const uint32_t dcol = tmem + lane_addr + (uint32_t)((g & 1) * 256);
                 uint32_t r0[16], r1[16];
                 // one 16-column block: wait for its TMEM load, prefetch the next one, then
-                // swish + bf16 hi/lo split -> next layer's A operand (k-step ks)
+                // swish + bf16 hi/lo split -> next layer's A operand (k-step ks).  Blocks are
+                // published per ROUND (the kTcClasses blocks ks = r*kTcClasses + c, one per class):
+                // every epilogue warp arrives on a_ready[r] exactly once per layer, with or
+                // without a block of its own in that round, so the MMA warp polls one barrier per
+                // round instead of one per k-step.
                 auto do_block = [&](int ks, uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
                     tc_wait_ld();
-                    if (ks + 4 < s.nksh) tc_ld16(dcol + (ks + 4) * 16, nxt);
+                    if (ks + kTcClasses < s.nksh) tc_ld16(dcol + (ks + kTcClasses) * 16, nxt);
                     float v[16];
 #pragma unroll
                     for (int t = 0; t < 16; ++t)
                         v[t] = (dbg & 4) ? __uint_as_float(cur[t]) : fast_swish(__uint_as_float(cur[t]));
                     split_store8(v, sA_hi + (2 * ks) * 2048u + row_off, sA_lo + (2 * ks) * 2048u + row_off);
                     split_store8(v + 8, sA_hi + (2 * ks + 1) * 2048u + row_off, sA_lo + (2 * ks + 1) * 2048u + row_off);
-                    if (!(dbg & 16)) fence_proxy_async();
+                    fence_proxy_async();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(a_ready(ks));
+                    if (lane == 0) mbar_arrive(a_ready(ks / kTcClasses));
                 };
                 if (c < s.nksh) tc_ld16(dcol + c * 16, r0);
-                for (int ks = c; ks < s.nksh; ks += 8) {
+                int ks = c;
+                for (; ks < s.nksh; ks += 2 * kTcClasses) {
                     do_block(ks, r0, r1);
-                    if (ks + 4 < s.nksh) do_block(ks + 4, r1, r0);
+                    if (ks + kTcClasses < s.nksh) do_block(ks + kTcClasses, r1, r0);
+                }
+                // rounds in which this class has no block (only the last one can be partial)
+                if (lane == 0) {
+                    const int rounds = (s.nksh + kTcClasses - 1) / kTcClasses;
+                    const int mine = (s.nksh - c + kTcClasses - 1) / kTcClasses;    // blocks this class processed
+                    for (int r = mine; r < rounds; ++r) mbar_arrive(a_ready(r));
                 }
                 if (warp == kTcEpiWarp0) TL(i, 17 + l * 2);
             }
@@ -502,47 +519,60 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 const uint32_t idesc = umma_idesc(NP);
                 const uint32_t d_tmem = tmem + (uint32_t)((g & 1) * 256);
                 const uint64_t b0 = umma_desc(sRing, (uint32_t)NP * 16u, 128u);
-                const uint32_t lo_off = (uint32_t)(32 * NP) >> 4;
+                const uint32_t lo_off = (uint32_t)(32 * NP) >> 4;       // hi block -> lo block of a k-step
+                const uint32_t ks_off = (uint32_t)(64 * NP) >> 4;       // k-step -> next k-step in a stage
                 // layer 1 of tile i reuses the accumulator the head of tile i-1 is reading
                 if (l == 1 && i >= 1) mbar_wait(h_free, (uint32_t)(i - 1) & 1u);
                 TL(i, l * 2);
-                long long t_a = 0, t_w = 0;
-                for (int ks = 0; ks < nks; ++ks) {
-                    long long c0 = 0, c1 = 0, c2 = 0;
-                    if (dbg & 8) c0 = clock64();
-                    {   // poll both barriers together so their try_wait latencies overlap
-                        const uint32_t ab = a_ready(ks), ap = (aphase >> ks) & 1u, wb = w_full(stage);
-                        bool ra = mbar_try_wait(ab, ap), rw = mbar_try_wait(wb, wphase);
-                        for (uint32_t spin = 0; !(ra && rw); ++spin) {
-                            if (!ra) ra = mbar_try_wait(ab, ap);
-                            if (!rw) rw = mbar_try_wait(wb, wphase);
-                            if (spin > (1u << 26)) mbar_timeout(ra ? wb : ab, ra ? wphase : ap);
+                // This loop is the pacing resource of the kernel (it shares its SM sub-partition's
+                // issue slots with five other warps; a poll of an already-complete mbarrier alone
+                // costs ~100 cycles), so it polls as rarely as possible: one weight stage carries
+                // TWO k-steps, the epilogue publishes per round of kTcClasses k-steps, layer 0 has
+                // one barrier for the whole staged input.  Polls are unbounded here (every other
+                // waiter is bounded and traps).
+                if (l == 0) {
+                    while (!mbar_try_wait(x_ready, (uint32_t)i & 1u)) {}
+                }
+                uint64_t a_hi = a_hi0, a_lo = a_lo0;
+                int rounds_seen = 0;                  // a_ready rounds of this layer already observed
+                for (int ks = 0; ks < nks; ks += 2) {
+                    if (l > 0) {                      // rounds covering k-steps ks and ks+1
+                        const int need = (ks + 1 < nks ? ks + 1 : ks) / kTcClasses;
+                        for (; rounds_seen <= need; ++rounds_seen) {
+                            while (!mbar_try_wait(a_ready(rounds_seen), (aphase >> rounds_seen) & 1u)) {}
+                            aphase ^= 1u << rounds_seen;
                         }
                     }
-                    if (dbg & 8) { c1 = clock64(); c2 = c1; t_a += c1 - c0; t_w += c2 - c1; }
-                    aphase ^= 1u << ks;
+                    while (!mbar_try_wait(w_full(stage), wphase)) {}
                     tc_fence_after();
-                    const uint64_t a_hi = a_hi0 + (uint64_t)(ks * 256);
-                    const uint64_t a_lo = a_lo0 + (uint64_t)(ks * 256);
                     const uint64_t b_hi = b0 + (uint64_t)((uint32_t)(stage * s.slot) >> 4);
                     const uint64_t b_lo = b_hi + lo_off;
+                    const bool two = ks + 1 < nks;
                     if (elect_one()) {
                         tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
                         if (!(dbg & 1)) {
                             tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
                             tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
                         }
+                        if (two) {                                  // second k-step of the stage
+                            tc_mma_bf16(d_tmem, a_hi + 256, b_hi + ks_off, idesc, 1u);
+                            if (!(dbg & 1)) {
+                                tc_mma_bf16(d_tmem, a_lo + 256, b_hi + ks_off, idesc, 1u);
+                                tc_mma_bf16(d_tmem, a_hi + 256, b_lo + ks_off, idesc, 1u);
+                            }
+                        }
                         tc_commit(w_empty(stage));
-                        if (ks == nks - 1) {
+                        if (ks + 2 >= nks) {
                             tc_commit(d_full(g & 1));
                             if (l == L - 1) tc_commit(d_last);
                         }
                     }
                     __syncwarp();
+                    a_hi += 512;
+                    a_lo += 512;
                     if (++stage == s.stages) { stage = 0; wphase ^= 1u; }
                 }
                 TL(i, l * 2 + 1);
-                if ((dbg & 8) && blockIdx.x == 0 && i < 4 && lane == 0 && l == 2) { tl[i][36] = t_a; tl[i][37] = t_w; }
             }
         }
     } else if (warp == kTcProdWarp) {
@@ -557,13 +587,14 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     const int nks = tc_layer_nks(s, l);
                     const uint32_t bytes = (uint32_t)tc_stage_bytes(s, l);
                     const uint8_t* lp = mp + tc_layer_off(s, l);
-                    for (int ks = 0; ks < nks; ++ks) {
+                    for (int ks = 0; ks < nks; ks += 2) {
+                        const uint32_t nb = ks + 1 < nks ? 2u * bytes : bytes;   // two k-steps per stage
                         mbar_wait_relaxed(w_empty(stage), wphase ^ 1u);
                         if (dbg & 2) {
                             mbar_arrive(w_full(stage));
                         } else {
-                            mbar_expect_tx(w_full(stage), bytes);
-                            bulk_g2s(sRing + (uint32_t)stage * s.slot, lp + (size_t)ks * bytes, bytes, w_full(stage));
+                            mbar_expect_tx(w_full(stage), nb);
+                            bulk_g2s(sRing + (uint32_t)stage * s.slot, lp + (size_t)ks * bytes, nb, w_full(stage));
                         }
                         if (++stage == s.stages) { stage = 0; wphase ^= 1u; }
                     }
@@ -653,7 +684,8 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             for (int l = 0; l + 1 < L; ++l) printf("L%d %lld %lld | ", l, tl[i][16 + 2 * l] - t0, tl[i][17 + 2 * l] - t0);
             printf("\n        HEAD(dlast,done) %lld %lld  STAGE(dfull,done) %lld %lld  L2 waits: a_ready %lld w_full %lld\n",
                    tl[i][24] - t0, tl[i][25] - t0, tl[i][33] - t0, tl[i][34] - t0, tl[i][36], tl[i][37]);
-            printf("        STAGE detail: cpwait %lld norm %lld stores %lld\n", tl[i][35] - t0, tl[i][38] - t0, tl[i][39] - t0);
+            printf("        MMA L2 ks=10: top %lld a_ready %lld w_full %lld issued %lld synced %lld\n",
+                   tl[i][26] - t0, tl[i][27] - t0, tl[i][28] - t0, tl[i][29] - t0, tl[i][30] - t0);
         }
     }
     if (warp == kTcMmaWarp) {
