@@ -131,12 +131,15 @@ int mb_pe_loss(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs,
  * NLL + log-std bound + L2, backward, Adam -- for the members [member_begin, member_end) only
  * (member-sharded training: each rank passes its own slice; the others are untouched).
  * params/exp_avg/exp_avg_sq: packed blobs (same layout), updated in place.
- * step = 1-based Adam step count AFTER this update.  Batch tensors are [E][B][.].
+ * step = 1-based Adam step count AFTER this update; if step_counter (device int32, optional) is
+ * given, the call increments it on the device and uses it instead (the launch sequence then has
+ * no host-side state, so it can be captured once in a CUDA graph and replayed every step).
+ * Batch tensors are [E][B][.].
  * ensemble_loss[E] (entries of this slice written), loss_terms[3] += {sum_e loss_e, l2, bound}
  * over this slice (zeroed by the call). */
 size_t mb_pe_train_workspace_bytes(const mb_pe_model* m, int64_t B);
 int mb_pe_train_step(const mb_pe_model* m, const mb_train_cfg* cfg, float* params,
-                     float* exp_avg, float* exp_avg_sq, int64_t step,
+                     float* exp_avg, float* exp_avg_sq, int64_t step, int32_t* step_counter,
                      const float* obs, const float* act, const float* delta,
                      const float* reward, const float* done, int64_t B,
                      int member_begin, int member_end,
@@ -152,9 +155,12 @@ int mb_pe_loss_grads(const mb_pe_model* m, const mb_train_cfg* cfg, const float*
 
 /* ---- (3) critic-ensemble targets ----------------------------------------------------------
  * Plain ensemble forward [E][B][out] (EnsembleQValue / TQCQValue `only_return_ensemble`). */
+/* workspace for the three critic entry points (intermediate activations of the per-layer path
+ * used at small batch); workspace may be NULL, which forces the single-launch tile kernels. */
+size_t mb_critic_workspace_bytes(const mb_mlp_desc* d, int64_t B);
 int mb_critic_forward(const mb_mlp_desc* d, const float* params, const float* obs,
                       const float* act, int obs_dim, int act_dim, int64_t B, float* out,
-                      void* stream);
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* EnsembleQValue.value (ensemble_value.py:65-107) with the subset reduced on the fly, fused with
  * SACAgent.compute_q_target (sac_agent.py:80-85) when td != 0:
@@ -168,7 +174,7 @@ int mb_critic_redq_target(const mb_mlp_desc* d, const float* params, const float
                           const int32_t* members_host, const uint8_t* row_members, int n_sub,
                           int mode, int td, const float* reward, const float* terminal,
                           const float* log_prob, float alpha, float discount, float* value,
-                          void* stream);
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* TQCQValue.value(return_atoms=True) (distributional_value.py:32-93) fused with
  * TQCAgent.compute_q_target (tqc_agent.py:41-57) when td != 0.  atoms[B][E*Q - n_drop] ascending
@@ -178,7 +184,8 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
                          const float* act, int obs_dim, int act_dim, int64_t B, int n_drop,
                          int td, const float* reward, const float* terminal,
                          const float* log_prob, float alpha, float discount,
-                         float* value, float* atoms, void* stream);
+                         float* value, float* atoms, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- tcgen05 operand pack: bf16 hi/lo split of every member's weights in the UMMA
  * shared-memory layout the rollout kernel streams (rebuild after the weights change). */

@@ -58,16 +58,17 @@ SIGNATURES = {
     "mb_pe_loss": (c_int, [POINTER(PeModel), POINTER(TrainCfg), P, P, P, P, P, c_int, c_int64, P,
                            P, P]),
     "mb_pe_train_workspace_bytes": (c_size_t, [POINTER(PeModel), c_int64]),
-    "mb_pe_train_step": (c_int, [POINTER(PeModel), POINTER(TrainCfg), P, P, P, c_int64, P, P, P,
+    "mb_pe_train_step": (c_int, [POINTER(PeModel), POINTER(TrainCfg), P, P, P, c_int64, P, P, P, P,
                                  P, P, c_int64, c_int, c_int, P, P, P, c_size_t, P]),
     "mb_pe_loss_grads": (c_int, [POINTER(PeModel), POINTER(TrainCfg), P, P, P, P, P, c_int64, P,
                                  P, P, P, c_size_t, P]),
-    "mb_critic_forward": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64, P, P]),
+    "mb_critic_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
+    "mb_critic_forward": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64, P, P, c_size_t, P]),
     "mb_critic_redq_target": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64,
                                       POINTER(c_int32), P, c_int, c_int, c_int, P, P, P, c_float,
-                                      c_float, P, P]),
+                                      c_float, P, P, c_size_t, P]),
     "mb_critic_tqc_target": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64, c_int,
-                                     c_int, P, P, P, c_float, c_float, P, P, P]),
+                                     c_int, P, P, P, c_float, c_float, P, P, P, c_size_t, P]),
     "mb_pe_tc_pack_bytes": (c_size_t, [POINTER(PeModel)]),
     "mb_pe_tc_pack": (c_int, [POINTER(PeModel), P, P]),
     "mb_profile_enable": (c_int, [c_int]),

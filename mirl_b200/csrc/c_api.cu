@@ -176,7 +176,7 @@ size_t mb_pe_train_workspace_bytes(const mb_pe_model* m, int64_t B) {
 }
 
 static int train_common(const char* who, const mb_pe_model* m, const mb_train_cfg* cfg, float* params,
-                        float* exp_avg, float* exp_avg_sq, int64_t step, const float* obs,
+                        float* exp_avg, float* exp_avg_sq, int64_t step, int32_t* step_counter, const float* obs,
                         const float* act, const float* delta, const float* reward, const float* done,
                         int64_t B, int e0, int e1, float* grads, float* ensemble_loss,
                         float* loss_terms, void* workspace, size_t workspace_bytes, void* stream) {
@@ -193,19 +193,19 @@ static int train_common(const char* who, const mb_pe_model* m, const mb_train_cf
         set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, mb_pe_train_workspace_bytes(m, B));
         return MB_EWORKSPACE;
     }
-    return launch_pe_train(to_dev(m), *cfg, params, exp_avg, exp_avg_sq, step, obs, act, delta, reward, done,
+    return launch_pe_train(to_dev(m), *cfg, params, exp_avg, exp_avg_sq, step, step_counter, obs, act, delta, reward, done,
                            B, e0, e1, grads, ensemble_loss, loss_terms, workspace, (cudaStream_t)stream);
 }
 
 int mb_pe_train_step(const mb_pe_model* m, const mb_train_cfg* cfg, float* params, float* exp_avg,
-                     float* exp_avg_sq, int64_t step, const float* obs, const float* act,
+                     float* exp_avg_sq, int64_t step, int32_t* step_counter, const float* obs, const float* act,
                      const float* delta, const float* reward, const float* done, int64_t B,
                      int member_begin, int member_end, float* ensemble_loss, float* loss_terms,
                      void* workspace, size_t workspace_bytes, void* stream) {
     MB_CHECK_ARG(params && exp_avg && exp_avg_sq, "mb_pe_train_step: null optimiser state");
     MB_CHECK_ARG(m && params == m->params, "mb_pe_train_step: params must be the model's blob");
-    MB_CHECK_ARG(step >= 1, "mb_pe_train_step: step must be >= 1");
-    return train_common("mb_pe_train_step", m, cfg, params, exp_avg, exp_avg_sq, step, obs, act, delta,
+    MB_CHECK_ARG(step >= 1 || step_counter, "mb_pe_train_step: step must be >= 1 (or pass step_counter)");
+    return train_common("mb_pe_train_step", m, cfg, params, exp_avg, exp_avg_sq, step, step_counter, obs, act, delta,
                         reward, done, B, member_begin, member_end, nullptr, ensemble_loss, loss_terms,
                         workspace, workspace_bytes, stream);
 }
@@ -215,7 +215,7 @@ int mb_pe_loss_grads(const mb_pe_model* m, const mb_train_cfg* cfg, const float*
                      float* grads, float* ensemble_loss, float* loss_terms, void* workspace,
                      size_t workspace_bytes, void* stream) {
     MB_CHECK_ARG(grads != nullptr, "mb_pe_loss_grads: null grads");
-    return train_common("mb_pe_loss_grads", m, cfg, nullptr, nullptr, nullptr, 1, obs, act, delta, reward,
+    return train_common("mb_pe_loss_grads", m, cfg, nullptr, nullptr, nullptr, 1, nullptr, obs, act, delta, reward,
                         done, B, 0, m ? m->mlp.ensemble_size : 0, grads, ensemble_loss, loss_terms, workspace,
                         workspace_bytes, stream);
 }
@@ -231,20 +231,31 @@ static int check_critic(const char* who, const mb_mlp_desc* d, const float* para
     return MB_OK;
 }
 
+size_t mb_critic_workspace_bytes(const mb_mlp_desc* d, int64_t B) {
+    return d ? critic_workspace_bytes(*d, B < 1 ? 1 : B) : 0;
+}
+
+// a workspace that is too small is treated like no workspace (single-launch tile kernels)
+static void* usable_ws(const mb_mlp_desc* d, int64_t B, void* ws, size_t bytes) {
+    return (ws && bytes >= critic_workspace_bytes(*d, B)) ? ws : nullptr;
+}
+
 int mb_critic_forward(const mb_mlp_desc* d, const float* params, const float* obs, const float* act,
-                      int obs_dim, int act_dim, int64_t B, float* out, void* stream) {
+                      int obs_dim, int act_dim, int64_t B, float* out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
     int rc = check_critic("mb_critic_forward", d, params, obs, act, obs_dim, act_dim, B);
     if (rc) return rc;
     if (B == 0) return MB_OK;
     MB_CHECK_ARG(out != nullptr, "mb_critic_forward: null out");
-    return launch_critic_forward(*d, params, obs, act, obs_dim, act_dim, B, out, (cudaStream_t)stream);
+    return launch_critic_forward(*d, params, obs, act, obs_dim, act_dim, B, out,
+                                 usable_ws(d, B, workspace, workspace_bytes), (cudaStream_t)stream);
 }
 
 int mb_critic_redq_target(const mb_mlp_desc* d, const float* params, const float* obs, const float* act,
                           int obs_dim, int act_dim, int64_t B, const int32_t* members_host,
                           const uint8_t* row_members, int n_sub, int mode, int td, const float* reward,
                           const float* terminal, const float* log_prob, float alpha, float discount,
-                          float* value, void* stream) {
+                          float* value, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_critic("mb_critic_redq_target", d, params, obs, act, obs_dim, act_dim, B);
     if (rc) return rc;
     if (B == 0) return MB_OK;
@@ -260,13 +271,14 @@ int mb_critic_redq_target(const mb_mlp_desc* d, const float* params, const float
                          "mb_critic_redq_target: member id %d out of range", members_host[i]);
     MB_CHECK_ARG(!td || (reward && terminal && log_prob), "mb_critic_redq_target: td needs reward/terminal/log_prob");
     return launch_critic_redq(*d, params, obs, act, obs_dim, act_dim, B, members_host, row_members, n_sub, mode,
-                              td, reward, terminal, log_prob, alpha, discount, value, (cudaStream_t)stream);
+                              td, reward, terminal, log_prob, alpha, discount, value,
+                              usable_ws(d, B, workspace, workspace_bytes), (cudaStream_t)stream);
 }
 
 int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float* obs, const float* act,
                          int obs_dim, int act_dim, int64_t B, int n_drop, int td, const float* reward,
                          const float* terminal, const float* log_prob, float alpha, float discount,
-                         float* value, float* atoms, void* stream) {
+                         float* value, float* atoms, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_critic("mb_critic_tqc_target", d, params, obs, act, obs_dim, act_dim, B);
     if (rc) return rc;
     if (B == 0) return MB_OK;
@@ -275,7 +287,8 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
     MB_CHECK_ARG(NA <= 512, "mb_critic_tqc_target: %d atoms per row unsupported (max 512)", NA);
     MB_CHECK_ARG(!td || (reward && terminal && log_prob), "mb_critic_tqc_target: td needs reward/terminal/log_prob");
     return launch_critic_tqc(*d, params, obs, act, obs_dim, act_dim, B, n_drop, td, reward, terminal, log_prob,
-                             alpha, discount, value, atoms, (cudaStream_t)stream);
+                             alpha, discount, value, atoms, usable_ws(d, B, workspace, workspace_bytes),
+                             (cudaStream_t)stream);
 }
 
 int mb_profile_enable(int on) {

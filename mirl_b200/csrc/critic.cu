@@ -8,6 +8,7 @@
 // REDQ target evaluates only the drawn members.
 #include "common.cuh"
 #include "simt_mlp.cuh"
+#include "layer_gemm.cuh"
 #include "pe_kernels.h"
 
 namespace mb {
@@ -178,6 +179,115 @@ k_critic_tqc(mb_mlp_desc d, const float* __restrict__ params, const float* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Small-batch path: one launch per layer (layer_gemm.cuh) + a reduce / sort kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int64_t kLayeredMaxRows = 1 << 20;      // rows x members up to which the layered path is used
+
+size_t critic_workspace_bytes(const mb_mlp_desc& d, int64_t B) {
+    int w = 0;
+    for (int l = 0; l <= d.num_layers; ++l) w = d.sizes[l] > w ? d.sizes[l] : w;
+    return (size_t)(2 * (int64_t)d.ensemble_size * B * w + (int64_t)d.ensemble_size * B * d.sizes[d.num_layers]) * 4 + 256;
+}
+
+// Runs the stack for `nmem` members; returns the final layer's output [nmem][B][N_out] (in ws
+// unless `final_out` is given).
+static int layered_forward(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
+                           int O, int A, int64_t B, const int* members, int nmem, float* ws, float* final_out,
+                           float** result, cudaStream_t s) {
+    int w = 0;
+    for (int l = 0; l <= d.num_layers; ++l) w = d.sizes[l] > w ? d.sizes[l] : w;
+    float* buf[2] = {ws, ws + (int64_t)d.ensemble_size * B * w};
+    float* last = final_out ? final_out : ws + 2 * (int64_t)d.ensemble_size * B * w;
+    ConcatIn ci{obs, act, nullptr, O, A, 0};
+    for (int l = 0; l < d.num_layers; ++l) {
+        LayerArgs a;
+        a.B = (int)B; a.K = d.sizes[l]; a.N = d.sizes[l + 1];
+        a.A = l == 0 ? nullptr : buf[(l - 1) & 1];
+        a.a_slot_stride = (int64_t)B * a.K;
+        a.W = params + w_offset(d, l);
+        a.bias = params + b_offset(d, l);
+        a.out = l + 1 == d.num_layers ? last : buf[l & 1];
+        a.a_act = -1;
+        a.out_act = l + 1 < d.num_layers ? d.activation : -1;
+        a.slot0 = 0;
+        a.nmem = nmem;
+        for (int i = 0; i < nmem; ++i) a.member[i] = members[i];
+        int rc = launch_layer(a, l == 0 ? &ci : nullptr, s);
+        if (rc) return rc;
+    }
+    *result = last;
+    return MB_OK;
+}
+
+// value[b] = reduce over the evaluated members that count for row b (+ optional TD transform)
+__global__ void k_redq_reduce(const float* __restrict__ q, int nmem, MemberList ml, int64_t B,
+                              const uint8_t* __restrict__ row_members, int n_sub, int mode, int td,
+                              const float* __restrict__ reward, const float* __restrict__ terminal,
+                              const float* __restrict__ log_prob, float alpha, float discount,
+                              float* __restrict__ value) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    float acc = mode == MB_REDUCE_MIN ? INFINITY : mode == MB_REDUCE_MAX ? -INFINITY : 0.f;
+    for (int k = 0; k < nmem; ++k) {
+        bool use = true;
+        if (row_members) {
+            use = false;
+            for (int sidx = 0; sidx < n_sub; ++sidx) use = use || (row_members[(int64_t)sidx * B + r] == ml.id[k]);
+        }
+        if (use) {
+            const float v = q[(int64_t)k * B + r];
+            acc = mode == MB_REDUCE_MIN ? fminf(acc, v) : mode == MB_REDUCE_MAX ? fmaxf(acc, v) : acc + v;
+        }
+    }
+    if (mode == MB_REDUCE_MEAN) acc /= (float)n_sub;
+    if (td) acc = reward[r] + (1.f - terminal[r]) * discount * (acc - alpha * log_prob[r]);
+    value[r] = acc;
+}
+
+// one warp per row: pool E*Q atoms (member-major), bitonic sort, drop the n_drop largest
+__global__ void __launch_bounds__(256)
+k_tqc_sort(const float* __restrict__ raw /*[E][B][Q]*/, int E, int Q, int64_t B, int n_drop, int npad, int td,
+           const float* __restrict__ reward, const float* __restrict__ terminal,
+           const float* __restrict__ log_prob, float alpha, float discount, float* __restrict__ value,
+           float* __restrict__ atoms) {
+    extern __shared__ float pool[];                       // [8 warps][npad]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+    if (r >= B) return;
+    float* row = pool + warp * npad;
+    const int NA = E * Q, keep = NA - n_drop;
+    for (int t = lane; t < npad; t += 32) {
+        float v = INFINITY;
+        if (t < NA) { const int e = t / Q, qi = t - e * Q; v = raw[((int64_t)e * B + r) * Q + qi]; }
+        row[t] = v;
+    }
+    __syncwarp();
+    if (n_drop > 0) {
+        for (int k = 2; k <= npad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < npad / 2; t += 32) {
+                    const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+                    const bool up = ((lo & k) == 0);
+                    const float a = row[lo], b = row[hi];
+                    if ((a > b) == up) { row[lo] = b; row[hi] = a; }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    float sum = 0.f;
+    for (int t = lane; t < keep; t += 32) sum += row[t];
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0 && value) value[r] = sum / (float)keep;
+    if (atoms) {
+        float rw = 0.f, sc = 1.f, sh = 0.f;
+        if (td) { rw = reward[r]; sc = (1.f - terminal[r]) * discount; sh = alpha * log_prob[r]; }
+        for (int t = lane; t < keep; t += 32) atoms[r * keep + t] = td ? rw + sc * (row[t] - sh) : row[t];
+    }
+}
+
 static int max_width(const mb_mlp_desc& d) {
     int w = 0;
     for (int l = 0; l <= d.num_layers; ++l) w = d.sizes[l] > w ? d.sizes[l] : w;
@@ -203,8 +313,14 @@ static int critic_forward_t(const mb_mlp_desc& d, const float* params, const flo
 }
 
 int launch_critic_forward(const mb_mlp_desc& d, const float* params, const float* obs,
-                          const float* act, int O, int A, int64_t B, float* out, cudaStream_t s) {
+                          const float* act, int O, int A, int64_t B, float* out, void* ws, cudaStream_t s) {
     const int w = max_width(d);
+    if (ws && B * d.ensemble_size <= kLayeredMaxRows) {
+        int members[32];
+        for (int i = 0; i < d.ensemble_size; ++i) members[i] = i;
+        float* res = nullptr;
+        return layered_forward(d, params, obs, act, O, A, B, members, d.ensemble_size, (float*)ws, out, &res, s);
+    }
     if (w <= SimtTile64::MAXW) return critic_forward_t<SimtTile64>(d, params, obs, act, O, A, B, out, s);
     if (w <= SimtTile32::MAXW) return critic_forward_t<SimtTile32>(d, params, obs, act, O, A, B, out, s);
     set_error("critic width %d > %d unsupported", w, SimtTile32::MAXW);
@@ -232,7 +348,7 @@ static int critic_redq_t(const mb_mlp_desc& d, const float* params, const float*
 int launch_critic_redq(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
                        int O, int A, int64_t B, const int32_t* members, const uint8_t* row_members,
                        int n_sub, int mode, int td, const float* reward, const float* terminal,
-                       const float* log_prob, float alpha, float discount, float* value,
+                       const float* log_prob, float alpha, float discount, float* value, void* ws,
                        cudaStream_t s) {
     MemberList ml;
     if (members) {
@@ -244,6 +360,15 @@ int launch_critic_redq(const mb_mlp_desc& d, const float* params, const float* o
         if (!row_members) n_sub = d.ensemble_size;
     }
     const int w = max_width(d);
+    if (ws && B * ml.n <= kLayeredMaxRows) {
+        float* q = nullptr;
+        int rc = layered_forward(d, params, obs, act, O, A, B, ml.id, ml.n, (float*)ws, nullptr, &q, s);
+        if (rc) return rc;
+        k_redq_reduce<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(q, ml.n, ml, B, row_members, n_sub, mode, td, reward,
+                                                                 terminal, log_prob, alpha, discount, value);
+        MB_CUDA_LAUNCH_CHECK("k_redq_reduce");
+        return MB_OK;
+    }
     // small batches are latency bound: 32-row tiles spread a 256-row batch over more SMs
     if (w <= SimtTile64::MAXW && B > 64 * 148)
         return critic_redq_t<SimtTile64>(d, params, obs, act, O, A, B, ml, row_members, n_sub, mode, td,
@@ -258,9 +383,24 @@ int launch_critic_redq(const mb_mlp_desc& d, const float* params, const float* o
 int launch_critic_tqc(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
                       int O, int A, int64_t B, int n_drop, int td, const float* reward,
                       const float* terminal, const float* log_prob, float alpha, float discount,
-                      float* value, float* atoms, cudaStream_t s) {
+                      float* value, float* atoms, void* ws, cudaStream_t s) {
     using Tile = SimtTile32;
     const int w = max_width(d);
+    if (ws && B * d.ensemble_size <= kLayeredMaxRows) {
+        int members[32];
+        for (int i = 0; i < d.ensemble_size; ++i) members[i] = i;
+        float* raw = nullptr;
+        int rc = layered_forward(d, params, obs, act, O, A, B, members, d.ensemble_size, (float*)ws, nullptr, &raw, s);
+        if (rc) return rc;
+        const int NAl = d.ensemble_size * d.sizes[d.num_layers];
+        int np2 = 32;
+        while (np2 < NAl) np2 <<= 1;
+        k_tqc_sort<<<(unsigned)((B + 7) / 8), 256, (size_t)8 * np2 * sizeof(float), s>>>(
+            raw, d.ensemble_size, d.sizes[d.num_layers], B, n_drop, np2, td, reward, terminal, log_prob, alpha, discount,
+            value, atoms);
+        MB_CUDA_LAUNCH_CHECK("k_tqc_sort");
+        return MB_OK;
+    }
     if (w > Tile::MAXW) { set_error("critic width %d > %d unsupported", w, Tile::MAXW); return MB_EUNSUPPORTED; }
     const int NA = d.ensemble_size * d.sizes[d.num_layers];
     int npad = 32;

@@ -55,22 +55,23 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, con
 // ---- model training (pe_train.cu)
 size_t train_workspace_bytes(const mb_mlp_desc& d, int64_t B);
 int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, float* exp_avg,
-                    float* exp_avg_sq, int64_t step, const float* obs, const float* act,
+                    float* exp_avg_sq, int64_t step, int32_t* step_counter, const float* obs, const float* act,
                     const float* delta, const float* reward, const float* done, int64_t B,
                     int e0, int e1, float* grads_out, float* ensemble_loss, float* loss_terms,
                     void* ws, cudaStream_t s);
 
 // ---- critic targets (critic.cu)
+size_t critic_workspace_bytes(const mb_mlp_desc& d, int64_t B);
 int launch_critic_forward(const mb_mlp_desc& d, const float* params, const float* obs,
-                          const float* act, int O, int A, int64_t B, float* out, cudaStream_t s);
+                          const float* act, int O, int A, int64_t B, float* out, void* ws, cudaStream_t s);
 int launch_critic_redq(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
                        int O, int A, int64_t B, const int32_t* members, const uint8_t* row_members,
                        int n_sub, int mode, int td, const float* reward, const float* terminal,
-                       const float* log_prob, float alpha, float discount, float* value,
+                       const float* log_prob, float alpha, float discount, float* value, void* ws,
                        cudaStream_t s);
 int launch_critic_tqc(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
                       int O, int A, int64_t B, int n_drop, int td, const float* reward,
                       const float* terminal, const float* log_prob, float alpha, float discount,
-                      float* value, float* atoms, cudaStream_t s);
+                      float* value, float* atoms, void* ws, cudaStream_t s);
 
 }  // namespace mb

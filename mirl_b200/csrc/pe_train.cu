@@ -10,6 +10,7 @@
 // may cover any member slice [e0, e1) -- that is the multi-GPU partition; no collective.
 #include "common.cuh"
 #include "simt_mlp.cuh"
+#include "layer_gemm.cuh"
 #include "pe_kernels.h"
 
 namespace mb {
@@ -147,12 +148,113 @@ k_train_fwd(PeDev m, mb_train_cfg cfg, int e0, const float* __restrict__ obs,
     }
 }
 
+// ---- small-batch forward path: prep + one launch per layer (layer_gemm.cuh) + loss head -------
+// x0[e][b][:] = normalised [obs | act] (Normalizer.process, normalizer.py:17-18); also zeroes the
+// atomically accumulated outputs of the member slice so the step needs no memset nodes.
+__global__ void k_train_prep(PeDev m, int e0, int ne, const float* __restrict__ obs,
+                             const float* __restrict__ act, int64_t B, float* __restrict__ x0s,
+                             float* __restrict__ grads, float* __restrict__ ensemble_loss,
+                             float* __restrict__ loss_terms) {
+    const int O = m.O, A = m.A, IN = O + A, D = O + 1;
+    const float* nrm = m.norm;
+    const int64_t total = (int64_t)ne * B * IN;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t t = gid; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rowl = t / IN;
+        const int j = (int)(t - rowl * IN);
+        const int64_t r = (int64_t)e0 * B + rowl;
+        float v;
+        if (j < O) v = (obs[r * O + j] - nrm[j]) / (nrm[O + j] + kNormEps);
+        else v = (act[r * A + (j - O)] - nrm[2 * O + (j - O)]) / (nrm[2 * O + A + (j - O)] + kNormEps);
+        x0s[r * IN + j] = v;
+    }
+    if (gid < ne) ensemble_loss[e0 + gid] = 0.f;
+    if (gid < 3) loss_terms[gid] = 0.f;
+    if (gid < 2 * (int64_t)ne * D) {
+        const int which = (int)(gid / (ne * D)), k = (int)(gid % (ne * D));
+        grads[logstd_offset(m.mlp, which) + (int64_t)e0 * D + k] = 0.f;
+    }
+}
+
+// Gaussian NLL head on the last layer's raw output out[e][b][2D]: loss, dL/d(out), log-std bound
+// gradients.  grid = (row chunks of kLossRows, members of the slice).
+constexpr int kLossRows = 32;       // rows per CTA: spreads a 256-row batch over 8 x members CTAs
+__global__ void __launch_bounds__(256)
+k_train_loss(PeDev m, mb_train_cfg cfg, int e0, const float* __restrict__ out,
+             const float* __restrict__ delta, const float* __restrict__ reward,
+             const float* __restrict__ done_in, int64_t B, float* __restrict__ gout,
+             float* __restrict__ grads, float* __restrict__ ensemble_loss, float* __restrict__ loss_terms) {
+    __shared__ float red[8];
+    __shared__ float gmx[64], gmn[64];
+    const int O = m.O, A = m.A, D = O + 1;
+    const int e = e0 + blockIdx.y;
+    const int64_t mrow = (int64_t)e * B;
+    const int64_t row0 = (int64_t)blockIdx.x * kLossRows;
+    const int cnt = (int)min((int64_t)kLossRows, B - row0);
+    const float* nrm = m.norm;
+    const float* dmean = nrm + 2 * O + 2 * A;
+    const float* dstd = dmean + O;
+    const float* mxp = m.params + logstd_offset(m.mlp, 0) + e * D;
+    const float* mnp = m.params + logstd_offset(m.mlp, 1) + e * D;
+    if (threadIdx.x < 64) { gmx[threadIdx.x] = 0.f; gmn[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const float invB = 1.f / (float)B;
+    float part = 0.f;
+    for (int t = threadIdx.x; t < cnt * D; t += 256) {
+        const int i = t / D, j = t - i * D;
+        const int64_t r = mrow + row0 + i;
+        const float mu = out[r * (2 * D) + j], raw = out[r * (2 * D) + D + j];
+        const float mx = mxp[j], mn = mnp[j];
+        const float a = mx - raw;
+        const float ls1 = mx - softplusf_(a);
+        const float c = ls1 - mn;
+        const float ls = mn + softplusf_(c);
+        float tgt, coef;
+        if (j < O) { tgt = (delta[r * O + j] - dmean[j]) / (dstd[j] + kNormEps); coef = 1.f; }
+        else { tgt = reward[r]; coef = cfg.reward_coef; }
+        const float mask = cfg.ignore_terminal_state ? 1.f - done_in[r] : 1.f;
+        const float inv_var = expf(-2.f * ls);
+        const float diff = tgt - mu;
+        const float w = mask * coef * invB;
+        part += w * 0.5f * (kLog2Pi + 2.f * ls + diff * diff * inv_var);
+        const float g_ls = w * (1.f - diff * diff * inv_var);
+        const float sa = softplus_gradf_(a), sb = softplus_gradf_(c);
+        gout[r * (2 * D) + j] = -w * diff * inv_var;
+        gout[r * (2 * D) + D + j] = g_ls * sb * sa;
+        atomicAdd(&gmx[j], g_ls * sb * (1.f - sa));
+        atomicAdd(&gmn[j], g_ls * (1.f - sb));
+    }
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sum = 0.f;
+        for (int w = 0; w < 8; ++w) sum += red[w];
+        atomicAdd(ensemble_loss + e, sum);
+        atomicAdd(loss_terms + 0, sum);
+    }
+    if (threadIdx.x < D) {
+        const int j = threadIdx.x;
+        float gx = gmx[j], gn = gmn[j];
+        if (blockIdx.x == 0) {   // bound regulariser, once per member (pe_model.py:81,105-108)
+            gx += cfg.bound_reg_coef;
+            gn -= cfg.bound_reg_coef;
+            atomicAdd(loss_terms + 2, cfg.bound_reg_coef * (mxp[j] - mnp[j]));
+        }
+        atomicAdd(grads + logstd_offset(m.mlp, 0) + e * D + j, gx);
+        atomicAdd(grads + logstd_offset(m.mlp, 1) + e * D + j, gn);
+    }
+}
+
 // ---- backward GEMMs ------------------------------------------------------------------------
 // DW: dW[k][n] = sum_b h[b][k] * g[b][n] + wd * W[k][n];  db[n] = sum_b g[b][n]
 // DX: gprev[b][k] = (sum_n g[b][n] * W[k][n]) * swish'(z[b][k])
+// Same structure as layer_gemm.cuh: 64x64 output tile, reduction in chunks of 32 with the next
+// chunk's operands prefetched into registers (the grids are ~1 CTA per SM).
 constexpr int kGT = 64;    // output tile edge
-constexpr int kGR = 16;    // reduction chunk
+constexpr int kGR = 32;    // reduction chunk
 constexpr int kGLD = kGT + 4;
+constexpr int kGPer = kGT * kGR / 256;   // operand elements per thread per chunk
 
 template <bool DX>
 __global__ void __launch_bounds__(256)
@@ -172,6 +274,59 @@ k_train_gemm(int e0, int64_t B, int K, int N, const float* __restrict__ hin /*x0
     const float* ge = g + (int64_t)e * B * N;
     const float* he = DX ? nullptr : hin + (int64_t)e * B * K;
     const float* We = W + (int64_t)e * K * N;
+    float ra[kGPer], rb[kGPer];
+    // DX: both operands have the REDUCTION index contiguous in memory (g[b][n], W[k][n]):
+    //     thread -> output index tid/4, 8 consecutive reduction indices (stored transposed)
+    // DW: both operands have the OUTPUT index contiguous (h[b][k], g[b][n]):
+    //     thread -> reduction index tid/8, 8 consecutive output indices
+    const int xo = tid >> 2, xr = (tid & 3) * kGPer;
+    const int wr = tid >> 3, wo = (tid & 7) * kGPer;
+
+    // 16-byte loads when K and N are multiples of 4 (every row then starts 16-byte aligned)
+    const bool vec = (K & 3) == 0 && (N & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(ge) | reinterpret_cast<uintptr_t>(We) |
+                       reinterpret_cast<uintptr_t>(he)) & 15) == 0;
+    auto ld4 = [](const float* p, bool ok, float* dst) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = __ldg(reinterpret_cast<const float4*>(p));
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    };
+    auto fetch = [&](int r0) {
+        if (DX) {
+            if (vec) {
+#pragma unroll
+                for (int h = 0; h < kGPer / 4; ++h) {
+                    const int r = r0 + xr + 4 * h;
+                    ld4(ge + (int64_t)(m0 + xo) * N + r, r < R && m0 + xo < M, ra + 4 * h);
+                    ld4(We + (int64_t)(n0 + xo) * N + r, r < R && n0 + xo < NN, rb + 4 * h);
+                }
+                return;
+            }
+#pragma unroll
+            for (int c = 0; c < kGPer; ++c) {
+                const int r = r0 + xr + c;
+                const bool rin = r < R;
+                ra[c] = (rin && m0 + xo < M) ? ge[(int64_t)(m0 + xo) * N + r] : 0.f;
+                rb[c] = (rin && n0 + xo < NN) ? We[(int64_t)(n0 + xo) * N + r] : 0.f;
+            }
+        } else {
+            const bool rin = r0 + wr < R;
+            if (vec) {
+#pragma unroll
+                for (int h = 0; h < kGPer / 4; ++h) {
+                    ld4(he + (int64_t)(r0 + wr) * K + m0 + wo + 4 * h, rin && m0 + wo + 4 * h < M, ra + 4 * h);
+                    ld4(ge + (int64_t)(r0 + wr) * N + n0 + wo + 4 * h, rin && n0 + wo + 4 * h < NN, rb + 4 * h);
+                }
+                return;
+            }
+#pragma unroll
+            for (int c = 0; c < kGPer; ++c) {
+                ra[c] = (rin && m0 + wo + c < M) ? he[(int64_t)(r0 + wr) * K + m0 + wo + c] : 0.f;
+                rb[c] = (rin && n0 + wo + c < NN) ? ge[(int64_t)(r0 + wr) * N + n0 + wo + c] : 0.f;
+            }
+        }
+    };
+
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -179,33 +334,20 @@ k_train_gemm(int e0, int64_t B, int K, int N, const float* __restrict__ hin /*x0
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float bsum = 0.f;
 
+    fetch(0);
     for (int r0 = 0; r0 < R; r0 += kGR) {
-        if (DX) {
-            // As[r][m] = g[m0+m][r0+r] ; Bs[r][n] = W[n0+n][r0+r]   (reduction index contiguous)
-            const int mm = tid >> 2, rq = (tid & 3) * 4;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int r = rq + c;
-                const bool rin = r0 + r < R;
-                As[r][mm] = (rin && m0 + mm < M) ? ge[(int64_t)(m0 + mm) * N + r0 + r] : 0.f;
-                Bs[r][mm] = (rin && n0 + mm < NN) ? We[(int64_t)(n0 + mm) * N + r0 + r] : 0.f;
-            }
-        } else {
-            // As[r][m] = h[r0+r][m0+m] ; Bs[r][n] = g[r0+r][n0+n]   (output index contiguous)
-            const int r = tid >> 4, cq = (tid & 15) * 4;
-            const bool rin = r0 + r < R;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float a = 0.f;
-                if (rin && m0 + cq + c < M) {
-                    a = he[(int64_t)(r0 + r) * K + m0 + cq + c];
-                    if (hin_is_z) a = swishf_(a);
-                }
-                As[r][cq + c] = a;
-                Bs[r][cq + c] = (rin && n0 + cq + c < NN) ? ge[(int64_t)(r0 + r) * N + n0 + cq + c] : 0.f;
+        for (int c = 0; c < kGPer; ++c) {
+            if (DX) {
+                As[xr + c][xo] = ra[c];
+                Bs[xr + c][xo] = rb[c];
+            } else {
+                As[wr][wo + c] = hin_is_z ? swishf_(ra[c]) : ra[c];
+                Bs[wr][wo + c] = rb[c];
             }
         }
         __syncthreads();
+        if (r0 + kGR < R) fetch(r0 + kGR);
 #pragma unroll
         for (int r = 0; r < kGR; ++r) {
             const float4 a = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
@@ -248,9 +390,9 @@ k_train_gemm(int e0, int64_t B, int K, int N, const float* __restrict__ hin /*x0
         if ((tid & 31) == 0) red[tid >> 5] = l2;
         __syncthreads();
         if (tid == 0) {
-            float s = 0.f;
-            for (int w = 0; w < 8; ++w) s += red[w];
-            atomicAdd(loss_terms + 1, s);
+            float sacc = 0.f;
+            for (int w = 0; w < 8; ++w) sacc += red[w];
+            atomicAdd(loss_terms + 1, sacc);
         }
     }
 }
@@ -258,9 +400,24 @@ k_train_gemm(int e0, int64_t B, int K, int N, const float* __restrict__ hin /*x0
 // ---- Adam (torch.optim.Adam defaults, no weight decay / amsgrad) ----------------------------
 struct AdamSegs { int n; int64_t off[2 * MB_MAX_LAYERS + 2]; int64_t len[2 * MB_MAX_LAYERS + 2]; };
 
+__global__ void k_step_inc(int32_t* step_counter) { *step_counter += 1; }
+
+// step_dev != nullptr: bias corrections come from the device-resident step counter (graph replay)
 __global__ void k_adam(AdamSegs segs, float* __restrict__ p, float* __restrict__ m1,
                        float* __restrict__ m2, const float* __restrict__ g, float beta1,
-                       float beta2, float eps, float step_size, float bc2_sqrt) {
+                       float beta2, float eps, float step_size, float bc2_sqrt,
+                       const int32_t* __restrict__ step_dev, float lr) {
+    __shared__ float sh[2];
+    if (step_dev != nullptr) {
+        if (threadIdx.x == 0) {
+            const double t = (double)*step_dev;
+            sh[0] = (float)((double)lr / (1.0 - pow((double)beta1, t)));
+            sh[1] = (float)sqrt(1.0 - pow((double)beta2, t));
+        }
+        __syncthreads();
+        step_size = sh[0];
+        bc2_sqrt = sh[1];
+    }
     const int s = blockIdx.y;
     const int64_t off = segs.off[s], len = segs.len[s];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len;
@@ -284,7 +441,7 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, float* exp_avg,
-                    float* exp_avg_sq, int64_t step, const float* obs, const float* act,
+                    float* exp_avg_sq, int64_t step, int32_t* step_counter, const float* obs, const float* act,
                     const float* delta, const float* reward, const float* done, int64_t B,
                     int e0, int e1, float* grads_out, float* ensemble_loss, float* loss_terms,
                     void* ws, cudaStream_t s) {
@@ -294,23 +451,52 @@ int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, floa
     TrainWs w = carve(d, B, ws);
     float* grads = grads_out ? grads_out : w.grads;
 
-    // zero the atomically accumulated outputs of this slice
-    cudaMemsetAsync(ensemble_loss + e0, 0, sizeof(float) * ne, s);
-    cudaMemsetAsync(loss_terms, 0, sizeof(float) * 3, s);
-    cudaMemsetAsync(grads + logstd_offset(d, 0) + (int64_t)e0 * D, 0, sizeof(float) * ne * D, s);
-    cudaMemsetAsync(grads + logstd_offset(d, 1) + (int64_t)e0 * D, 0, sizeof(float) * ne * D, s);
-
-    int rc = set_smem(k_train_fwd, Tile::kSmemBytes);
-    if (rc) return rc;
-    ZPtrs zs;
-    for (int l = 0; l < MB_MAX_LAYERS; ++l) zs.p[l] = w.z[l];
     float* gcur = w.gA;
     float* gnext = w.gB;
-    dim3 gf((unsigned)((B + Tile::TM - 1) / Tile::TM), (unsigned)ne);
-    k_train_fwd<<<gf, kSimtThreads, Tile::kSmemBytes, s>>>(m, cfg, e0, obs, act, delta, reward, done, B,
-                                                           w.x0, zs, gcur, grads, ensemble_loss,
-                                                           loss_terms);
-    MB_CUDA_LAUNCH_CHECK("k_train_fwd");
+    if (B * ne <= 65536) {
+        // small batch: one launch per layer spreads the work over all SMs
+        {
+            const int64_t total = (int64_t)ne * B * d.sizes[0];
+            k_train_prep<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m, e0, ne, obs, act, B, w.x0, grads,
+                                                                       ensemble_loss, loss_terms);
+            MB_CUDA_LAUNCH_CHECK("k_train_prep");
+        }
+        for (int l = 0; l < L; ++l) {
+            LayerArgs a;
+            a.B = (int)B; a.K = d.sizes[l]; a.N = d.sizes[l + 1];
+            a.A = l == 0 ? w.x0 : w.z[l - 1];
+            a.a_slot_stride = (int64_t)B * a.K;
+            a.W = m.params + w_offset(d, l);
+            a.bias = m.params + b_offset(d, l);
+            a.out = l + 1 < L ? w.z[l] : gnext;              // raw head output parks in the spare g buffer
+            a.a_act = l == 0 ? -1 : d.activation;            // layers consume stored PRE-activations
+            a.out_act = -1;
+            a.slot0 = e0;
+            a.nmem = ne;
+            for (int i = 0; i < ne; ++i) a.member[i] = e0 + i;
+            int rc = launch_layer(a, nullptr, s);
+            if (rc) return rc;
+        }
+        dim3 gl((unsigned)((B + kLossRows - 1) / kLossRows), (unsigned)ne);
+        k_train_loss<<<gl, 256, 0, s>>>(m, cfg, e0, gnext, delta, reward, done, B, gcur, grads, ensemble_loss,
+                                        loss_terms);
+        MB_CUDA_LAUNCH_CHECK("k_train_loss");
+    } else {
+        // large batch: fused tile kernel keeps the activations on chip
+        cudaMemsetAsync(ensemble_loss + e0, 0, sizeof(float) * ne, s);
+        cudaMemsetAsync(loss_terms, 0, sizeof(float) * 3, s);
+        cudaMemsetAsync(grads + logstd_offset(d, 0) + (int64_t)e0 * D, 0, sizeof(float) * ne * D, s);
+        cudaMemsetAsync(grads + logstd_offset(d, 1) + (int64_t)e0 * D, 0, sizeof(float) * ne * D, s);
+        int rc = set_smem(k_train_fwd, Tile::kSmemBytes);
+        if (rc) return rc;
+        ZPtrs zs;
+        for (int l = 0; l < MB_MAX_LAYERS; ++l) zs.p[l] = w.z[l];
+        dim3 gf((unsigned)((B + Tile::TM - 1) / Tile::TM), (unsigned)ne);
+        k_train_fwd<<<gf, kSimtThreads, Tile::kSmemBytes, s>>>(m, cfg, e0, obs, act, delta, reward, done, B,
+                                                               w.x0, zs, gcur, grads, ensemble_loss,
+                                                               loss_terms);
+        MB_CUDA_LAUNCH_CHECK("k_train_fwd");
+    }
     for (int l = L - 1; l >= 0; --l) {
         const int K = d.sizes[l], N = d.sizes[l + 1];
         const float* Wl = m.params + w_offset(d, l);
@@ -339,12 +525,17 @@ int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, floa
         }
         segs.off[segs.n] = logstd_offset(d, 0) + (int64_t)e0 * D; segs.len[segs.n++] = (int64_t)ne * D;
         segs.off[segs.n] = logstd_offset(d, 1) + (int64_t)e0 * D; segs.len[segs.n++] = (int64_t)ne * D;
-        const double bc1 = 1.0 - pow((double)cfg.beta1, (double)step);
-        const double bc2 = 1.0 - pow((double)cfg.beta2, (double)step);
+        const double hstep = step >= 1 ? (double)step : 1.0;
+        const double bc1 = 1.0 - pow((double)cfg.beta1, hstep);
+        const double bc2 = 1.0 - pow((double)cfg.beta2, hstep);
         const int64_t nb = (maxlen + 255) / 256;
         dim3 ga((unsigned)(nb < 1184 ? nb : 1184), (unsigned)segs.n);
+        if (step_counter) {
+            k_step_inc<<<1, 1, 0, s>>>(step_counter);
+            MB_CUDA_LAUNCH_CHECK("k_step_inc");
+        }
         k_adam<<<ga, 256, 0, s>>>(segs, params, exp_avg, exp_avg_sq, grads, cfg.beta1, cfg.beta2, cfg.eps,
-                                  (float)(cfg.lr / bc1), (float)sqrt(bc2));
+                                  (float)(cfg.lr / bc1), (float)sqrt(bc2), step_counter, cfg.lr);
         MB_CUDA_LAUNCH_CHECK("k_adam");
     }
     (void)E;

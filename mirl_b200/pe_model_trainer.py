@@ -45,7 +45,8 @@ class B200PEModelTrainer(Component):
                  load_best=True, valid_ratio=0.2, max_valid=2000, resample=True, batch_size=256,
                  report_freq=100, max_not_improve=20, silent=False, load_dataset_dir=None,
                  tb_log_freq=100, optimizer_class="Adam", optimizer_kwargs={}, load_dir=None,
-                 save_dir=None, ignore_terminal_state=False, members=None, snapshot_to_disk=False):
+                 save_dir=None, ignore_terminal_state=False, members=None, snapshot_to_disk=False,
+                 use_cuda_graph=True):
         if optimizer_class not in ("Adam", torch.optim.Adam):
             raise NotImplementedError("the fused training step implements torch.optim.Adam only")
         extra = set(optimizer_kwargs) - {"betas", "eps"}
@@ -76,6 +77,9 @@ class B200PEModelTrainer(Component):
         self.save_dir = osp.expanduser(save_dir) if save_dir is not None else None
         self.members = tuple(members) if members is not None else (0, model.ensemble_size)
         self.snapshot_to_disk = snapshot_to_disk
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None            # (key, CUDAGraph, static batch dict)
+        self._step_dev = None         # device-resident Adam step counter (graph replay)
         self._ws = None
         self._loss_terms = None
         self._ensemble_loss = None
@@ -89,10 +93,28 @@ class B200PEModelTrainer(Component):
             self._ensemble_loss = torch.zeros(self.model.ensemble_size, device=dev)
             self._loss_terms = torch.zeros(3, device=dev)
 
+    def _launch(self, t, B, step_counter):
+        """Enqueue the fused step on the current stream (one C-ABI call = 18 kernel launches)."""
+        model, L = self.model, _lib.lib()
+        m = model._c_model(None)
+        cfg = model.train_cfg(self.ignore_terminal_state, self.lr, self.betas, self.eps)
+        e0, e1 = self.members
+        _lib.check(L.mb_pe_train_step(
+            ctypes.byref(m), ctypes.byref(cfg), _lib.ptr(model.module.flat.data),
+            _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.num_train_steps,
+            _lib.ptr(step_counter) if step_counter is not None else None,
+            _lib.ptr(t["observations"]), _lib.ptr(t["actions"]), _lib.ptr(t["deltas"]),
+            _lib.ptr(t["rewards"]), _lib.ptr(t["terminals"]), B, e0, e1, _lib.ptr(self._ensemble_loss),
+            _lib.ptr(self._loss_terms), _lib.ptr(self._ws), self._ws.numel(), _lib.stream()))
+
     def train_step_async(self, batch):
         """Enqueue one fused training step; returns device tensors
         ``(ensemble_loss [E], loss_terms [3] = sum_e loss_e, l2, bound)`` without synchronising
-        (the reference syncs twice per step, pe_model_trainer.py:101-104)."""
+        (the reference syncs twice per step, pe_model_trainer.py:101-104).
+
+        With ``use_cuda_graph`` the launch sequence is captured once per batch shape and replayed:
+        the step has no host-side state (the Adam step count lives on the device), so a replay is
+        one graph launch instead of 18 kernel launches."""
         model, L = self.model, _lib.lib()
         dev = model.device
         self._state_to(dev)
@@ -102,18 +124,33 @@ class B200PEModelTrainer(Component):
             "training batches are per-member [E,B,.] (pe_model_trainer.py:268-270)"
         B = o.shape[1]
         m = model._c_model(None)
-        cfg = model.train_cfg(self.ignore_terminal_state, self.lr, self.betas, self.eps)
         need = L.mb_pe_train_workspace_bytes(ctypes.byref(m), B)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._graph = None
         self.num_train_steps += 1
-        e0, e1 = self.members
-        _lib.check(L.mb_pe_train_step(
-            ctypes.byref(m), ctypes.byref(cfg), _lib.ptr(model.module.flat.data),
-            _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.num_train_steps,
-            _lib.ptr(o), _lib.ptr(t["actions"]), _lib.ptr(t["deltas"]), _lib.ptr(t["rewards"]),
-            _lib.ptr(t["terminals"]), B, e0, e1, _lib.ptr(self._ensemble_loss),
-            _lib.ptr(self._loss_terms), _lib.ptr(self._ws), self._ws.numel(), _lib.stream()))
+        if not self.use_cuda_graph:
+            self._launch(t, B, None)
+        else:
+            if self._step_dev is None or self._step_dev.device != dev:
+                self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            key = (B, model.module.flat.data_ptr(), model._norm().data_ptr(), self.ignore_terminal_state,
+                   self.lr, self.members)
+            if self._graph is None or self._graph[0] != key:
+                static = {k: torch.empty_like(v) for k, v in t.items()}
+                self._step_dev.fill_(self.num_train_steps - 1)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                # capture does not execute: the first replay below performs step `num_train_steps`
+                with torch.cuda.graph(g, stream=side):
+                    self._launch(static, B, self._step_dev)
+                self._graph = (key, g, static)
+            _, g, static = self._graph
+            for k in _FIELDS:
+                static[k].copy_(t[k], non_blocking=True)
+            g.replay()
         model.module.mark_weights_changed()
         return self._ensemble_loss, self._loss_terms
 

@@ -53,6 +53,13 @@ class _CriticBase(nn.Module, QValue):
     def device(self):
         return self.module.flat.device
 
+    def _workspace(self, B):
+        need = _lib.lib().mb_critic_workspace_bytes(ctypes.byref(self.module.desc), B)
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need or ws.device != self.device:
+            ws = self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return ws
+
     def parameters(self, recurse=True):
         """Per-member views in the reference's order (``net.{2l}.weight_net{e}``,
         ``net.{2l}.bias_net{e}`` per layer, per member) -- see the module docstring."""
@@ -84,9 +91,11 @@ class _CriticBase(nn.Module, QValue):
         B = obs2.shape[0]
         out = torch.empty(E, B, N, device=self.device)
         mod = self.module
+        ws = self._workspace(B)
         _lib.check(_lib.lib().mb_critic_forward(
             ctypes.byref(mod.desc), _lib.ptr(mod.flat.data), _lib.ptr(obs2), _lib.ptr(act2),
-            self.observation_shape[0], self.action_shape[0], B, _lib.ptr(out), _lib.stream()))
+            self.observation_shape[0], self.action_shape[0], B, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+            _lib.stream()))
         return out
 
     def _ensemble_shaped(self, obs2, act2, lead):
@@ -127,6 +136,7 @@ class B200EnsembleQValue(_CriticBase):
         mod, dev = self.module, self.device
         B = obs2.shape[0]
         value = torch.empty(B, 1, device=dev)
+        ws = self._workspace(B)
         mem = rows = None
         if members is not None:
             mem = (ctypes.c_int32 * len(members))(*[int(i) for i in members])
@@ -141,7 +151,7 @@ class B200EnsembleQValue(_CriticBase):
             ctypes.byref(mod.desc), _lib.ptr(mod.flat.data), _lib.ptr(obs2), _lib.ptr(act2),
             self.observation_shape[0], self.action_shape[0], B, mem, _lib.ptr(rows), int(n_sub),
             _lib.REDUCE[mode], int(td is not None), _lib.ptr(r), _lib.ptr(t), _lib.ptr(lp), alpha, disc,
-            _lib.ptr(value), _lib.stream()))
+            _lib.ptr(value), _lib.ptr(ws), ws.numel(), _lib.stream()))
         return value
 
     def value(self, obs, action, sample_number=2, batchwise_sample=False, mode="min",
@@ -195,6 +205,7 @@ class B200TQCQValue(_CriticBase):
         B = obs2.shape[0]
         value = torch.empty(B, 1, device=dev)
         atoms = torch.empty(B, n_atom - n_drop, device=dev)
+        ws = self._workspace(B)
         r = t = lp = None
         alpha = disc = 0.0
         if td is not None:
@@ -204,7 +215,7 @@ class B200TQCQValue(_CriticBase):
             ctypes.byref(mod.desc), _lib.ptr(mod.flat.data), _lib.ptr(obs2), _lib.ptr(act2),
             self.observation_shape[0], self.action_shape[0], B, int(n_drop), int(td is not None),
             _lib.ptr(r), _lib.ptr(t), _lib.ptr(lp), alpha, disc, _lib.ptr(value), _lib.ptr(atoms),
-            _lib.stream()))
+            _lib.ptr(ws), ws.numel(), _lib.stream()))
         return value, atoms
 
     def value(self, obs, action, number_drop=None, percentage_drop=None, return_atoms=False,
