@@ -66,7 +66,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -134,6 +134,40 @@ def cpu_arm(steps, warmup, threads=None):
                       "%d states, %.2f s/step" % (steps, B, sec)}, sec
 
 
+def secondary_metrics(dev, world, rank, timed):
+    """Model-train samples/s (members sharded over ranks, no collective in the step) and
+    REDQ / TQC critic-target throughput at batch 256 (replicas), device-resident inputs."""
+    import mirl_b200
+    from mirl_b200.dist import member_partition
+    from tests.golden import cases
+    from tests.helpers_gpu import FakeEnv, make_critic, make_pe_model
+    from tests.util import T
+    E, B = 7, 256
+    m, _ = make_pe_model(cases.MBPO, 11, device=dev)
+    e0, e1 = member_partition(E, world)[rank]
+    out = {}
+    if e1 > e0:
+        tr = mirl_b200.B200PEModelTrainer(FakeEnv(), m, tb_log_freq=-1, silent=True, members=(e0, e1))
+        bt = {k: T(v, dev) for k, v in cases.train_batch(600, E, B).items()}
+        ms = timed(lambda: tr.train_step_async(bt), 200, 20) / 200
+    else:
+        ms = timed(lambda: None, 200, 20) / 200
+    out["model_train_samples_per_s"] = E * B / (ms * 1e-3)
+    out["model_train_ms_per_step"] = ms
+    out["model_train_config"] = "7 members x batch 256 (bootstrap batches), fused fwd+NLL+bwd+Adam, members sharded over %d GPU(s)" % world
+    q, _ = make_critic("redq", 71, device=dev)
+    t, _ = make_critic("tqc", 81, device=dev)
+    x = cases.critic_inputs(72, B)
+    o, a = T(x["obs"], dev), T(x["act"], dev)
+    r, d, lp = T(x["rewards"], dev), T(x["terminals"], dev), T(x["log_prob"], dev)
+    ms = timed(lambda: q.q_target(o, a, r, d, lp, alpha=0.2, sample_number=2, batchwise_sample=True), 200, 20) / 200
+    out["redq_targets_per_s"] = world * B / (ms * 1e-3)
+    ms = timed(lambda: t.atoms_target(o, a, r, d, lp, alpha=0.2, percentage_drop=8), 200, 20) / 200
+    out["tqc_targets_per_s"] = world * B / (ms * 1e-3)
+    out["critic_config"] = "batch 256; REDQ 10x(2x256) random-2 min + TD; TQC 5x(3x512)x25 drop 10 + TD; replicas"
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -154,7 +188,7 @@ def workload_config(n):
     return {"workload": "MBPO model rollout sweep point: %d start states/GPU x horizon %d, 7 members / "
                         "5 elites, 4x200 swish, obs17/act6, cheetah done" % (ROWS, HORIZON),
             "rows_per_gpu": ROWS, "horizon": HORIZON, "ensemble": 7, "elites": 5,
-            "parallelism": "rows sharded over %d GPU(s); transitions all-gathered" % n,
+            "parallelism": "rows sharded over %d GPU(s); transitions all-gathered per horizon step (NCCL, overlapped)" % n,
             "l2_policy": "inputs larger than L2 (%.0f MB of obs/act/noise per step)" %
                          (ROWS * HORIZON * (24 + 72 + 1) / 1e6 + ROWS * 68 / 1e6)}
 
@@ -162,7 +196,7 @@ def workload_config(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
@@ -186,6 +220,9 @@ def main():
         dist.barrier()
     from mirl_b200 import _lib
     L = _lib.lib()
+    if world > 1:
+        # leave a few SMs to the NCCL all-gather so it overlaps with the persistent rollout kernel
+        _lib.check(L.mb_set_reserved_sms(int(os.environ.get("MB_BENCH_RESERVED_SMS", 0))))
     model, _ = build_model(dev)
     kernel = model._resolve_kernel()
     B, H, O, A, D = ROWS, HORIZON, 17, 6, 18
@@ -198,18 +235,21 @@ def main():
     idx = torch.from_numpy(idx_host).to(dev)
     # replicated pool the generated transitions are gathered into (o, a, o', r, d = 42 floats)
     trans = torch.empty(H, B, 2 * O + A + 2, device=dev)
-    pool = torch.empty(world, H, B, 2 * O + A + 2, device=dev) if world > 1 else None
+    pool = torch.empty(H, world, B, 2 * O + A + 2, device=dev) if world > 1 else None
 
     def device_step():
         o = obs0
+        works = []
         for h in range(H):
             no, r, d, _ = model.step(o, acts[h], indices=idx[h], noise=noise[h])
             t = trans[h]
             t[:, :O] = o; t[:, O:O + A] = acts[h]; t[:, O + A:2 * O + A] = no
             t[:, 2 * O + A:2 * O + A + 1] = r; t[:, 2 * O + A + 1:] = d
             o = no
-        if world > 1:
-            dist.all_gather_into_tensor(pool.view(world, -1), trans.view(-1))
+            if world > 1:   # gather this horizon step's transitions while the next one computes
+                works.append(dist.all_gather_into_tensor(pool[h].view(world, -1), t.view(-1), async_op=True))
+        for w in works:
+            w.wait()
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -285,6 +325,9 @@ def main():
             with open(prof) as f:
                 roof["traffic"] = json.load(f).get(roof["kernel"])
 
+    # ---- secondary metrics of BASELINE.json: model-train samples/s, REDQ / TQC targets/s ----------
+    secondary = secondary_metrics(dev, world, rank, timed)
+
     if rank == 0:
         base, _ = cpu_arm(3, 1)
         launches_per_step = H * 4 + (1 if world > 1 else 0) * 0
@@ -293,7 +336,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(workload_config(world), kernel=kernel),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "roofline": roof, "cpu_baseline": base}
+                "roofline": roof, "cpu_baseline": base, "secondary": secondary}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

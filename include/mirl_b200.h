@@ -192,6 +192,11 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
 size_t mb_pe_tc_pack_bytes(const mb_pe_model* m);
 int mb_pe_tc_pack(const mb_pe_model* m, void* pack, void* stream);
 
+/* Persistent kernels launch one CTA per SM.  When a collective has to overlap with them (rollout
+ * sharded over GPUs: NCCL all-gather of the generated transitions), leave `n` SMs free for the
+ * communication kernels.  0 (default) = use every SM. */
+int mb_set_reserved_sms(int n);
+
 /* ---- instrumentation for bench.py's roofline leg (not used on the product path) ---------------
  * When enabled, mb_pe_rollout_step brackets its dominant kernel (the fused MLP kernel, not the
  * bucketing pre-pass) with CUDA events on `stream`; mb_profile_last_ms waits for the end event

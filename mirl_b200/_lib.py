@@ -71,6 +71,7 @@ SIGNATURES = {
                                      c_int, P, P, P, c_float, c_float, P, P, P, c_size_t, P]),
     "mb_pe_tc_pack_bytes": (c_size_t, [POINTER(PeModel)]),
     "mb_pe_tc_pack": (c_int, [POINTER(PeModel), P, P]),
+    "mb_set_reserved_sms": (c_int, [c_int]),
     "mb_profile_enable": (c_int, [c_int]),
     "mb_profile_last_ms": (c_int, [POINTER(c_float)]),
 }

@@ -48,6 +48,9 @@ int validate_model(const mb_pe_model* m, const char* who) {
     return MB_OK;
 }
 
+static int g_reserved_sms = 0;
+int reserved_sms() { return g_reserved_sms; }
+
 static bool g_prof_on = false;
 static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
 void prof_begin(cudaStream_t s) {
@@ -289,6 +292,12 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
     return launch_critic_tqc(*d, params, obs, act, obs_dim, act_dim, B, n_drop, td, reward, terminal, log_prob,
                              alpha, discount, value, atoms, usable_ws(d, B, workspace, workspace_bytes),
                              (cudaStream_t)stream);
+}
+
+int mb_set_reserved_sms(int n) {
+    MB_CHECK_ARG(n >= 0 && n <= 64, "mb_set_reserved_sms: %d outside [0,64]", n);
+    g_reserved_sms = n;
+    return MB_OK;
 }
 
 int mb_profile_enable(int on) {

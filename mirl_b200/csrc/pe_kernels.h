@@ -25,6 +25,8 @@ struct BucketPlan {
 size_t bucket_workspace_bytes(int64_t B, int TM);
 BucketPlan bucket_rows(const uint8_t* idx, int64_t B, int E, int TM, void* ws, cudaStream_t s);
 
+int reserved_sms();     // mb_set_reserved_sms (c_api.cu)
+
 // bench instrumentation (c_api.cu): events around the dominant rollout kernel when enabled
 void prof_begin(cudaStream_t s);
 void prof_end(cudaStream_t s);

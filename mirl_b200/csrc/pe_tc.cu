@@ -720,6 +720,7 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, con
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms -= reserved_sms();
     const int grid = p.max_tiles < sms ? p.max_tiles : sms;
     const char* dbg_env = getenv("MB_TC_DEBUG");        // timing experiments only (wrong numerics)
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
