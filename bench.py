@@ -188,7 +188,8 @@ def workload_config(n):
     return {"workload": "MBPO model rollout sweep point: %d start states/GPU x horizon %d, 7 members / "
                         "5 elites, 4x200 swish, obs17/act6, cheetah done" % (ROWS, HORIZON),
             "rows_per_gpu": ROWS, "horizon": HORIZON, "ensemble": 7, "elites": 5,
-            "parallelism": "rows sharded over %d GPU(s); transitions all-gathered per horizon step (NCCL, overlapped)" % n,
+            "parallelism": "rows sharded over %d GPU(s); every transition row is stored into all %d pool replicas "
+                           "by the rollout kernel itself (peer stores over NVLink), one 4-byte all-reduce per step" % (n, n),
             "l2_policy": "inputs larger than L2 (%.0f MB of obs/act/noise per step)" %
                          (ROWS * HORIZON * (24 + 72 + 1) / 1e6 + ROWS * 68 / 1e6)}
 
@@ -220,9 +221,6 @@ def main():
         dist.barrier()
     from mirl_b200 import _lib
     L = _lib.lib()
-    if world > 1:
-        # leave a few SMs to the NCCL all-gather so it overlaps with the persistent rollout kernel
-        _lib.check(L.mb_set_reserved_sms(int(os.environ.get("MB_BENCH_RESERVED_SMS", 0))))
     model, _ = build_model(dev)
     kernel = model._resolve_kernel()
     B, H, O, A, D = ROWS, HORIZON, 17, 6, 18
@@ -233,23 +231,19 @@ def main():
     rs = np.random.RandomState(99 + rank)
     idx_host = rs.choice(model.elite_indices, (H, B)).astype(np.uint8)
     idx = torch.from_numpy(idx_host).to(dev)
-    # replicated pool the generated transitions are gathered into (o, a, o', r, d = 42 floats)
-    trans = torch.empty(H, B, 2 * O + A + 2, device=dev)
-    pool = torch.empty(H, world, B, 2 * O + A + 2, device=dev) if world > 1 else None
+    # Model pool of generated transitions, rows [o | a | o' | r | d] (42 floats), replicated on every
+    # rank: [H][world][B] rows.  The rollout kernel writes each row into every replica from its
+    # epilogue (local HBM + peer-mapped NVLink stores), so there is no separate gather pass.
+    from mirl_b200.dist import PeerPools
+    pools = PeerPools(H * world * B, 2 * O + A + 2, device=dev)
+    dests = pools.destinations()
 
     def device_step():
         o = obs0
-        works = []
         for h in range(H):
-            no, r, d, _ = model.step(o, acts[h], indices=idx[h], noise=noise[h])
-            t = trans[h]
-            t[:, :O] = o; t[:, O:O + A] = acts[h]; t[:, O + A:2 * O + A] = no
-            t[:, 2 * O + A:2 * O + A + 1] = r; t[:, 2 * O + A + 1:] = d
-            o = no
-            if world > 1:   # gather this horizon step's transitions while the next one computes
-                works.append(dist.all_gather_into_tensor(pool[h].view(world, -1), t.view(-1), async_op=True))
-        for w in works:
-            w.wait()
+            o, _, _ = model.step_rows(o, acts[h], dests, row_offset=(h * world + rank) * B,
+                                      indices=idx[h], noise=noise[h])
+        pools.fence()     # N>1: one stream-ordered 4-byte all-reduce = every replica is complete
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -330,7 +324,7 @@ def main():
 
     if rank == 0:
         base, _ = cpu_arm(3, 1)
-        launches_per_step = H * 4 + (1 if world > 1 else 0) * 0
+        launches_per_step = H * 4
         line = {"metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -338,6 +332,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "roofline": roof, "cpu_baseline": base, "secondary": secondary}
         print(json.dumps(line))
+    pools.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

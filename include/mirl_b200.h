@@ -91,6 +91,19 @@ int mb_pe_rollout_step(const mb_pe_model* m, int kernel, const float* obs, const
                        float* next_obs, float* reward, float* done,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same step fused with the collector's pool-row assembly (MBPOCollector.add_sample,
+ * mbpo_collector.py:69-83): row b is written as [obs | act | next_obs | reward | done]
+ * (2*O + A + 2 floats) to row (row_offset + b) of EVERY destination in dst_host[n_dst] (host array
+ * of device pointers; 1..8).  Destinations may be peer-mapped buffers of other GPUs: the kernel
+ * then pushes the generated transitions over NVLink itself (stores from its epilogue warps), which
+ * replaces the all-gather of transitions into a replicated model pool.  obs / act may be strided
+ * row views (e.g. the next_obs columns of the previous step's rows): *_stride = floats per row. */
+int mb_pe_rollout_step_rows(const mb_pe_model* m, int kernel, const float* obs, int64_t obs_stride,
+                            const float* act, int64_t act_stride, const uint8_t* member_idx,
+                            const float* noise, int64_t B, int done_kind, float* const* dst_host,
+                            int n_dst, int64_t row_offset, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* PEModel.step(return_distribution=True) + MOPOCollector penalty (mopo_collector.py:42-53).
  * elites_host[n_elite]: elite member ids in RANK order (pe_model.py:234-237).
  * info tensors are [n_elite][B][.] in that order; any of them may be NULL.
@@ -191,6 +204,19 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
  * shared-memory layout the rollout kernel streams (rebuild after the weights change). */
 size_t mb_pe_tc_pack_bytes(const mb_pe_model* m);
 int mb_pe_tc_pack(const mb_pe_model* m, void* pack, void* stream);
+
+/* ---- peer-mapped pools: the multi-GPU destinations of mb_pe_rollout_step_rows -------------------
+ * One process per GPU.  Every rank allocates its replica of the model pool with
+ * mb_peer_pool_alloc (cudaMalloc + CUDA IPC export; `handle` receives MB_IPC_HANDLE_BYTES bytes),
+ * the ranks exchange the handles over any host channel (torch.distributed all_gather_object in
+ * mirl_b200.dist.PeerPools), and mb_peer_pool_open maps a peer's replica into this process
+ * (peer access over NVLink is enabled by the driver).  The mapped pointers are then passed as
+ * destinations; close every mapping before the owner frees its pool. */
+#define MB_IPC_HANDLE_BYTES 64
+int mb_peer_pool_alloc(size_t bytes, void** dev_ptr, unsigned char* handle);
+int mb_peer_pool_open(const unsigned char* handle, void** dev_ptr);
+int mb_peer_pool_close(void* dev_ptr);
+int mb_peer_pool_free(void* dev_ptr);
 
 /* Persistent kernels launch one CTA per SM.  When a collective has to overlap with them (rollout
  * sharded over GPUs: NCCL all-gather of the generated transitions), leave `n` SMs free for the

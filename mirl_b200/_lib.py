@@ -51,6 +51,8 @@ SIGNATURES = {
     "mb_pe_rollout_workspace_bytes": (c_size_t, [POINTER(PeModel), c_int64]),
     "mb_pe_rollout_step": (c_int, [POINTER(PeModel), c_int, P, P, P, P, c_int64, c_int, P, P, P,
                                    P, c_size_t, P]),
+    "mb_pe_rollout_step_rows": (c_int, [POINTER(PeModel), c_int, P, c_int64, P, c_int64, P, P, c_int64, c_int,
+                                        POINTER(c_void_p), c_int, c_int64, P, c_size_t, P]),
     "mb_pe_rollout_step_dist": (c_int, [POINTER(PeModel), P, P, P, P, c_int64, c_int,
                                         POINTER(c_int32), c_int, P, P, P, P, P, P, P, P, c_int,
                                         c_float, P, P, P]),
@@ -71,6 +73,10 @@ SIGNATURES = {
                                      c_int, P, P, P, c_float, c_float, P, P, P, c_size_t, P]),
     "mb_pe_tc_pack_bytes": (c_size_t, [POINTER(PeModel)]),
     "mb_pe_tc_pack": (c_int, [POINTER(PeModel), P, P]),
+    "mb_peer_pool_alloc": (c_int, [c_size_t, POINTER(c_void_p), ctypes.c_char_p]),
+    "mb_peer_pool_open": (c_int, [ctypes.c_char_p, POINTER(c_void_p)]),
+    "mb_peer_pool_close": (c_int, [P]),
+    "mb_peer_pool_free": (c_int, [P]),
     "mb_set_reserved_sms": (c_int, [c_int]),
     "mb_profile_enable": (c_int, [c_int]),
     "mb_profile_last_ms": (c_int, [POINTER(c_float)]),

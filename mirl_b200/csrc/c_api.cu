@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include "common.cuh"
+#include <cstring>
 #include "pe_kernels.h"
 #include "simt_mlp.cuh"
 
@@ -91,34 +92,63 @@ size_t mb_pe_rollout_workspace_bytes(const mb_pe_model* m, int64_t B) {
     return bucket_workspace_bytes(B < 1 ? 1 : B, 64);
 }
 
-int mb_pe_rollout_step(const mb_pe_model* m, int kernel, const float* obs, const float* act,
-                       const uint8_t* member_idx, const float* noise, int64_t B, int done_kind,
-                       float* next_obs, float* reward, float* done, void* workspace,
-                       size_t workspace_bytes, void* stream) {
-    int rc = validate_model(m, "mb_pe_rollout_step");
+static int rollout_common(const char* who, const mb_pe_model* m, int kernel, const float* obs, int64_t obs_stride,
+                          const float* act, int64_t act_stride, const uint8_t* member_idx, const float* noise,
+                          int64_t B, int done_kind, float* next_obs, float* reward, float* done,
+                          const RowsOut& rows, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate_model(m, who);
     if (rc) return rc;
-    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "mb_pe_rollout_step: B %lld out of range", (long long)B);
+    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "%s: B %lld out of range", who, (long long)B);
     if (B == 0) return MB_OK;
-    MB_CHECK_ARG(obs && act && member_idx && noise && next_obs && reward && done,
-                 "mb_pe_rollout_step: null tensor");
+    MB_CHECK_ARG(obs && act && member_idx && noise, "%s: null input tensor", who);
+    MB_CHECK_ARG(obs_stride >= m->obs_dim && act_stride >= m->act_dim, "%s: row strides smaller than the rows", who);
     MB_CHECK_ARG(done_kind >= MB_DONE_CHEETAH && done_kind <= MB_DONE_INVERTED_PENDULUM,
-                 "mb_pe_rollout_step: unknown done_kind %d", done_kind);
+                 "%s: unknown done_kind %d", who, done_kind);
     if (workspace == nullptr || workspace_bytes < mb_pe_rollout_workspace_bytes(m, B)) {
-        set_error("mb_pe_rollout_step: workspace %zu < %zu bytes", workspace_bytes,
-                  mb_pe_rollout_workspace_bytes(m, B));
+        set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, mb_pe_rollout_workspace_bytes(m, B));
         return MB_EWORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
     if (kernel == MB_KERNEL_SIMT)
-        return launch_pe_rollout_simt(to_dev(m), obs, act, member_idx, noise, B, done_kind, next_obs, reward,
-                                      done, workspace, s);
+        return launch_pe_rollout_simt(to_dev(m), obs, obs_stride, act, act_stride, member_idx, noise, B, done_kind,
+                                      next_obs, reward, done, rows, workspace, s);
     if (kernel == MB_KERNEL_TCGEN05) {
-        MB_CHECK_ARG(m->tc_pack != nullptr, "mb_pe_rollout_step: MB_KERNEL_TCGEN05 needs tc_pack");
-        return launch_pe_rollout_tc(to_dev(m), m->tc_pack, obs, act, member_idx, noise, B, done_kind, next_obs,
-                                    reward, done, workspace, s);
+        MB_CHECK_ARG(m->tc_pack != nullptr, "%s: MB_KERNEL_TCGEN05 needs tc_pack", who);
+        return launch_pe_rollout_tc(to_dev(m), m->tc_pack, obs, obs_stride, act, act_stride, member_idx, noise, B,
+                                    done_kind, next_obs, reward, done, rows, workspace, s);
     }
-    set_error("mb_pe_rollout_step: unknown kernel family %d", kernel);
+    set_error("%s: unknown kernel family %d", who, kernel);
     return MB_EINVAL;
+}
+
+int mb_pe_rollout_step(const mb_pe_model* m, int kernel, const float* obs, const float* act,
+                       const uint8_t* member_idx, const float* noise, int64_t B, int done_kind,
+                       float* next_obs, float* reward, float* done, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    MB_CHECK_ARG(next_obs && reward && done, "mb_pe_rollout_step: null output tensor");
+    RowsOut rows{};
+    return rollout_common("mb_pe_rollout_step", m, kernel, obs, m ? m->obs_dim : 0, act, m ? m->act_dim : 0,
+                          member_idx, noise, B, done_kind, next_obs, reward, done, rows, workspace,
+                          workspace_bytes, stream);
+}
+
+int mb_pe_rollout_step_rows(const mb_pe_model* m, int kernel, const float* obs, int64_t obs_stride,
+                            const float* act, int64_t act_stride, const uint8_t* member_idx,
+                            const float* noise, int64_t B, int done_kind, float* const* dst_host,
+                            int n_dst, int64_t row_offset, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    MB_CHECK_ARG(dst_host && n_dst >= 1 && n_dst <= kMaxRowDest, "mb_pe_rollout_step_rows: n_dst %d outside [1,%d]",
+                 n_dst, kMaxRowDest);
+    MB_CHECK_ARG(row_offset >= 0, "mb_pe_rollout_step_rows: negative row_offset");
+    RowsOut rows{};
+    rows.n = n_dst;
+    rows.row_offset = row_offset;
+    for (int i = 0; i < n_dst; ++i) {
+        MB_CHECK_ARG(dst_host[i] != nullptr, "mb_pe_rollout_step_rows: null destination %d", i);
+        rows.dst[i] = dst_host[i];
+    }
+    return rollout_common("mb_pe_rollout_step_rows", m, kernel, obs, obs_stride, act, act_stride, member_idx, noise,
+                          B, done_kind, nullptr, nullptr, nullptr, rows, workspace, workspace_bytes, stream);
 }
 
 int mb_pe_rollout_step_dist(const mb_pe_model* m, const float* obs, const float* act,
@@ -292,6 +322,65 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
     return launch_critic_tqc(*d, params, obs, act, obs_dim, act_dim, B, n_drop, td, reward, terminal, log_prob,
                              alpha, discount, value, atoms, usable_ws(d, B, workspace, workspace_bytes),
                              (cudaStream_t)stream);
+}
+
+// ---- peer-mapped pools (CUDA IPC): destinations of mb_pe_rollout_step_rows on other GPUs ---------
+int mb_peer_pool_alloc(size_t bytes, void** dev_ptr, unsigned char* handle) {
+    MB_CHECK_ARG(dev_ptr && handle && bytes > 0, "mb_peer_pool_alloc: null argument or zero size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(h) == MB_IPC_HANDLE_BYTES, "IPC handle size");
+        e = cudaIpcGetMemHandle(&h, p);
+        if (e == cudaSuccess) memcpy(handle, &h, sizeof(h));
+        else cudaFree(p);
+    }
+    if (e != cudaSuccess) {
+        set_error("mb_peer_pool_alloc(%zu): %s", bytes, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return MB_ECUDA;
+    }
+    *dev_ptr = p;
+    return MB_OK;
+}
+
+int mb_peer_pool_open(const unsigned char* handle, void** dev_ptr) {
+    MB_CHECK_ARG(dev_ptr && handle, "mb_peer_pool_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    // lazy peer access: the driver maps the exporting GPU's memory over NVLink / PCIe P2P
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        set_error("mb_peer_pool_open: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return MB_ECUDA;
+    }
+    *dev_ptr = p;
+    return MB_OK;
+}
+
+int mb_peer_pool_close(void* dev_ptr) {
+    if (dev_ptr == nullptr) return MB_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    if (e != cudaSuccess) {
+        set_error("mb_peer_pool_close: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return MB_ECUDA;
+    }
+    return MB_OK;
+}
+
+int mb_peer_pool_free(void* dev_ptr) {
+    if (dev_ptr == nullptr) return MB_OK;
+    cudaError_t e = cudaFree(dev_ptr);
+    if (e != cudaSuccess) {
+        set_error("mb_peer_pool_free: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return MB_ECUDA;
+    }
+    return MB_OK;
 }
 
 int mb_set_reserved_sms(int n) {

@@ -22,6 +22,17 @@ struct BucketPlan {
     int* ntiles;
     int max_tiles;
 };
+// Optional fused pool-row output of the rollout step: row b of the batch is written as
+// [obs | act | next_obs | reward | done] (2O+A+2 floats, mbpo_collector.py:69-83 field order) to
+// row (row_offset + b) of every destination -- the local pool and/or peer-mapped pools of the
+// other GPUs (stores over NVLink straight from the kernel, no collective call).
+constexpr int kMaxRowDest = 8;
+struct RowsOut {
+    float* dst[kMaxRowDest];
+    int n;                    // 0 = disabled
+    int64_t row_offset;
+};
+
 size_t bucket_workspace_bytes(int64_t B, int TM);
 BucketPlan bucket_rows(const uint8_t* idx, int64_t B, int E, int TM, void* ws, cudaStream_t s);
 
@@ -32,9 +43,10 @@ void prof_begin(cudaStream_t s);
 void prof_end(cudaStream_t s);
 
 // ---- SIMT fp32 family (pe_simt.cu)
-int launch_pe_rollout_simt(const PeDev& m, const float* obs, const float* act, const uint8_t* idx,
-                           const float* noise, int64_t B, int done_kind, float* next_obs,
-                           float* reward, float* done, void* ws, cudaStream_t s);
+int launch_pe_rollout_simt(const PeDev& m, const float* obs, int64_t obs_stride, const float* act,
+                           int64_t act_stride, const uint8_t* idx, const float* noise, int64_t B,
+                           int done_kind, float* next_obs, float* reward, float* done,
+                           const RowsOut& rows, void* ws, cudaStream_t s);
 int launch_pe_forward_simt(const PeDev& m, const float* obs, const float* act, int per_member,
                            int normalize, int64_t B, float* mean, float* logstd, const float* delta,
                            const float* reward, const float* done, int ignore_terminal,
@@ -50,9 +62,10 @@ int launch_pe_rollout_dist_simt(const PeDev& m, const int32_t* elites, int n_eli
 // ---- tcgen05 family (pe_tc.cu)
 size_t tc_pack_bytes(const mb_mlp_desc& d);
 int launch_tc_pack(const PeDev& m, void* pack, cudaStream_t s);
-int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, const float* act,
-                         const uint8_t* idx, const float* noise, int64_t B, int done_kind,
-                         float* next_obs, float* reward, float* done, void* ws, cudaStream_t s);
+int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, int64_t obs_stride,
+                         const float* act, int64_t act_stride, const uint8_t* idx, const float* noise,
+                         int64_t B, int done_kind, float* next_obs, float* reward, float* done,
+                         const RowsOut& rows, void* ws, cudaStream_t s);
 
 // ---- model training (pe_train.cu)
 size_t train_workspace_bytes(const mb_mlp_desc& d, int64_t B);

@@ -117,21 +117,26 @@ template <class Tile>
 __device__ __forceinline__ void stage_inputs(const PeDev& m, const float* __restrict__ obs,
                                              const float* __restrict__ act, int cnt,
                                              const int* __restrict__ rows, int64_t row0,
-                                             bool normalize, float* x0, float* raw_obs) {
+                                             bool normalize, float* x0, float* raw_obs,
+                                             int64_t obs_stride = -1, int64_t act_stride = -1,
+                                             float* raw_act = nullptr) {
     const int O = m.O, A = m.A, IN = O + A, IN4 = (IN + 3) & ~3;
     const float* nrm = m.norm;
+    if (obs_stride < 0) obs_stride = O;
+    if (act_stride < 0) act_stride = A;
     for (int t = threadIdx.x; t < Tile::TM * IN4; t += kSimtThreads) {
         const int i = t / IN4, j = t - i * IN4;
         float v = 0.f;
         if (i < cnt && j < IN) {
             const int64_t r = rows ? (int64_t)rows[i] : row0 + i;
             if (j < O) {
-                const float x = obs[r * O + j];
+                const float x = obs[r * obs_stride + j];
                 if (raw_obs) raw_obs[i * O + j] = x;
                 v = normalize ? (x - nrm[j]) / (nrm[O + j] + kNormEps) : x;
             } else {
                 const int k = j - O;
-                const float x = act[r * A + k];
+                const float x = act[r * act_stride + k];
+                if (raw_act) raw_act[i * A + k] = x;
                 v = normalize ? (x - nrm[2 * O + k]) / (nrm[2 * O + A + k] + kNormEps) : x;
             }
         }
@@ -143,11 +148,12 @@ __device__ __forceinline__ void stage_inputs(const PeDev& m, const float* __rest
 // Fused rollout step (one member per tile).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSimtThreads, 1)
-k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, const float* __restrict__ act,
+k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, int64_t obs_stride,
+                  const float* __restrict__ act, int64_t act_stride,
                   const float* __restrict__ noise, const int* __restrict__ perm,
                   const int4* __restrict__ tiles, const int* __restrict__ ntiles_p, int done_kind,
                   float* __restrict__ next_obs, float* __restrict__ reward,
-                  float* __restrict__ done) {
+                  float* __restrict__ done, RowsOut rows_out) {
     using Tile = SimtTile64;
     extern __shared__ __align__(16) float smem[];
     float* buf0 = smem;
@@ -155,7 +161,8 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, const float* __restric
     float* wbuf = buf1 + Tile::kActFloats;
     float* raw = wbuf + 2 * Tile::kWFloats;          // [TM][O] raw observations
     float* nob = raw + Tile::TM * m.O;               // [TM][O] next observations
-    const int O = m.O, D = O + 1;
+    float* rawa = nob + Tile::TM * m.O;              // [TM][A] raw actions (row output)
+    const int O = m.O, D = O + 1, A = m.A, W = 2 * m.O + m.A + 2;
     const int ntiles = *ntiles_p;
     const float* nrm = m.norm;
     const float* dmean = nrm + 2 * O + 2 * m.A;
@@ -167,7 +174,7 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, const float* __restric
         const int4 ti = tiles[tile];
         const int e = ti.x, cnt = ti.z;
         const int* rows = perm + ti.y;
-        stage_inputs<Tile>(m, obs, act, cnt, rows, 0, true, buf0, raw);
+        stage_inputs<Tile>(m, obs, act, cnt, rows, 0, true, buf0, raw, obs_stride, act_stride, rawa);
         __syncthreads();
         const float* res = Tile::forward(m.mlp, m.params, e, buf0, buf1, wbuf, nullptr, cnt);
         for (int t = threadIdx.x; t < cnt * D; t += kSimtThreads) {
@@ -180,13 +187,34 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, const float* __restric
                 const float delta = s * (dstd[j] + kNormEps) + dmean[j];
                 const float v = raw[i * O + j] + delta;
                 nob[i * O + j] = v;
-                next_obs[r * O + j] = v;
+                if (next_obs) next_obs[r * O + j] = v;
+#pragma unroll
+                for (int k = 0; k < kMaxRowDest; ++k) {
+                    if (k >= rows_out.n) continue;
+                    float* dst = rows_out.dst[k] + (size_t)(rows_out.row_offset + r) * W;
+                    dst[j] = raw[i * O + j];
+                    dst[O + A + j] = v;
+                }
             } else {
-                reward[r] = s;
+                if (reward) reward[r] = s;
+#pragma unroll
+                for (int k = 0; k < kMaxRowDest; ++k)
+                    if (k < rows_out.n) rows_out.dst[k][(size_t)(rows_out.row_offset + r) * W + 2 * O + A] = s;
             }
         }
         __syncthreads();
-        if (threadIdx.x < cnt) done[rows[threadIdx.x]] = done_fn(done_kind, nob + threadIdx.x * O, O);
+        if (threadIdx.x < cnt) {
+            const int64_t r = rows[threadIdx.x];
+            const float dn = done_fn(done_kind, nob + threadIdx.x * O, O);
+            if (done) done[r] = dn;
+#pragma unroll
+            for (int k = 0; k < kMaxRowDest; ++k) {
+                if (k >= rows_out.n) continue;
+                float* dst = rows_out.dst[k] + (size_t)(rows_out.row_offset + r) * W;
+                dst[2 * O + A + 1] = dn;
+                for (int j = 0; j < A; ++j) dst[O + j] = rawa[threadIdx.x * A + j];
+            }
+        }
         __syncthreads();
     }
 }
@@ -399,19 +427,21 @@ static int set_smem(K kernel, size_t bytes) {
     return MB_OK;
 }
 
-int launch_pe_rollout_simt(const PeDev& m, const float* obs, const float* act, const uint8_t* idx,
-                           const float* noise, int64_t B, int done_kind, float* next_obs,
-                           float* reward, float* done, void* ws, cudaStream_t s) {
+int launch_pe_rollout_simt(const PeDev& m, const float* obs, int64_t obs_stride, const float* act,
+                           int64_t act_stride, const uint8_t* idx, const float* noise, int64_t B,
+                           int done_kind, float* next_obs, float* reward, float* done,
+                           const RowsOut& rows, void* ws, cudaStream_t s) {
     using Tile = SimtTile64;
     BucketPlan p = bucket_rows(idx, B, m.mlp.ensemble_size, Tile::TM, ws, s);
     MB_CUDA_LAUNCH_CHECK("bucket_rows");
-    const size_t smem = Tile::kSmemBytes + (size_t)2 * Tile::TM * m.O * sizeof(float);
+    const size_t smem = Tile::kSmemBytes + (size_t)Tile::TM * (2 * m.O + m.A) * sizeof(float);
     int rc = set_smem(k_pe_rollout_simt, smem);
     if (rc) return rc;
     const int grid = (int)min((int64_t)p.max_tiles, (int64_t)sm_count() * 4);
     prof_begin(s);
-    k_pe_rollout_simt<<<grid, kSimtThreads, smem, s>>>(m, obs, act, noise, p.perm, p.tiles, p.ntiles,
-                                                       done_kind, next_obs, reward, done);
+    k_pe_rollout_simt<<<grid, kSimtThreads, smem, s>>>(m, obs, obs_stride, act, act_stride, noise, p.perm,
+                                                       p.tiles, p.ntiles, done_kind, next_obs, reward, done,
+                                                       rows);
     prof_end(s);
     MB_CUDA_LAUNCH_CHECK("k_pe_rollout_simt");
     return MB_OK;

@@ -95,8 +95,8 @@ static int ru16(int x) { return (x + 15) & ~15; }
 static size_t tc_smem_bytes(const TcShape& s, int O, int A) {
     size_t a = (size_t)2 * kTcTM * s.HP * 2;          // A hi + lo
     size_t ring = (size_t)s.stages * s.slot;
-    size_t misc = (size_t)kTcTM * ((O + A) + O + (O + 1)) * 4 + (size_t)(128 + 64) * 4 +
-                  1024;                               // staging, head obs, head noise, constants, barriers
+    size_t misc = (size_t)kTcTM * ((O + A) + ((2 * O + A + 2) | 1)) * 4 + (size_t)(128 + 64) * 4 +
+                  1024;              // staging, head pool rows, constants, barriers
     return a + ring + misc + 1024;                    // + alignment slack
 }
 
@@ -317,10 +317,11 @@ __device__ __forceinline__ float fast_clamp_logstd(float raw, float mx, float mn
 // ---- the kernel ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const float* __restrict__ obs,
-                const float* __restrict__ act, const float* __restrict__ noise,
+                int64_t obs_stride, const float* __restrict__ act, int64_t act_stride,
+                const float* __restrict__ noise,
                 const int* __restrict__ perm, const int4* __restrict__ tiles,
                 const int* __restrict__ ntiles_p, int done_kind, float* __restrict__ next_obs,
-                float* __restrict__ reward, float* __restrict__ done, int dbg) {
+                float* __restrict__ reward, float* __restrict__ done, RowsOut rows, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -331,14 +332,16 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     const uint32_t sRing = sA_lo + a_bytes;
     uint8_t* misc = smem + 2 * a_bytes + (size_t)s.stages * s.slot;
     float* xin = reinterpret_cast<float*>(misc);                  // [TM][O+A] staging: raw obs | act
-    float* hobs = xin + kTcTM * IN;                               // [TM][O] head: raw obs -> next obs
-    float* heps = hobs + kTcTM * O;                               // [TM][D] head: noise
+    // head: one pool row per batch row, [obs O | act A | noise D -> next_obs O, reward | done];
+    // odd row stride so that per-thread row accesses are bank-conflict free
+    const int W = 2 * O + A + 2, WS = W | 1;
+    float* hrow = xin + kTcTM * IN;                               // [TM][WS]
     // constants, padded to 32 so the consumers are branch-free:
     //   cmean/cinv[j]: input column j = [obs | act | ones | pad]: x_norm = (x - cmean) * cinv, with
     //                  cinv = 1/(std+eps); the ones column is (0 - (-1)) * 1, pads are (0 - 0) * 1
     //   dmean/dscale[j]: delta de-normalisation (delta_mean, delta_std+eps), 0 beyond O
     //   hc: [32 max_logstd | 32 min_logstd] of the head's member
-    float* cmean = heps + kTcTM * D;
+    float* cmean = hrow + kTcTM * WS;
     float* cinv = cmean + 32;
     float* dmean = cinv + 32;
     float* dscale = dmean + 32;
@@ -411,8 +414,8 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             const int4 ti = tiles[blockIdx.x + i * gridDim.x];
             const int xrow = row < ti.z ? perm[ti.y + row] : -1;
             if (xrow >= 0) {
-                const float* op = obs + (size_t)xrow * O;
-                const float* ap = act + (size_t)xrow * A;
+                const float* op = obs + (size_t)xrow * obs_stride;
+                const float* ap = act + (size_t)xrow * act_stride;
                 for (int j = 0; j < O; ++j) cp_async4(xr + j, op + j);
                 for (int j = 0; j < A; ++j) cp_async4(xr + O + j, ap + j);
             }
@@ -612,8 +615,9 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int ht = threadIdx.x - kTcHeadWarp0 * 32;            // 0..127 within the head group
-        float* epsr = heps + row * D;
-        float* ro = hobs + row * O;                                // raw obs in, next obs out
+        float* ro = hrow + row * WS;                               // raw obs
+        float* ra = ro + O;                                        // raw action (row output only)
+        float* epsr = ra + A;                                      // noise in; next obs | reward out
         for (int i = 0; i < n_my; ++i) {
             const int g = i * L + L - 1;
             const int4 ti = tiles[blockIdx.x + i * gridDim.x];
@@ -625,9 +629,13 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             if (ht < 64) cp_async4(hc + ht, hb + ht);
             if (r >= 0) {
                 const float* eps = noise + (size_t)r * D;
-                const float* op = obs + (size_t)r * O;
+                const float* op = obs + (size_t)r * obs_stride;
                 for (int j = 0; j < D; ++j) cp_async4(epsr + j, eps + j);
                 for (int j = 0; j < O; ++j) cp_async4(ro + j, op + j);
+                if (rows.n > 0) {
+                    const float* ap = act + (size_t)r * act_stride;
+                    for (int j = 0; j < A; ++j) cp_async4(ra + j, ap + j);
+                }
             }
             cp_async_commit();
             mbar_wait_relaxed(d_last, (uint32_t)i & 1u);
@@ -664,12 +672,44 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                         const float sv = e * __expf(ls) + mu;
                         const float o0 = in_o ? ro[j] : 0.f;
                         const float v = o0 + (sv * dscale[j] + dmean[j]);
-                        if (in_o) { ro[j] = v; next_obs[(size_t)r * O + j] = v; }
-                        if (r >= 0 && j == O) reward[r] = sv;
+                        // the consumed noise slot is recycled: epsr[0..O) <- next obs, epsr[O] <- reward
+                        if (in_o) { epsr[j] = v; if (next_obs) next_obs[(size_t)r * O + j] = v; }
+                        if (r >= 0 && j == O) { epsr[j] = sv; if (reward) reward[r] = sv; }
                     }
                 }
             }
-            if (r >= 0) done[r] = done_fn(done_kind, ro, O);
+            const float dn = r >= 0 ? done_fn(done_kind, epsr, O) : 0.f;
+            if (r >= 0 && done) done[r] = dn;
+            if (rows.n > 0) {
+                // Pool rows [obs | act | next_obs | reward | done]: one warp-wide store per row
+                // (2O+A+2 consecutive floats) to every destination, local or peer-mapped.
+                epsr[D] = dn;
+                __syncwarp();
+                for (int i2 = 0; i2 < 32; i2 += 4) {
+                    int gr[4];
+                    float v0[4], v1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        gr[u] = __shfl_sync(0xffffffffu, r, i2 + u);
+                        const float* src = hrow + (q * 32 + i2 + u) * WS;
+                        v0[u] = lane < W ? src[lane] : 0.f;                  // W <= 64 (O <= 31, O + A <= 31)
+                        v1[u] = lane + 32 < W ? src[lane + 32] : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (gr[u] < 0) continue;
+                        const size_t off = (size_t)(rows.row_offset + gr[u]) * W + lane;
+#pragma unroll
+                        for (int k = 0; k < kMaxRowDest; ++k) {
+                            if (k < rows.n) {
+                                if (lane < W) rows.dst[k][off] = v0[u];
+                                if (lane + 32 < W) rows.dst[k][off + 32] = v1[u];
+                            }
+                        }
+                    }
+                }
+                __syncwarp();          // rows are re-filled by this warp's next cp.async batch
+            }
             if (warp == kTcHeadWarp0) TL(i, 25);
         }
     }
@@ -703,9 +743,10 @@ int launch_tc_pack(const PeDev& m, void* pack, cudaStream_t st) {
     return MB_OK;
 }
 
-int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, const float* act,
-                         const uint8_t* idx, const float* noise, int64_t B, int done_kind,
-                         float* next_obs, float* reward, float* done, void* ws, cudaStream_t st) {
+int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, int64_t obs_stride,
+                         const float* act, int64_t act_stride, const uint8_t* idx, const float* noise,
+                         int64_t B, int done_kind, float* next_obs, float* reward, float* done,
+                         const RowsOut& rows, void* ws, cudaStream_t st) {
     TcShape s = tc_shape(m.mlp);
     if (!s.ok) { set_error("tcgen05 rollout kernel does not support this model shape"); return MB_EUNSUPPORTED; }
     BucketPlan p = bucket_rows(idx, B, m.mlp.ensemble_size, kTcTM, ws, st);
@@ -725,9 +766,9 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, con
     const char* dbg_env = getenv("MB_TC_DEBUG");        // timing experiments only (wrong numerics)
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     prof_begin(st);
-    k_pe_rollout_tc<<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, act, noise,
-                                                    p.perm, p.tiles, p.ntiles, done_kind, next_obs, reward, done,
-                                                    dbg);
+    k_pe_rollout_tc<<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, obs_stride,
+                                                    act, act_stride, noise, p.perm, p.tiles, p.ntiles, done_kind,
+                                                    next_obs, reward, done, rows, dbg);
     prof_end(st);
     MB_CUDA_LAUNCH_CHECK("k_pe_rollout_tc");
     return MB_OK;

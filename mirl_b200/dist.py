@@ -100,3 +100,83 @@ def all_gather_rows(t, group=None):
     recv = t.new_empty((ws * m,) + tuple(t.shape[1:]))
     dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
     return torch.cat([recv[r * m: r * m + c] for r, c in enumerate(counts)], dim=0)
+
+
+class _RawCudaArray:
+    """``__cuda_array_interface__`` view of a raw device pointer (memory owned elsewhere)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerPools:
+    """Replicated model pool filled by the rollout kernels themselves (north_star: "all-gather of
+    generated transitions into the model pool"; SURVEY §8e prefers epilogue peer stores).
+
+    Every rank owns one ``[rows, width]`` float32 replica (``.local``).  The replicas are exported
+    over CUDA IPC and mapped into every other process, so ``destinations()`` -- the local tensor
+    followed by the peers' mapped pointers -- can be handed to ``B200PEModel.step_rows``: each
+    rank's kernel then writes its rows into ALL replicas while it computes, over NVLink, and the
+    NCCL all-gather (which does not overlap with a persistent kernel) disappears.  A rank's rows
+    are complete everywhere after its stream has drained and the ranks have passed ``fence()``.
+    """
+
+    def __init__(self, rows, width, device=None, group=None):
+        import ctypes
+
+        from . import _lib
+        self._lib = _lib
+        L = _lib.lib()
+        self.rank, self.world = world()
+        self.group = group
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.rows, self.width = int(rows), int(width)
+        nbytes = self.rows * self.width * 4
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _lib.check(L.mb_peer_pool_alloc(nbytes, ctypes.byref(ptr), handle))
+        self._own = ptr.value
+        self.local = torch.as_tensor(_RawCudaArray(self._own, (self.rows, self.width)), device=self.device)
+        self.ptrs = [None] * self.world
+        self.ptrs[self.rank] = self._own
+        self._mapped = []
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            with torch.cuda.device(self.device):
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    p = ctypes.c_void_p()
+                    _lib.check(L.mb_peer_pool_open(h, ctypes.byref(p)))
+                    self.ptrs[r] = p.value
+                    self._mapped.append(p.value)
+
+    def destinations(self):
+        """Local replica first (a tensor, so step_rows can return views into it), then the peers."""
+        return [self.local] + [self.ptrs[r] for r in range(self.world) if r != self.rank]
+
+    def fence(self):
+        """All ranks' kernels issued so far have landed in every replica once this returns on the
+        current stream's timeline (stream-ordered all-reduce of one element = barrier)."""
+        if self.world > 1:
+            if not hasattr(self, "_flag"):
+                self._flag = torch.zeros(1, device=self.device)
+            dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        L = self._lib.lib()
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for p in self._mapped:
+            self._lib.check(L.mb_peer_pool_close(p))
+        self._mapped = []
+        if self.world > 1:
+            dist.barrier(group=self.group)       # nobody frees while a peer still maps it
+        if self._own is not None:
+            self.local = None
+            self._lib.check(L.mb_peer_pool_free(self._own))
+            self._own = None

@@ -300,6 +300,61 @@ class B200PEModel(Component, nn.Module):
             info["penalty"], info["penalized_reward"] = pen, pr
         return next_obs, reward, done, info
 
+    def row_width(self):
+        """Floats per pool row ``[obs | act | next_obs | reward | done]``."""
+        return 2 * self.obs_size + self.action_size + 2
+
+    def step_rows(self, obs, action, dest, row_offset=0, indices=None, noise=None):
+        """``PEModel.step`` fused with the collector's pool-row assembly (mbpo_collector.py:69-83):
+        row ``b`` of the batch lands as ``[obs | act | next_obs | reward | done]`` in row
+        ``row_offset + b`` of every buffer in ``dest``.
+
+        ``dest`` is one ``[rows, 2O+A+2]`` float32 CUDA tensor, or a list of up to 8 destinations
+        mixing tensors and raw device pointers (ints) -- peer-mapped pools of the other GPUs, which
+        the kernel fills over NVLink from its epilogue (see ``dist.PeerPools``).  ``obs`` /
+        ``action`` may be column slices of a previous step's rows (row stride > width), so a
+        horizon loop chains on the ``next_obs`` columns without a copy.  Returns the local
+        destination's ``(next_obs, reward, done)`` views when ``dest[0]`` is a tensor."""
+        dev = self.device
+        L = _lib.lib()
+        B, O, A, D = obs.shape[0], self.obs_size, self.action_size, self.obs_size + 1
+        W = self.row_width()
+        for t, w in ((obs, O), (action, A)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == w
+                    and (B == 0 or t.stride(1) == 1)):
+                raise ValueError("step_rows: obs/action must be float32 CUDA [B, width] with unit column stride")
+        dests = list(dest) if isinstance(dest, (list, tuple)) else [dest]
+        if not 1 <= len(dests) <= 8:
+            raise ValueError("step_rows: 1..8 destinations")
+        ptrs = []
+        for d in dests:
+            if torch.is_tensor(d):
+                if not (d.is_cuda and d.dtype == torch.float32 and d.dim() == 2 and d.shape[1] == W
+                        and d.is_contiguous() and d.shape[0] >= row_offset + B):
+                    raise ValueError(f"step_rows: destination must be contiguous float32 CUDA [>= {row_offset + B}, {W}]")
+                ptrs.append(d.data_ptr())
+            else:
+                ptrs.append(int(d))
+        idx = self._member_indices(B, indices)
+        if noise is None:
+            noise = torch.randn(B, D, device=dev)                     # pe_model.py:176
+        noise = _lib.f32(noise, dev)
+        assert noise.shape == (B, D) and idx.shape == (B,)
+        if B > 0:
+            kname = self._resolve_kernel()
+            pack = self._tc_pack() if kname == "tcgen05" else None
+            m = self._c_model(pack)
+            ws = self._workspace(L.mb_pe_rollout_workspace_bytes(ctypes.byref(m), B))
+            arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+            _lib.check(L.mb_pe_rollout_step_rows(
+                ctypes.byref(m), _lib.KERNEL[kname], obs.data_ptr(), obs.stride(0), action.data_ptr(),
+                action.stride(0), _lib.ptr(idx), _lib.ptr(noise), B, _lib.DONE_KIND[self.done_kind],
+                arr, len(ptrs), int(row_offset), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        if torch.is_tensor(dests[0]):
+            rows = dests[0][row_offset:row_offset + B]
+            return rows[:, O + A:2 * O + A], rows[:, 2 * O + A:2 * O + A + 1], rows[:, 2 * O + A + 1:]
+        return None
+
     def step_np(self, obs, action, **kwargs):
         """base_model.py:78-86."""
         dev = self.device

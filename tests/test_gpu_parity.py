@@ -261,6 +261,39 @@ def test_rollout_ragged_batches_match_oracle(B, kernel):
     assert outside == 0
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("env,B", [("hopper", 1), ("hopper", 129), ("cheetah", 5000), ("walker2d", 4099)])
+def test_step_rows_equals_step_plus_pool_assembly(env, B, kernel):
+    """The fused pool-row output is bit-identical to step() followed by the collector's
+    concatenation [o | a | o' | r | d] (mbpo_collector.py:69-83) -- in two destinations at a row
+    offset, and again when the next horizon step reads obs as a strided view of those rows."""
+    m, _ = make_pe_model(cases.MBPO, 11, env, kernel=kernel)
+    _kernel_or_skip(m, kernel)
+    m.remember_loss(LOSS_VEC7)
+    O, A = m.obs_size, m.action_size
+    W = m.row_width()
+    o, a = cases.rollout_inputs(300 + B, B, env=env)
+    o, a = T(o, "cuda"), T(a, "cuda")
+    rs = np.random.RandomState(B)
+    idx = rs.choice(m.elite_indices, B)
+    eps = T(rs.standard_normal((B, O + 1)).astype(np.float32), "cuda")
+    no, r, d, _ = m.step(o, a, indices=idx, noise=eps)
+    want = torch.cat([o, a, no, r, d], 1)
+    off = 7
+    dst = [torch.full((B + 11, W), -7.0, device="cuda") for _ in range(2)]
+    vno, vr, vd = m.step_rows(o, a, dst, row_offset=off, indices=idx, noise=eps)
+    for t in dst:
+        assert torch.equal(t[off:off + B], want)
+        assert float((t[:off] + 7).abs().sum()) == 0 and float((t[off + B:] + 7).abs().sum()) == 0
+    assert torch.equal(vno, no) and torch.equal(vr, r) and torch.equal(vd, d)
+    # chained step: obs is the next_obs column block of the rows just written (row stride W)
+    a2 = T(cases.rollout_inputs(301 + B, B, env=env)[1], "cuda")
+    no2, r2, d2, _ = m.step(no, a2, indices=idx, noise=eps)
+    dst2 = torch.empty(B, W, device="cuda")
+    m.step_rows(vno, a2, dst2, indices=idx, noise=eps)
+    assert torch.equal(dst2, torch.cat([no, a2, no2, r2, d2], 1))
+
+
 def test_rollout_empty_batch():
     m, _ = make_pe_model(cases.MBPO, 11)
     no, r, d, _ = m.step(torch.zeros(0, 17, device="cuda"), torch.zeros(0, 6, device="cuda"))
