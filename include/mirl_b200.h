@@ -91,6 +91,20 @@ int mb_pe_rollout_step(const mb_pe_model* m, int kernel, const float* obs, const
                        float* next_obs, float* reward, float* done,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Random-elite selection of PEModel.step, `np.random.choice(elite, B)` (pe_model.py:165-169), on
+ * the device and bit-exact with NumPy's legacy global RandomState: the MT19937 stream with
+ * randint's masked rejection.  mt_state is device uint32[627]: [0,624) key and [624] pos as
+ * returned by np.random.get_state(); both are advanced in place to where NumPy would be after the
+ * draws (write them back with np.random.set_state to keep host code reproducible), and
+ * [625],[626] receive the low/high word of the number of members produced.  That number is B
+ * unless the word budget of the workspace (expected attempts + 12 sigma) ran out -- then the
+ * caller draws the remaining B - produced members with a second call from the advanced state.
+ * elites_host: the n_elites (1..64) member ids in rank order (host memory).  member_idx: device
+ * u8[B].  workspace: device scratch of mb_pe_draw_members_workspace_bytes(B, n_elites). */
+size_t mb_pe_draw_members_workspace_bytes(int64_t B, int n_elites);
+int mb_pe_draw_members(uint32_t* mt_state, const uint8_t* elites_host, int n_elites, int64_t B,
+                       uint8_t* member_idx, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The same step fused with the collector's pool-row assembly (MBPOCollector.add_sample,
  * mbpo_collector.py:69-83): row b is written as [obs | act | next_obs | reward | done]
  * (2*O + A + 2 floats) to row (row_offset + b) of EVERY destination in dst_host[n_dst] (host array

@@ -324,6 +324,25 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
                              (cudaStream_t)stream);
 }
 
+size_t mb_pe_draw_members_workspace_bytes(int64_t B, int n_elites) {
+    if (B <= 0 || n_elites < 1 || n_elites > 64) return 0;
+    return draw_workspace_bytes(B, n_elites);
+}
+
+int mb_pe_draw_members(uint32_t* mt_state, const uint8_t* elites_host, int n_elites, int64_t B,
+                       uint8_t* member_idx, void* workspace, size_t workspace_bytes, void* stream) {
+    MB_CHECK_ARG(mt_state && elites_host && n_elites >= 1 && n_elites <= 64,
+                 "mb_pe_draw_members: need 1..64 elites and a state buffer (got %d)", n_elites);
+    MB_CHECK_ARG(B >= 0 && B <= (int64_t)1 << 28, "mb_pe_draw_members: B %lld out of range", (long long)B);
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(member_idx != nullptr, "mb_pe_draw_members: null output");
+    if (workspace == nullptr || workspace_bytes < draw_workspace_bytes(B, n_elites)) {
+        set_error("mb_pe_draw_members: workspace %zu < %zu bytes", workspace_bytes, draw_workspace_bytes(B, n_elites));
+        return MB_EWORKSPACE;
+    }
+    return launch_draw_members(mt_state, elites_host, n_elites, B, member_idx, workspace, (cudaStream_t)stream);
+}
+
 // ---- peer-mapped pools (CUDA IPC): destinations of mb_pe_rollout_step_rows on other GPUs ---------
 int mb_peer_pool_alloc(size_t bytes, void** dev_ptr, unsigned char* handle) {
     MB_CHECK_ARG(dev_ptr && handle && bytes > 0, "mb_peer_pool_alloc: null argument or zero size");

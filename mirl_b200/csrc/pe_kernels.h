@@ -33,6 +33,11 @@ struct RowsOut {
     int64_t row_offset;
 };
 
+// np.random.choice(elite, B) on the device, bit-exact with NumPy's legacy MT19937 stream (member_draw.cu)
+size_t draw_workspace_bytes(int64_t B, int n);
+int launch_draw_members(uint32_t* state, const uint8_t* elites, int n, int64_t B, uint8_t* out, void* ws,
+                        cudaStream_t s);
+
 size_t bucket_workspace_bytes(int64_t B, int TM);
 BucketPlan bucket_rows(const uint8_t* idx, int64_t B, int E, int TM, void* ws, cudaStream_t s);
 

@@ -294,6 +294,41 @@ def test_step_rows_equals_step_plus_pool_assembly(env, B, kernel):
     assert torch.equal(dst2, torch.cat([no, a2, no2, r2, d2], 1))
 
 
+@pytest.mark.parametrize("seed,elites,B", [(0, [3, 1, 5, 0, 6], 1000), (1, [2, 0, 1, 4, 3, 6, 5], 100003),
+                                           (5, [0, 1], 7), (9, [4], 10), (3, list(range(15)), 50000),
+                                           (7, [6, 2, 4, 1, 0], 1_000_000)])
+def test_device_member_draw_is_numpy_choice_bit_exact(seed, elites, B):
+    """draw_members == np.random.choice(elite, B) (pe_model.py:169) bit for bit, and the global
+    NumPy generator ends in the same state (next host draws agree, cached Gaussian included)."""
+    m, _ = make_pe_model(cases.SMALL, 11)            # only the elite list matters here
+    m.elite_indices = list(elites)
+    np.random.seed(seed)
+    np.random.standard_normal(3)                     # leaves a cached Gaussian in the state
+    st = np.random.get_state()
+    want = np.random.choice(elites, B)
+    want_next = np.random.standard_normal(5), np.random.randint(0, 1000, 5)
+    np.random.set_state(st)
+    got = m.draw_members(B)
+    got_next = np.random.standard_normal(5), np.random.randint(0, 1000, 5)
+    assert got.dtype == torch.uint8 and np.array_equal(got.cpu().numpy(), want.astype(np.uint8))
+    assert np.array_equal(want_next[0], got_next[0]) and np.array_equal(want_next[1], got_next[1])
+
+
+def test_step_draws_members_on_device_for_large_batches():
+    m, _ = make_pe_model(cases.MBPO, 11)
+    m.remember_loss(LOSS_VEC7)
+    B = m.device_draw_min_rows + 5
+    o, a = cases.rollout_inputs(77, B)
+    o, a = T(o, "cuda"), T(a, "cuda")
+    eps = torch.randn(B, 18, device="cuda")
+    np.random.seed(123)
+    idx = np.random.choice(m.elite_indices, B)
+    want = m.step(o, a, indices=idx, noise=eps)
+    np.random.seed(123)
+    got = m.step(o, a, noise=eps)
+    assert all(torch.equal(x, y) for x, y in zip(want[:3], got[:3]))
+
+
 def test_rollout_empty_batch():
     m, _ = make_pe_model(cases.MBPO, 11)
     no, r, d, _ = m.step(torch.zeros(0, 17, device="cuda"), torch.zeros(0, 6, device="cuda"))
