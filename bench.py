@@ -279,14 +279,30 @@ def main():
     np.random.seed(4321 + rank)
     torch.manual_seed(4321 + rank)
 
+    # Public-API loop a user writes: actions arrive from pinned host memory every horizon step, the
+    # model draws members (NumPy stream) and noise (torch) itself like PEModel.step, and every
+    # step's [next_obs | reward | done] goes back to pinned host memory.  The D2H of step h runs on
+    # a copy stream under the H2D + rollout of step h+1 (two row buffers).
+    W = 2 * O + A + 2
+    e2e_rows = torch.empty(2, B, W, device=dev)
+    copy_stream = torch.cuda.Stream(dev)
+    copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e_step():
+        main = torch.cuda.current_stream()
         o = h_obs0.to(dev, non_blocking=True)
         for h in range(H):
             a = h_acts[h].to(dev, non_blocking=True)
-            no, r, d, _ = model.step(o, a)          # draws indices (NumPy, host) and noise (torch)
-            h_out[h].copy_(torch.cat([no, r, d], dim=1), non_blocking=True)
-            o = no
-        torch.cuda.current_stream().synchronize()   # the caller owns the transitions now
+            buf = e2e_rows[h & 1]
+            main.wait_event(copy_done[h & 1])      # its previous contents have left for the host
+            o, _, _ = model.step_rows(o, a, buf)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                h_out[h].copy_(buf[:, O + A:], non_blocking=True)
+                copy_done[h & 1].record(copy_stream)
+        copy_stream.synchronize()                  # the caller owns the transitions now
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_ms = timed(e2e_step, e2e_steps, 3) / e2e_steps

@@ -146,6 +146,7 @@ class B200PEModel(Component, nn.Module):
         self._pack_cache = (None, None)
         self._ws = None
         self._draw_ws = None
+        self._draw_stream = None
 
     # ---- reference bookkeeping ---------------------------------------------------------------
     def remember_loss(self, loss):
@@ -253,25 +254,35 @@ class B200PEModel(Component, nn.Module):
         st = np.random.get_state()
         assert st[0] == "MT19937"
         key, pos = st[1], int(st[2])
-        out = torch.empty(B, dtype=torch.uint8, device=dev)
         el = bytes(int(e) for e in elite)
-        done = 0
-        while done < B:      # one pass unless the word budget (mean + 12 sigma attempts) ran out
-            host = np.zeros(627, dtype=np.uint32)
-            host[:624], host[624] = key, pos
-            state = torch.from_numpy(host.view(np.int32)).to(dev)
-            n = B - done
-            nbytes = L.mb_pe_draw_members_workspace_bytes(n, len(el))
-            if self._draw_ws is None or self._draw_ws.numel() < nbytes or self._draw_ws.device != dev:
-                self._draw_ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
-            _lib.check(L.mb_pe_draw_members(_lib.ptr(state), el, len(el), n, _lib.ptr(out[done:]),
-                                            _lib.ptr(self._draw_ws), self._draw_ws.numel(), _lib.stream()))
-            back = state.cpu().numpy().view(np.uint32)
-            if len(el) > 1:
-                key, pos = back[:624].copy(), int(back[624])
-            produced = int(back[625]) | (int(back[626]) << 32)
-            assert 0 < produced <= n
-            done += produced
+        # The draw depends on host state only, so it runs on its own stream: the state read-back
+        # below then waits for the draw kernels alone, not for rollout work queued earlier.
+        main = torch.cuda.current_stream(dev)
+        if self._draw_stream is None:
+            self._draw_stream = torch.cuda.Stream(dev)
+        side = self._draw_stream
+        with torch.cuda.stream(side):
+            out = torch.empty(B, dtype=torch.uint8, device=dev)
+            done = 0
+            while done < B:  # one pass unless the word budget (mean + 12 sigma attempts) ran out
+                host = np.zeros(627, dtype=np.uint32)
+                host[:624], host[624] = key, pos
+                state = torch.from_numpy(host.view(np.int32)).to(dev)
+                n = B - done
+                nbytes = L.mb_pe_draw_members_workspace_bytes(n, len(el))
+                if self._draw_ws is None or self._draw_ws.numel() < nbytes or self._draw_ws.device != dev:
+                    self._draw_ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
+                _lib.check(L.mb_pe_draw_members(_lib.ptr(state), el, len(el), n, _lib.ptr(out[done:]),
+                                                _lib.ptr(self._draw_ws), self._draw_ws.numel(),
+                                                ctypes.c_void_p(side.cuda_stream)))
+                back = state.cpu().numpy().view(np.uint32)
+                if len(el) > 1:
+                    key, pos = back[:624].copy(), int(back[624])
+                produced = int(back[625]) | (int(back[626]) << 32)
+                assert 0 < produced <= n
+                done += produced
+        main.wait_stream(side)
+        out.record_stream(main)
         np.random.set_state((st[0], key, pos, st[3], st[4]))
         return out
 
