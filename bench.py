@@ -307,7 +307,7 @@ def main():
     e2e_steps = max(2, min(args.steps, 5))
     e2e_ms = timed(e2e_step, e2e_steps, 3) / e2e_steps
     e2e = {"value": world * B * H / (e2e_ms * 1e-3), "unit": "transitions/s",
-           "h2d_bytes_per_step": B * O * 4 + H * B * (A * 4 + 1),
+           "h2d_bytes_per_step": B * O * 4 + H * (B * A * 4 + 627 * 4),
            "d2h_bytes_per_step": H * B * (O + 2) * 4, "ms_per_step": e2e_ms}
 
     # ---- roofline of the dominant kernel (events inside the C ABI around that kernel only) -------
@@ -340,7 +340,7 @@ def main():
 
     if rank == 0:
         base, _ = cpu_arm(3, 1)
-        launches_per_step = H * 4
+        launches_per_step = H * 2          # k_bucket + k_pe_rollout_tc per horizon step
         line = {"metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

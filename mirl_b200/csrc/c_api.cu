@@ -88,8 +88,8 @@ int64_t mb_mlp_param_count(const mb_mlp_desc* d, int probabilistic) {
 }
 
 size_t mb_pe_rollout_workspace_bytes(const mb_pe_model* m, int64_t B) {
-    (void)m;
-    return bucket_workspace_bytes(B < 1 ? 1 : B, 64);
+    if (m == nullptr) return 0;
+    return bucket_workspace_bytes(B < 1 ? 1 : B, m->mlp.ensemble_size);
 }
 
 static int rollout_common(const char* who, const mb_pe_model* m, int kernel, const float* obs, int64_t obs_stride,

@@ -14,14 +14,49 @@ struct PeDev {
     const float* norm;
 };
 
-// Rows grouped by drawn member: perm[start .. start+count) are the rows of tile t = tiles[t]
-// (x = member, y = start, z = count).  *ntiles is computed on the device (no host sync).
+// Rows grouped by drawn member.  Member e owns the segment perm[e * seg .. e * seg + totals[e])
+// (seg = batch size: a segment can never overflow), filled by ONE kernel: every block counts its
+// rows per member, reserves a range of each segment with one atomicAdd per member, and scatters.
+// Tiles are not materialised: a consumer CTA derives tile t -> (member, first row, count) from the
+// E totals (TileIndex below).  No host sync anywhere.
+constexpr int kMaxMembers = 32;
 struct BucketPlan {
     int* perm;
-    int4* tiles;
-    int* ntiles;
-    int max_tiles;
+    int* totals;        // [kMaxMembers] rows per member (device)
+    int64_t seg;        // segment stride in perm
+    int max_tiles;      // upper bound of the tile count (grid sizing)
 };
+
+#ifdef __CUDACC__
+struct TileIndex {
+    int toff[kMaxMembers + 1];      // first tile of member e; toff[E] = number of tiles
+    int total[kMaxMembers];
+};
+// Called by one full warp; the caller synchronises the CTA afterwards.
+__device__ __forceinline__ void tile_index_build(TileIndex& ti, const int* __restrict__ totals, int E, int TM) {
+    const int lane = threadIdx.x & 31;
+    const int tot = lane < E ? totals[lane] : 0;
+    int incl = (tot + TM - 1) / TM;
+    const int mine = incl;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    ti.total[lane] = tot;
+    ti.toff[lane] = incl - mine;
+    if (lane == 31) ti.toff[32] = incl;
+}
+// tile t -> (x = member, y = first row inside the member's segment, z = rows in the tile)
+__device__ __forceinline__ int4 tile_at(const TileIndex& ti, int TM, int t) {
+    int e = 0;
+    while (e + 1 < kMaxMembers && t >= ti.toff[e + 1]) ++e;
+    const int k = t - ti.toff[e];
+    const int left = ti.total[e] - k * TM;
+    return make_int4(e, k * TM, left < TM ? left : TM, 0);
+}
+#endif
+
 // Optional fused pool-row output of the rollout step: row b of the batch is written as
 // [obs | act | next_obs | reward | done] (2O+A+2 floats, mbpo_collector.py:69-83 field order) to
 // row (row_offset + b) of every destination -- the local pool and/or peer-mapped pools of the
@@ -38,7 +73,7 @@ size_t draw_workspace_bytes(int64_t B, int n);
 int launch_draw_members(uint32_t* state, const uint8_t* elites, int n, int64_t B, uint8_t* out, void* ws,
                         cudaStream_t s);
 
-size_t bucket_workspace_bytes(int64_t B, int TM);
+size_t bucket_workspace_bytes(int64_t B, int E);
 BucketPlan bucket_rows(const uint8_t* idx, int64_t B, int E, int TM, void* ws, cudaStream_t s);
 
 int reserved_sms();     // mb_set_reserved_sms (c_api.cu)

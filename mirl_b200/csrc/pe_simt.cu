@@ -16,97 +16,46 @@ namespace mb {
 constexpr int kBucketRows = 2048;   // rows per block
 constexpr int kMaxE = 32;
 
-__global__ void k_bucket_count(const uint8_t* __restrict__ idx, int64_t B, int* block_counts) {
-    __shared__ int hist[kMaxE];
+__global__ void __launch_bounds__(256)
+k_bucket(const uint8_t* __restrict__ idx, int64_t B, int E, int* __restrict__ totals, int* __restrict__ perm) {
+    __shared__ int hist[kMaxE], base[kMaxE];
     if (threadIdx.x < kMaxE) hist[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kBucketRows;
-    for (int i = threadIdx.x; i < kBucketRows; i += blockDim.x) {
-        int64_t r = base + i;
-        if (r < B) atomicAdd(&hist[idx[r] & (kMaxE - 1)], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x < kMaxE) block_counts[blockIdx.x * kMaxE + threadIdx.x] = hist[threadIdx.x];
-}
-
-// One block of 32 warps: warp e owns member e.
-__global__ void k_bucket_scan(const int* __restrict__ block_counts, int nblk, int E, int TM,
-                              int* block_base, int4* tiles, int* ntiles) {
-    __shared__ int total[kMaxE], moff[kMaxE + 1], toff[kMaxE + 1];
-    const int e = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int sum = 0;
-    for (int b = lane; b < nblk; b += 32) sum += block_counts[b * kMaxE + e];
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) total[e] = (e < E) ? sum : 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int m = 0, t = 0;
-        for (int i = 0; i < kMaxE; ++i) {
-            moff[i] = m; toff[i] = t;
-            m += total[i];
-            t += (total[i] + TM - 1) / TM;
-        }
-        moff[kMaxE] = m; toff[kMaxE] = t;
-        *ntiles = t;
-    }
-    __syncthreads();
-    int run = moff[e];
-    for (int b0 = 0; b0 < nblk; b0 += 32) {
-        int b = b0 + lane;
-        int c = (b < nblk) ? block_counts[b * kMaxE + e] : 0;
-        int incl = c;
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (b < nblk) block_base[b * kMaxE + e] = run + incl - c;
-        run += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    const int nt = toff[e + 1] - toff[e];
-    for (int t = lane; t < nt; t += 32)
-        tiles[toff[e] + t] = make_int4(e, moff[e] + t * TM, min(TM, total[e] - t * TM), 0);
-}
-
-__global__ void k_bucket_scatter(const uint8_t* __restrict__ idx, int64_t B,
-                                 const int* __restrict__ block_base, int* perm) {
-    __shared__ int cursor[kMaxE];
-    if (threadIdx.x < kMaxE) cursor[threadIdx.x] = block_base[blockIdx.x * kMaxE + threadIdx.x];
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kBucketRows;
-    for (int i = threadIdx.x; i < kBucketRows; i += blockDim.x) {
-        int64_t r = base + i;
+    const int64_t r0 = (int64_t)blockIdx.x * kBucketRows;
+    int e_of[kBucketRows / 256], rank[kBucketRows / 256];
+#pragma unroll
+    for (int k = 0; k < kBucketRows / 256; ++k) {
+        const int64_t r = r0 + k * 256 + threadIdx.x;
+        e_of[k] = -1;
         if (r < B) {
-            int pos = atomicAdd(&cursor[idx[r] & (kMaxE - 1)], 1);
-            perm[pos] = (int)r;
+            const int e = idx[r];
+            e_of[k] = e < E ? e : E - 1;         // out-of-range ids are clamped (memory safety)
+            rank[k] = atomicAdd(&hist[e_of[k]], 1);
         }
     }
+    __syncthreads();
+    if (threadIdx.x < kMaxE && hist[threadIdx.x] > 0)
+        base[threadIdx.x] = atomicAdd(&totals[threadIdx.x], hist[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBucketRows / 256; ++k)
+        if (e_of[k] >= 0) perm[(int64_t)e_of[k] * B + base[e_of[k]] + rank[k]] = (int)(r0 + k * 256 + threadIdx.x);
 }
 
-size_t bucket_workspace_bytes(int64_t B, int TM) {
-    const int64_t nblk = (B + kBucketRows - 1) / kBucketRows;
-    const int64_t max_tiles = (B + TM - 1) / TM + kMaxE;
-    size_t bytes = 0;
-    bytes += (size_t)nblk * kMaxE * 4 * 2;        // block_counts, block_base
-    bytes += 256;                                 // ntiles (+pad)
-    bytes += (size_t)max_tiles * sizeof(int4);    // tiles
-    bytes += (size_t)B * 4 + 256;                 // perm
-    return bytes + 1024;
+size_t bucket_workspace_bytes(int64_t B, int E) {
+    return 256 + (size_t)E * (size_t)B * 4 + 1024;         // totals | one segment per member
 }
 
 BucketPlan bucket_rows(const uint8_t* idx, int64_t B, int E, int TM, void* ws, cudaStream_t s) {
     BucketPlan p;
     const int nblk = (int)((B + kBucketRows - 1) / kBucketRows);
     char* w = reinterpret_cast<char*>(ws);
-    auto take = [&](size_t bytes) { char* r = w; w += (bytes + 255) & ~size_t(255); return r; };
-    int* block_counts = reinterpret_cast<int*>(take((size_t)nblk * kMaxE * 4));
-    int* block_base = reinterpret_cast<int*>(take((size_t)nblk * kMaxE * 4));
-    p.ntiles = reinterpret_cast<int*>(take(16));
+    p.totals = reinterpret_cast<int*>(w);
+    p.perm = reinterpret_cast<int*>(w + 256);
+    p.seg = B;
     p.max_tiles = (int)((B + TM - 1) / TM + E);
-    p.tiles = reinterpret_cast<int4*>(take((size_t)((B + TM - 1) / TM + kMaxE) * sizeof(int4)));
-    p.perm = reinterpret_cast<int*>(take((size_t)B * 4));
-    k_bucket_count<<<nblk, 256, 0, s>>>(idx, B, block_counts);
-    k_bucket_scan<<<1, 32 * kMaxE, 0, s>>>(block_counts, nblk, E, TM, block_base, p.tiles, p.ntiles);
-    k_bucket_scatter<<<nblk, 256, 0, s>>>(idx, B, block_base, p.perm);
+    cudaMemsetAsync(p.totals, 0, kMaxE * sizeof(int), s);
+    k_bucket<<<nblk, 256, 0, s>>>(idx, B, E, p.totals, p.perm);
     return p;
 }
 
@@ -151,10 +100,13 @@ __global__ void __launch_bounds__(kSimtThreads, 1)
 k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, int64_t obs_stride,
                   const float* __restrict__ act, int64_t act_stride,
                   const float* __restrict__ noise, const int* __restrict__ perm,
-                  const int4* __restrict__ tiles, const int* __restrict__ ntiles_p, int done_kind,
+                  const int* __restrict__ totals, int64_t seg, int done_kind,
                   float* __restrict__ next_obs, float* __restrict__ reward,
                   float* __restrict__ done, RowsOut rows_out) {
     using Tile = SimtTile64;
+    __shared__ TileIndex tix;
+    if (threadIdx.x < 32) tile_index_build(tix, totals, m.mlp.ensemble_size, Tile::TM);
+    __syncthreads();
     extern __shared__ __align__(16) float smem[];
     float* buf0 = smem;
     float* buf1 = buf0 + Tile::kActFloats;
@@ -163,7 +115,7 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, int64_t obs_stride,
     float* nob = raw + Tile::TM * m.O;               // [TM][O] next observations
     float* rawa = nob + Tile::TM * m.O;              // [TM][A] raw actions (row output)
     const int O = m.O, D = O + 1, A = m.A, W = 2 * m.O + m.A + 2;
-    const int ntiles = *ntiles_p;
+    const int ntiles = tix.toff[kMaxMembers];
     const float* nrm = m.norm;
     const float* dmean = nrm + 2 * O + 2 * m.A;
     const float* dstd = dmean + O;
@@ -171,9 +123,9 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, int64_t obs_stride,
     const float* mnp = m.params + logstd_offset(m.mlp, 1);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int4 ti = tiles[tile];
+        const int4 ti = tile_at(tix, Tile::TM, tile);
         const int e = ti.x, cnt = ti.z;
-        const int* rows = perm + ti.y;
+        const int* rows = perm + (size_t)e * seg + ti.y;
         stage_inputs<Tile>(m, obs, act, cnt, rows, 0, true, buf0, raw, obs_stride, act_stride, rawa);
         __syncthreads();
         const float* res = Tile::forward(m.mlp, m.params, e, buf0, buf1, wbuf, nullptr, cnt);
@@ -440,7 +392,7 @@ int launch_pe_rollout_simt(const PeDev& m, const float* obs, int64_t obs_stride,
     const int grid = (int)min((int64_t)p.max_tiles, (int64_t)sm_count() * 4);
     prof_begin(s);
     k_pe_rollout_simt<<<grid, kSimtThreads, smem, s>>>(m, obs, obs_stride, act, act_stride, noise, p.perm,
-                                                       p.tiles, p.ntiles, done_kind, next_obs, reward, done,
+                                                       p.totals, p.seg, done_kind, next_obs, reward, done,
                                                        rows);
     prof_end(s);
     MB_CUDA_LAUNCH_CHECK("k_pe_rollout_simt");

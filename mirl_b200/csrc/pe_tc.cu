@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const float* __restrict__ obs,
                 int64_t obs_stride, const float* __restrict__ act, int64_t act_stride,
                 const float* __restrict__ noise,
-                const int* __restrict__ perm, const int4* __restrict__ tiles,
-                const int* __restrict__ ntiles_p, int done_kind, float* __restrict__ next_obs,
+                const int* __restrict__ perm, const int* __restrict__ totals,
+                int64_t seg, int done_kind, float* __restrict__ next_obs,
                 float* __restrict__ reward, float* __restrict__ done, RowsOut rows, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -363,7 +363,10 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     do {                                                                                  \
         if ((dbg & 8) && blockIdx.x == 0 && (i) < 4 && lane == 0) tl[(i)][(slot)] = clock64(); \
     } while (0)
-    const int ntiles = *ntiles_p;
+    __shared__ TileIndex tix;
+    if (threadIdx.x < 32) tile_index_build(tix, totals, m.mlp.ensemble_size, kTcTM);
+    __syncthreads();
+    const int ntiles = tix.toff[kMaxMembers];
     const int n_my = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (threadIdx.x == 0) {
@@ -411,8 +414,8 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
         //   load_inputs : raw obs/act of this thread's row -> smem via cp.async (no registers held)
         //   stage_tile  : normalise, ones column, bf16 hi/lo split, layer-0 A operand, a_ready
         auto load_inputs = [&](int i) {
-            const int4 ti = tiles[blockIdx.x + i * gridDim.x];
-            const int xrow = row < ti.z ? perm[ti.y + row] : -1;
+            const int4 ti = tile_at(tix, kTcTM, blockIdx.x + i * gridDim.x);
+            const int xrow = row < ti.z ? perm[(size_t)ti.x * seg + ti.y + row] : -1;
             if (xrow >= 0) {
                 const float* op = obs + (size_t)xrow * obs_stride;
                 const float* ap = act + (size_t)xrow * act_stride;
@@ -584,7 +587,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             int stage = 0;
             uint32_t wphase = 0;
             for (int i = 0; i < n_my; ++i) {
-                const int e = tiles[blockIdx.x + i * gridDim.x].x;
+                const int e = tile_at(tix, kTcTM, blockIdx.x + i * gridDim.x).x;
                 const uint8_t* mp = pack + (size_t)e * s.member_bytes;
                 for (int l = 0; l < L; ++l) {
                     const int nks = tc_layer_nks(s, l);
@@ -620,8 +623,8 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
         float* epsr = ra + A;                                      // noise in; next obs | reward out
         for (int i = 0; i < n_my; ++i) {
             const int g = i * L + L - 1;
-            const int4 ti = tiles[blockIdx.x + i * gridDim.x];
-            const int r = row < ti.z ? perm[ti.y + row] : -1;
+            const int4 ti = tile_at(tix, kTcTM, blockIdx.x + i * gridDim.x);
+            const int r = row < ti.z ? perm[(size_t)ti.x * seg + ti.y + row] : -1;
             // [32 max_logstd | 32 min_logstd] of the tile's member -> hc (all four head warps are
             // past the previous tile's use of hc once they meet at the named barrier below)
             const float* hb = reinterpret_cast<const float*>(pack + (size_t)ti.x * s.member_bytes + s.const_off);
@@ -767,7 +770,7 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, int
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     prof_begin(st);
     k_pe_rollout_tc<<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, obs_stride,
-                                                    act, act_stride, noise, p.perm, p.tiles, p.ntiles, done_kind,
+                                                    act, act_stride, noise, p.perm, p.totals, p.seg, done_kind,
                                                     next_obs, reward, done, rows, dbg);
     prof_end(st);
     MB_CUDA_LAUNCH_CHECK("k_pe_rollout_tc");
