@@ -235,14 +235,16 @@ def main():
     # rank: [H][world][B] rows.  The rollout kernel writes each row into every replica from its
     # epilogue (local HBM + peer-mapped NVLink stores), so there is no separate gather pass.
     from mirl_b200.dist import PeerPools
-    pools = PeerPools(H * world * B, 2 * O + A + 2, device=dev)
+    pools = PeerPools(H * world * B, model.row_stride(), device=dev)     # 44-float rows (16-byte aligned)
     dests = pools.destinations()
 
     def device_step():
         o = obs0
         for h in range(H):
+            # bucket order: a pool is a bag of samples, and a 128-row tile then leaves the SM as
+            # one bulk copy per replica; the next step chains on the next_obs columns in place
             o, _, _ = model.step_rows(o, acts[h], dests, row_offset=(h * world + rank) * B,
-                                      indices=idx[h], noise=noise[h])
+                                      indices=idx[h], noise=noise[h], ordered=False)
         pools.fence()     # N>1: one stream-ordered 4-byte all-reduce = every replica is complete
 
     def timed(fn, steps, warmup):

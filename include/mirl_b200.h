@@ -106,17 +106,25 @@ int mb_pe_draw_members(uint32_t* mt_state, const uint8_t* elites_host, int n_eli
                        uint8_t* member_idx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The same step fused with the collector's pool-row assembly (MBPOCollector.add_sample,
- * mbpo_collector.py:69-83): row b is written as [obs | act | next_obs | reward | done]
- * (2*O + A + 2 floats) to row (row_offset + b) of EVERY destination in dst_host[n_dst] (host array
+ * mbpo_collector.py:69-83): every transition is written as one row
+ * [obs | act | next_obs | reward | done | zero padding] of row_stride floats
+ * (2*O + A + 2 <= row_stride <= 2*O + A + 10) into EVERY destination in dst_host[n_dst] (host array
  * of device pointers; 1..8).  Destinations may be peer-mapped buffers of other GPUs: the kernel
- * then pushes the generated transitions over NVLink itself (stores from its epilogue warps), which
- * replaces the all-gather of transitions into a replicated model pool.  obs / act may be strided
- * row views (e.g. the next_obs columns of the previous step's rows): *_stride = floats per row. */
+ * then pushes the generated transitions over NVLink itself, which replaces the all-gather of
+ * transitions into a replicated model pool.
+ *   ordered = 1: batch row b lands in row (row_offset + b) (warp-wide stores per row).
+ *   ordered = 0: rows land in bucket order -- grouped by drawn member, order inside a group
+ *                unspecified, rows [row_offset, row_offset + B) all filled.  A pool is a bag of
+ *                samples, so this is the mode the collectors use: a tile of 128 rows is then
+ *                contiguous and leaves as ONE bulk copy per destination.  Needs row_stride % 4 == 0
+ *                and 16-byte aligned destinations.
+ * obs / act may be strided row views (e.g. the next_obs columns of the previous step's rows):
+ * *_stride = floats per row. */
 int mb_pe_rollout_step_rows(const mb_pe_model* m, int kernel, const float* obs, int64_t obs_stride,
                             const float* act, int64_t act_stride, const uint8_t* member_idx,
                             const float* noise, int64_t B, int done_kind, float* const* dst_host,
-                            int n_dst, int64_t row_offset, void* workspace, size_t workspace_bytes,
-                            void* stream);
+                            int n_dst, int64_t row_stride, int64_t row_offset, int ordered,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* PEModel.step(return_distribution=True) + MOPOCollector penalty (mopo_collector.py:42-53).
  * elites_host[n_elite]: elite member ids in RANK order (pe_model.py:234-237).

@@ -135,16 +135,28 @@ int mb_pe_rollout_step(const mb_pe_model* m, int kernel, const float* obs, const
 int mb_pe_rollout_step_rows(const mb_pe_model* m, int kernel, const float* obs, int64_t obs_stride,
                             const float* act, int64_t act_stride, const uint8_t* member_idx,
                             const float* noise, int64_t B, int done_kind, float* const* dst_host,
-                            int n_dst, int64_t row_offset, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            int n_dst, int64_t row_stride, int64_t row_offset, int ordered,
+                            void* workspace, size_t workspace_bytes, void* stream) {
     MB_CHECK_ARG(dst_host && n_dst >= 1 && n_dst <= kMaxRowDest, "mb_pe_rollout_step_rows: n_dst %d outside [1,%d]",
                  n_dst, kMaxRowDest);
     MB_CHECK_ARG(row_offset >= 0, "mb_pe_rollout_step_rows: negative row_offset");
+    MB_CHECK_ARG(m != nullptr, "mb_pe_rollout_step_rows: null model");
+    const int64_t W = 2 * (int64_t)m->obs_dim + m->act_dim + 2;
+    MB_CHECK_ARG(row_stride >= W && row_stride <= W + kRowPadMax,
+                 "mb_pe_rollout_step_rows: row_stride %lld outside [%lld,%lld]", (long long)row_stride, (long long)W,
+                 (long long)(W + kRowPadMax));
+    // bucket order moves whole tiles by 16-byte-granular bulk copies
+    MB_CHECK_ARG(ordered || row_stride % 4 == 0, "mb_pe_rollout_step_rows: ordered=0 needs row_stride %% 4 == 0 (got %lld)",
+                 (long long)row_stride);
     RowsOut rows{};
     rows.n = n_dst;
     rows.row_offset = row_offset;
+    rows.stride = row_stride;
+    rows.ordered = ordered ? 1 : 0;
     for (int i = 0; i < n_dst; ++i) {
         MB_CHECK_ARG(dst_host[i] != nullptr, "mb_pe_rollout_step_rows: null destination %d", i);
+        MB_CHECK_ARG(ordered || (reinterpret_cast<uintptr_t>(dst_host[i]) & 15) == 0,
+                     "mb_pe_rollout_step_rows: ordered=0 needs 16-byte aligned destinations");
         rows.dst[i] = dst_host[i];
     }
     return rollout_common("mb_pe_rollout_step_rows", m, kernel, obs, obs_stride, act, act_stride, member_idx, noise,

@@ -31,6 +31,7 @@ struct BucketPlan {
 struct TileIndex {
     int toff[kMaxMembers + 1];      // first tile of member e; toff[E] = number of tiles
     int total[kMaxMembers];
+    int roff[kMaxMembers];          // rows of members < e: position of member e in bucket order
 };
 // Called by one full warp; the caller synchronises the CTA afterwards.
 __device__ __forceinline__ void tile_index_build(TileIndex& ti, const int* __restrict__ totals, int E, int TM) {
@@ -43,8 +44,15 @@ __device__ __forceinline__ void tile_index_build(TileIndex& ti, const int* __res
         const int up = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += up;
     }
+    int rincl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, rincl, d);
+        if (lane >= d) rincl += up;
+    }
     ti.total[lane] = tot;
     ti.toff[lane] = incl - mine;
+    ti.roff[lane] = rincl - tot;
     if (lane == 31) ti.toff[32] = incl;
 }
 // tile t -> (x = member, y = first row inside the member's segment, z = rows in the tile)
@@ -62,10 +70,15 @@ __device__ __forceinline__ int4 tile_at(const TileIndex& ti, int TM, int t) {
 // row (row_offset + b) of every destination -- the local pool and/or peer-mapped pools of the
 // other GPUs (stores over NVLink straight from the kernel, no collective call).
 constexpr int kMaxRowDest = 8;
+constexpr int kRowPadMax = 8;       // destination row stride <= 2O+A+2 + kRowPadMax floats
 struct RowsOut {
     float* dst[kMaxRowDest];
     int n;                    // 0 = disabled
     int64_t row_offset;
+    int64_t stride;           // floats per destination row (>= 2O+A+2; columns beyond are zero-filled)
+    int ordered;              // 1: batch row b -> row_offset + b.  0: bucket order (rows grouped by
+                              //    drawn member, order inside a group unspecified) -- whole tiles are
+                              //    then contiguous and leave as one bulk copy per destination
 };
 
 // np.random.choice(elite, B) on the device, bit-exact with NumPy's legacy MT19937 stream (member_draw.cu)

@@ -114,7 +114,8 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, int64_t obs_stride,
     float* raw = wbuf + 2 * Tile::kWFloats;          // [TM][O] raw observations
     float* nob = raw + Tile::TM * m.O;               // [TM][O] next observations
     float* rawa = nob + Tile::TM * m.O;              // [TM][A] raw actions (row output)
-    const int O = m.O, D = O + 1, A = m.A, W = 2 * m.O + m.A + 2;
+    const int O = m.O, D = O + 1, A = m.A;
+    const int64_t W = rows_out.stride;               // destination row stride (floats)
     const int ntiles = tix.toff[kMaxMembers];
     const float* nrm = m.norm;
     const float* dmean = nrm + 2 * O + 2 * m.A;
@@ -132,6 +133,8 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, int64_t obs_stride,
         for (int t = threadIdx.x; t < cnt * D; t += kSimtThreads) {
             const int i = t / D, j = t - i * D;
             const int64_t r = rows[i];
+            // destination row: batch order, or bucket order (position of the row in its tile)
+            const int64_t dr = rows_out.row_offset + (rows_out.ordered ? r : (int64_t)tix.roff[e] + ti.y + i);
             const float mu = res[i * Tile::AS + j];
             const float ls = clamp_logstd(res[i * Tile::AS + D + j], mxp[e * D + j], mnp[e * D + j]);
             const float s = noise[r * D + j] * expf(ls) + mu;
@@ -143,7 +146,7 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, int64_t obs_stride,
 #pragma unroll
                 for (int k = 0; k < kMaxRowDest; ++k) {
                     if (k >= rows_out.n) continue;
-                    float* dst = rows_out.dst[k] + (size_t)(rows_out.row_offset + r) * W;
+                    float* dst = rows_out.dst[k] + (size_t)dr * W;
                     dst[j] = raw[i * O + j];
                     dst[O + A + j] = v;
                 }
@@ -151,20 +154,23 @@ k_pe_rollout_simt(PeDev m, const float* __restrict__ obs, int64_t obs_stride,
                 if (reward) reward[r] = s;
 #pragma unroll
                 for (int k = 0; k < kMaxRowDest; ++k)
-                    if (k < rows_out.n) rows_out.dst[k][(size_t)(rows_out.row_offset + r) * W + 2 * O + A] = s;
+                    if (k < rows_out.n) rows_out.dst[k][(size_t)dr * W + 2 * O + A] = s;
             }
         }
         __syncthreads();
         if (threadIdx.x < cnt) {
             const int64_t r = rows[threadIdx.x];
+            const int64_t dr = rows_out.row_offset +
+                               (rows_out.ordered ? r : (int64_t)tix.roff[e] + ti.y + (int64_t)threadIdx.x);
             const float dn = done_fn(done_kind, nob + threadIdx.x * O, O);
             if (done) done[r] = dn;
 #pragma unroll
             for (int k = 0; k < kMaxRowDest; ++k) {
                 if (k >= rows_out.n) continue;
-                float* dst = rows_out.dst[k] + (size_t)(rows_out.row_offset + r) * W;
+                float* dst = rows_out.dst[k] + (size_t)dr * W;
                 dst[2 * O + A + 1] = dn;
                 for (int j = 0; j < A; ++j) dst[O + j] = rawa[threadIdx.x * A + j];
+                for (int j = 2 * O + A + 2; j < W; ++j) dst[j] = 0.f;          // row padding
             }
         }
         __syncthreads();

@@ -92,11 +92,12 @@ __host__ __device__ inline int64_t tc_layer_off(const TcShape& s, int l) {
 
 static int ru16(int x) { return (x + 15) & ~15; }
 
+
 static size_t tc_smem_bytes(const TcShape& s, int O, int A) {
     size_t a = (size_t)2 * kTcTM * s.HP * 2;          // A hi + lo
     size_t ring = (size_t)s.stages * s.slot;
-    size_t misc = (size_t)kTcTM * ((O + A) + ((2 * O + A + 2) | 1)) * 4 + (size_t)(128 + 64) * 4 +
-                  1024;              // staging, head pool rows, constants, barriers
+    size_t misc = (size_t)kTcTM * ((O + A) + (2 * O + A + 2 + kRowPadMax)) * 4 + (size_t)(128 + 64) * 4 +
+                  1024;              // staging, head pool rows (any allowed row stride), constants, barriers
     return a + ring + misc + 1024;                    // + alignment slack
 }
 
@@ -332,9 +333,12 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     const uint32_t sRing = sA_lo + a_bytes;
     uint8_t* misc = smem + 2 * a_bytes + (size_t)s.stages * s.slot;
     float* xin = reinterpret_cast<float*>(misc);                  // [TM][O+A] staging: raw obs | act
-    // head: one pool row per batch row, [obs O | act A | noise D -> next_obs O, reward | done];
-    // odd row stride so that per-thread row accesses are bank-conflict free
-    const int W = 2 * O + A + 2, WS = W | 1;
+    // head: one pool row per batch row, [obs O | act A | noise D -> next_obs O, reward | done].
+    // Odd row stride (conflict-free per-thread rows) unless whole tiles leave by bulk copy: then
+    // the rows are laid out exactly like the destination (stride = destination row stride).
+    const int W = 2 * O + A + 2;
+    const bool bulk_rows = rows.n > 0 && !rows.ordered;
+    const int WS = bulk_rows ? (int)rows.stride : (W | 1);
     float* hrow = xin + kTcTM * IN;                               // [TM][WS]
     // constants, padded to 32 so the consumers are branch-free:
     //   cmean/cinv[j]: input column j = [obs | act | ones | pad]: x_norm = (x - cmean) * cinv, with
@@ -621,10 +625,14 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
         float* ro = hrow + row * WS;                               // raw obs
         float* ra = ro + O;                                        // raw action (row output only)
         float* epsr = ra + A;                                      // noise in; next obs | reward out
+        if (bulk_rows)
+            for (int j = W; j < WS; ++j) ro[j] = 0.f;              // row padding, never overwritten
         for (int i = 0; i < n_my; ++i) {
             const int g = i * L + L - 1;
             const int4 ti = tile_at(tix, kTcTM, blockIdx.x + i * gridDim.x);
             const int r = row < ti.z ? perm[(size_t)ti.x * seg + ti.y + row] : -1;
+            // the previous tile's rows must have left shared memory before they are refilled
+            if (bulk_rows && ht == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             // [32 max_logstd | 32 min_logstd] of the tile's member -> hc (all four head warps are
             // past the previous tile's use of hc once they meet at the named barrier below)
             const float* hb = reinterpret_cast<const float*>(pack + (size_t)ti.x * s.member_bytes + s.const_off);
@@ -683,11 +691,30 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             }
             const float dn = r >= 0 ? done_fn(done_kind, epsr, O) : 0.f;
             if (r >= 0 && done) done[r] = dn;
-            if (rows.n > 0) {
-                // Pool rows [obs | act | next_obs | reward | done]: one warp-wide store per row
-                // (2O+A+2 consecutive floats) to every destination, local or peer-mapped.
+            if (bulk_rows) {
+                // Bucket-order output: the tile's rows are consecutive in every destination, so
+                // the whole tile leaves as ONE bulk copy (TMA) per destination -- local HBM or a
+                // peer GPU's pool over NVLink -- issued by one thread; the copy engine streams it
+                // while the head warps go on to the next tile.
+                epsr[D] = dn;
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (ht == 0) {
+                    const size_t first = (size_t)(rows.row_offset + tix.roff[ti.x] + ti.y) * (size_t)WS;
+                    const uint32_t bytes = (uint32_t)ti.z * (uint32_t)WS * 4u;
+#pragma unroll
+                    for (int k = 0; k < kMaxRowDest; ++k)
+                        if (k < rows.n)
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                         ::"l"(rows.dst[k] + first), "r"(smem_u32(hrow)), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (rows.n > 0) {
+                // Batch-order output [obs | act | next_obs | reward | done | 0-padding]: warp-wide
+                // stores of each row to every destination, local or peer-mapped.
                 epsr[D] = dn;
                 __syncwarp();
+                const int S = (int)rows.stride;                            // <= W + kRowPadMax <= 72
                 for (int i2 = 0; i2 < 32; i2 += 4) {
                     int gr[4];
                     float v0[4], v1[4];
@@ -701,12 +728,13 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         if (gr[u] < 0) continue;
-                        const size_t off = (size_t)(rows.row_offset + gr[u]) * W + lane;
+                        const size_t off = (size_t)(rows.row_offset + gr[u]) * (size_t)S + lane;
 #pragma unroll
                         for (int k = 0; k < kMaxRowDest; ++k) {
                             if (k < rows.n) {
-                                if (lane < W) rows.dst[k][off] = v0[u];
-                                if (lane + 32 < W) rows.dst[k][off + 32] = v1[u];
+                                if (lane < S) rows.dst[k][off] = v0[u];
+                                if (lane + 32 < S) rows.dst[k][off + 32] = v1[u];
+                                if (lane + 64 < S) rows.dst[k][off + 64] = 0.f;
                             }
                         }
                     }
@@ -715,6 +743,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             }
             if (warp == kTcHeadWarp0) TL(i, 25);
         }
+        if (bulk_rows && ht == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();

@@ -358,16 +358,25 @@ class B200PEModel(Component, nn.Module):
         """Floats per pool row ``[obs | act | next_obs | reward | done]``."""
         return 2 * self.obs_size + self.action_size + 2
 
-    def step_rows(self, obs, action, dest, row_offset=0, indices=None, noise=None):
-        """``PEModel.step`` fused with the collector's pool-row assembly (mbpo_collector.py:69-83):
-        row ``b`` of the batch lands as ``[obs | act | next_obs | reward | done]`` in row
-        ``row_offset + b`` of every buffer in ``dest``.
+    def row_stride(self):
+        """Row width rounded up to 16 bytes: the stride a device pool needs for bucket-order
+        (bulk-copy) output."""
+        return (self.row_width() + 3) // 4 * 4
 
-        ``dest`` is one ``[rows, 2O+A+2]`` float32 CUDA tensor, or a list of up to 8 destinations
-        mixing tensors and raw device pointers (ints) -- peer-mapped pools of the other GPUs, which
-        the kernel fills over NVLink from its epilogue (see ``dist.PeerPools``).  ``obs`` /
-        ``action`` may be column slices of a previous step's rows (row stride > width), so a
-        horizon loop chains on the ``next_obs`` columns without a copy.  Returns the local
+    def step_rows(self, obs, action, dest, row_offset=0, indices=None, noise=None, ordered=True):
+        """``PEModel.step`` fused with the collector's pool-row assembly (mbpo_collector.py:69-83):
+        every transition is written as a row ``[obs | act | next_obs | reward | done | 0-padding]``
+        into rows ``[row_offset, row_offset + B)`` of every buffer in ``dest``.
+
+        ``dest`` is one ``[rows, stride]`` float32 CUDA tensor (``row_width() <= stride <=
+        row_width() + 8``), or a list of up to 8 destinations mixing such tensors and raw device
+        pointers (ints) -- peer-mapped pools of the other GPUs, which the kernel fills over NVLink
+        itself (see ``dist.PeerPools``).  ``ordered=True`` puts batch row ``b`` at
+        ``row_offset + b``; ``ordered=False`` writes in bucket order (grouped by drawn member):
+        a pool is a bag of samples, and whole 128-row tiles then leave as one bulk copy per
+        destination -- the mode to use for replicated pools (needs ``stride % 4 == 0``).
+        ``obs`` / ``action`` may be column slices of a previous step's rows (row stride > width),
+        so a horizon loop chains on the ``next_obs`` columns without a copy.  Returns the local
         destination's ``(next_obs, reward, done)`` views when ``dest[0]`` is a tensor."""
         dev = self.device
         L = _lib.lib()
@@ -380,12 +389,16 @@ class B200PEModel(Component, nn.Module):
         dests = list(dest) if isinstance(dest, (list, tuple)) else [dest]
         if not 1 <= len(dests) <= 8:
             raise ValueError("step_rows: 1..8 destinations")
+        if not torch.is_tensor(dests[0]):
+            raise ValueError("step_rows: the first destination must be a tensor (it defines the row stride)")
+        stride = dests[0].shape[1] if dests[0].dim() == 2 else -1
         ptrs = []
         for d in dests:
             if torch.is_tensor(d):
-                if not (d.is_cuda and d.dtype == torch.float32 and d.dim() == 2 and d.shape[1] == W
-                        and d.is_contiguous() and d.shape[0] >= row_offset + B):
-                    raise ValueError(f"step_rows: destination must be contiguous float32 CUDA [>= {row_offset + B}, {W}]")
+                if not (d.is_cuda and d.dtype == torch.float32 and d.dim() == 2 and d.shape[1] == stride
+                        and W <= stride <= W + 8 and d.is_contiguous() and d.shape[0] >= row_offset + B):
+                    raise ValueError(f"step_rows: destination must be contiguous float32 CUDA "
+                                     f"[>= {row_offset + B}, {W}..{W + 8}]")
                 ptrs.append(d.data_ptr())
             else:
                 ptrs.append(int(d))
@@ -403,11 +416,10 @@ class B200PEModel(Component, nn.Module):
             _lib.check(L.mb_pe_rollout_step_rows(
                 ctypes.byref(m), _lib.KERNEL[kname], obs.data_ptr(), obs.stride(0), action.data_ptr(),
                 action.stride(0), _lib.ptr(idx), _lib.ptr(noise), B, _lib.DONE_KIND[self.done_kind],
-                arr, len(ptrs), int(row_offset), _lib.ptr(ws), ws.numel(), _lib.stream()))
-        if torch.is_tensor(dests[0]):
-            rows = dests[0][row_offset:row_offset + B]
-            return rows[:, O + A:2 * O + A], rows[:, 2 * O + A:2 * O + A + 1], rows[:, 2 * O + A + 1:]
-        return None
+                arr, len(ptrs), int(stride), int(row_offset), int(bool(ordered)), _lib.ptr(ws), ws.numel(),
+                _lib.stream()))
+        rows = dests[0][row_offset:row_offset + B]
+        return rows[:, O + A:2 * O + A], rows[:, 2 * O + A:2 * O + A + 1], rows[:, 2 * O + A + 1:W]
 
     def step_np(self, obs, action, **kwargs):
         """base_model.py:78-86."""

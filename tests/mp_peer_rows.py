@@ -24,8 +24,9 @@ def main():
         m, _ = make_pe_model(cases.MBPO, 11, "hopper", device=dev, kernel=kernel)
         m.remember_loss([0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4])
         B, H, O, A = 3001, 3, m.obs_size, m.action_size
-        W = m.row_width()
-        pools = PeerPools(H * world * B, W, device=dev)
+        W, S = m.row_width(), m.row_stride()
+        ordered = kernel == "simt"          # tcgen05: bucket order = one bulk copy per tile and peer
+        pools = PeerPools(H * world * B, S, device=dev)
         pools.local.fill_(-1.0)
         torch.cuda.synchronize()
         dist.barrier()
@@ -33,23 +34,30 @@ def main():
         rs = np.random.RandomState(77 + rank)
         o = torch.from_numpy(o_np).to(dev)
         o_ref = o.clone()
-        want_local = []
+        want_local, o_ref_in = [], []
         for h in range(H):
             a = torch.from_numpy(cases.rollout_inputs(600 + 10 * h + rank, B, env="hopper")[1]).to(dev)
             idx = rs.choice(m.elite_indices, B)
             eps = torch.from_numpy(rs.standard_normal((B, O + 1)).astype(np.float32)).to(dev)
+            o_ref_in.append(o_ref)
             no, r, d, _ = m.step(o_ref, a, indices=idx, noise=eps)
-            want_local.append(torch.cat([o_ref, a, no, r, d], 1))
+            want_local.append(torch.cat([o_ref, a, no, r, d, torch.zeros(B, S - W, device=dev)], 1))
             o_ref = no
-            o, _, _ = m.step_rows(o, a, pools.destinations(), row_offset=(h * world + rank) * B,
-                                  indices=idx, noise=eps)
+            m.step_rows(o_ref_in[h], a, pools.destinations(), row_offset=(h * world + rank) * B,
+                        indices=idx, noise=eps, ordered=ordered)
         pools.fence()
         torch.cuda.synchronize()
         mine = torch.stack(want_local)                                    # [H, B, W]
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
-        want = torch.stack(gathered, 1).reshape(H * world * B, W)         # [H][world][B] rows
-        ok = torch.equal(pools.local, want)
+        want = torch.stack(gathered, 1).reshape(H * world, B, S)          # [H][world] blocks of B rows
+        got = pools.local.view(H * world, B, S)
+
+        def srt(t):
+            a_ = t.cpu().numpy()
+            return a_[np.lexsort(a_.T[::-1])]
+        ok = torch.equal(got, want) if ordered else all(
+            np.array_equal(srt(got[j]), srt(want[j])) for j in range(H * world))
         flag = torch.tensor([1.0 if ok else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         pools.close()

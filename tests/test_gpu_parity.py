@@ -261,17 +261,24 @@ def test_rollout_ragged_batches_match_oracle(B, kernel):
     assert outside == 0
 
 
+def _sorted_rows(t):
+    a = t.detach().cpu().numpy()
+    return a[np.lexsort(a.T[::-1])]
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("env,B", [("hopper", 1), ("hopper", 129), ("cheetah", 5000), ("walker2d", 4099)])
 def test_step_rows_equals_step_plus_pool_assembly(env, B, kernel):
     """The fused pool-row output is bit-identical to step() followed by the collector's
     concatenation [o | a | o' | r | d] (mbpo_collector.py:69-83) -- in two destinations at a row
-    offset, and again when the next horizon step reads obs as a strided view of those rows."""
+    offset, with and without row padding; again when the next horizon step reads obs as a strided
+    view of those rows; and as the same multiset of rows in bucket order (ordered=False)."""
     m, _ = make_pe_model(cases.MBPO, 11, env, kernel=kernel)
     _kernel_or_skip(m, kernel)
     m.remember_loss(LOSS_VEC7)
     O, A = m.obs_size, m.action_size
-    W = m.row_width()
+    W, S = m.row_width(), m.row_stride()
+    assert (W, S) == (42, 44)
     o, a = cases.rollout_inputs(300 + B, B, env=env)
     o, a = T(o, "cuda"), T(a, "cuda")
     rs = np.random.RandomState(B)
@@ -279,19 +286,34 @@ def test_step_rows_equals_step_plus_pool_assembly(env, B, kernel):
     eps = T(rs.standard_normal((B, O + 1)).astype(np.float32), "cuda")
     no, r, d, _ = m.step(o, a, indices=idx, noise=eps)
     want = torch.cat([o, a, no, r, d], 1)
-    off = 7
-    dst = [torch.full((B + 11, W), -7.0, device="cuda") for _ in range(2)]
-    vno, vr, vd = m.step_rows(o, a, dst, row_offset=off, indices=idx, noise=eps)
-    for t in dst:
-        assert torch.equal(t[off:off + B], want)
-        assert float((t[:off] + 7).abs().sum()) == 0 and float((t[off + B:] + 7).abs().sum()) == 0
-    assert torch.equal(vno, no) and torch.equal(vr, r) and torch.equal(vd, d)
-    # chained step: obs is the next_obs column block of the rows just written (row stride W)
+    off = 8
+    for stride in (W, S):
+        dst = [torch.full((B + 11, stride), -7.0, device="cuda") for _ in range(2)]
+        vno, vr, vd = m.step_rows(o, a, dst, row_offset=off, indices=idx, noise=eps)
+        for t in dst:
+            assert torch.equal(t[off:off + B, :W], want)
+            assert float(t[off:off + B, W:].abs().sum()) == 0
+            assert float((t[:off] + 7).abs().sum()) == 0 and float((t[off + B:] + 7).abs().sum()) == 0
+        assert torch.equal(vno, no) and torch.equal(vr, r) and torch.equal(vd, d)
+    # chained step: obs is the next_obs column block of the rows just written (row stride S)
     a2 = T(cases.rollout_inputs(301 + B, B, env=env)[1], "cuda")
     no2, r2, d2, _ = m.step(no, a2, indices=idx, noise=eps)
     dst2 = torch.empty(B, W, device="cuda")
     m.step_rows(vno, a2, dst2, indices=idx, noise=eps)
     assert torch.equal(dst2, torch.cat([no, a2, no2, r2, d2], 1))
+    # bucket order: same rows, grouped by member, every destination identical
+    dst3 = [torch.full((B + 11, S), -7.0, device="cuda") for _ in range(2)]
+    m.step_rows(o, a, dst3, row_offset=off, indices=idx, noise=eps, ordered=False)
+    assert torch.equal(dst3[0], dst3[1])
+    got = dst3[0][off:off + B]
+    assert float(got[:, W:].abs().sum()) == 0
+    assert float((dst3[0][:off] + 7).abs().sum()) == 0 and float((dst3[0][off + B:] + 7).abs().sum()) == 0
+    assert np.array_equal(_sorted_rows(got[:, :W]), _sorted_rows(want))
+    # grouped by member: the member of each output row (recovered through its obs) is non-decreasing
+    # in the order the members appear in the elite list's numeric order
+    key = {tuple(np.round(x, 6)): int(i) for x, i in zip(o.cpu().numpy(), idx)}
+    mem = np.array([key[tuple(np.round(x, 6))] for x in got[:, :O].cpu().numpy()])
+    assert np.all(np.diff(mem) >= 0)
 
 
 @pytest.mark.parametrize("seed,elites,B", [(0, [3, 1, 5, 0, 6], 1000), (1, [2, 0, 1, 4, 3, 6, 5], 100003),
