@@ -20,6 +20,7 @@ struct TrainWs {
     float* z[MB_MAX_LAYERS];       // [E][B][sizes[l+1]] pre-activations, l < L-1
     float* gA;                     // [E][B][maxW] dL/dz ping
     float* gB;                     // [E][B][maxW] dL/dz pong
+    float* gl[MB_MAX_LAYERS];      // small-batch path: dL/d(out of layer l), kept for the batched dW launch
     float* grads;                  // packed blob
 };
 
@@ -29,11 +30,15 @@ static int max_width(const mb_mlp_desc& d) {
     return w;
 }
 
+// Small batches keep every layer's delta so that all weight-gradient GEMMs go out as ONE launch.
+constexpr int64_t kSmallBatchRows = 65536;
+static bool kept_deltas(const mb_mlp_desc& d, int64_t B) { return B * d.ensemble_size <= kSmallBatchRows; }
+
 size_t train_workspace_bytes(const mb_mlp_desc& d, int64_t B) {
     const int64_t E = d.ensemble_size;
     int64_t f = round_up4(E * B * d.sizes[0]);
     for (int l = 0; l + 1 < d.num_layers; ++l) f += round_up4(E * B * d.sizes[l + 1]);
-    f += 2 * round_up4(E * B * max_width(d));
+    f += (kept_deltas(d, B) ? d.num_layers + 1 : 2) * round_up4(E * B * max_width(d));
     f += param_count(d, true);
     return (size_t)f * sizeof(float) + 256;
 }
@@ -47,6 +52,11 @@ static TrainWs carve(const mb_mlp_desc& d, int64_t B, void* ws) {
     for (int l = 0; l + 1 < d.num_layers; ++l) { w.z[l] = p; p += round_up4(E * B * d.sizes[l + 1]); }
     w.gA = p; p += round_up4(E * B * max_width(d));
     w.gB = p; p += round_up4(E * B * max_width(d));
+    for (int l = 0; l < MB_MAX_LAYERS; ++l) w.gl[l] = nullptr;
+    if (kept_deltas(d, B)) {
+        w.gl[d.num_layers - 1] = w.gA;                       // head delta
+        for (int l = 0; l + 1 < d.num_layers; ++l) { w.gl[l] = p; p += round_up4(E * B * max_width(d)); }
+    }
     w.grads = p;
     return w;
 }
@@ -256,21 +266,49 @@ constexpr int kGR = 32;    // reduction chunk
 constexpr int kGLD = kGT + 4;
 constexpr int kGPer = kGT * kGR / 256;   // operand elements per thread per chunk
 
+struct GemmLayer {
+    int K, N;                      // layer fan-in / fan-out
+    const float* hin;              // DW: x0 or z_{l-1}  [E][B][K]
+    int hin_is_z;
+    const float* g;                // delta of this layer's output [E][B][N]
+    const float* W;                // [E][K][N]
+    float wd;
+    const float* zprev;            // DX: pre-activations of the previous layer [E][B][K]
+    float* out;                    // DW: dW [E][K][N];  DX: delta of the previous layer [E][B][K]
+    float* dbias;                  // DW: [E][N]
+};
+struct GemmBatch {
+    int e0, ne, nl;                // blockIdx.z = layer slot * ne + member
+    int64_t B;
+    float* loss_terms;
+    GemmLayer l[MB_MAX_LAYERS];
+};
+
 template <bool DX>
 __global__ void __launch_bounds__(256)
-k_train_gemm(int e0, int64_t B, int K, int N, const float* __restrict__ hin /*x0 or z_{l-1}*/,
-             int hin_is_z, const float* __restrict__ g, const float* __restrict__ W, float wd,
-             const float* __restrict__ zprev, float* __restrict__ out, float* __restrict__ dbias,
-             float* __restrict__ loss_terms) {
+k_train_gemm(GemmBatch gb) {
     __shared__ __align__(16) float As[kGR][kGLD];
     __shared__ __align__(16) float Bs[kGR][kGLD];
     __shared__ float red[8];
-    const int e = e0 + blockIdx.z;
+    const GemmLayer& ly = gb.l[blockIdx.z / gb.ne];
+    const int e = gb.e0 + (int)(blockIdx.z % gb.ne);
+    const int64_t B = gb.B;
+    const int K = ly.K, N = ly.N;
+    const float* __restrict__ hin = ly.hin;
+    const int hin_is_z = ly.hin_is_z;
+    const float* __restrict__ g = ly.g;
+    const float* __restrict__ W = ly.W;
+    const float wd = ly.wd;
+    const float* __restrict__ zprev = ly.zprev;
+    float* __restrict__ out = ly.out;
+    float* __restrict__ dbias = ly.dbias;
+    float* __restrict__ loss_terms = gb.loss_terms;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int M = DX ? (int)B : K;        // output rows
     const int NN = DX ? K : N;            // output cols
     const int R = DX ? N : (int)B;        // reduction length
     const int m0 = blockIdx.y * kGT, n0 = blockIdx.x * kGT;
+    if (m0 >= M || n0 >= NN) return;      // batched launches size the grid for the widest layer
     const float* ge = g + (int64_t)e * B * N;
     const float* he = DX ? nullptr : hin + (int64_t)e * B * K;
     const float* We = W + (int64_t)e * K * N;
@@ -497,21 +535,47 @@ int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, floa
                                                                loss_terms);
         MB_CUDA_LAUNCH_CHECK("k_train_fwd");
     }
+    const bool batched_dw = kept_deltas(d, B) && B * ne <= kSmallBatchRows;
+    GemmBatch dw{};
+    dw.e0 = e0; dw.ne = ne; dw.nl = 0; dw.B = B; dw.loss_terms = loss_terms;
+    int maxK = 0, maxN = 0;
     for (int l = L - 1; l >= 0; --l) {
         const int K = d.sizes[l], N = d.sizes[l + 1];
         const float* Wl = m.params + w_offset(d, l);
-        dim3 gw((unsigned)((N + kGT - 1) / kGT), (unsigned)((K + kGT - 1) / kGT), (unsigned)ne);
-        k_train_gemm<false><<<gw, 256, 0, s>>>(e0, B, K, N, l == 0 ? w.x0 : w.z[l - 1], l > 0, gcur, Wl,
-                                               cfg.weight_decay[l], nullptr, grads + w_offset(d, l),
-                                               grads + b_offset(d, l), loss_terms);
-        MB_CUDA_LAUNCH_CHECK("k_train_gemm<DW>");
-        if (l > 0) {
-            dim3 gx((unsigned)((K + kGT - 1) / kGT), (unsigned)((B + kGT - 1) / kGT), (unsigned)ne);
-            k_train_gemm<true><<<gx, 256, 0, s>>>(e0, B, K, N, nullptr, 0, gcur, Wl, 0.f, w.z[l - 1], gnext,
-                                                  nullptr, nullptr);
-            MB_CUDA_LAUNCH_CHECK("k_train_gemm<DX>");
-            float* t = gcur; gcur = gnext; gnext = t;
+        GemmLayer gl{};
+        gl.K = K; gl.N = N; gl.hin = l == 0 ? w.x0 : w.z[l - 1]; gl.hin_is_z = l > 0; gl.g = gcur; gl.W = Wl;
+        gl.wd = cfg.weight_decay[l]; gl.out = grads + w_offset(d, l); gl.dbias = grads + b_offset(d, l);
+        if (batched_dw) {
+            dw.l[dw.nl++] = gl;
+            maxK = K > maxK ? K : maxK;
+            maxN = N > maxN ? N : maxN;
+        } else {
+            GemmBatch one{};
+            one.e0 = e0; one.ne = ne; one.nl = 1; one.B = B; one.loss_terms = loss_terms; one.l[0] = gl;
+            dim3 gw((unsigned)((N + kGT - 1) / kGT), (unsigned)((K + kGT - 1) / kGT), (unsigned)ne);
+            k_train_gemm<false><<<gw, 256, 0, s>>>(one);
+            MB_CUDA_LAUNCH_CHECK("k_train_gemm<DW>");
         }
+        if (l > 0) {
+            // with kept deltas every layer's delta has its own buffer (the weight-gradient GEMMs
+            // read them later); otherwise two buffers ping-pong
+            float* dst = batched_dw ? w.gl[l - 1] : gnext;
+            GemmBatch dx{};
+            dx.e0 = e0; dx.ne = ne; dx.nl = 1; dx.B = B; dx.loss_terms = nullptr;
+            dx.l[0].K = K; dx.l[0].N = N; dx.l[0].g = gcur; dx.l[0].W = Wl; dx.l[0].zprev = w.z[l - 1];
+            dx.l[0].out = dst;
+            dim3 gx((unsigned)((K + kGT - 1) / kGT), (unsigned)((B + kGT - 1) / kGT), (unsigned)ne);
+            k_train_gemm<true><<<gx, 256, 0, s>>>(dx);
+            MB_CUDA_LAUNCH_CHECK("k_train_gemm<DX>");
+            if (batched_dw) gcur = dst;
+            else { float* t = gcur; gcur = gnext; gnext = t; }
+        }
+    }
+    if (batched_dw) {
+        // all weight gradients (layers x members independent GEMMs) in one launch
+        dim3 gw((unsigned)((maxN + kGT - 1) / kGT), (unsigned)((maxK + kGT - 1) / kGT), (unsigned)(dw.nl * ne));
+        k_train_gemm<false><<<gw, 256, 0, s>>>(dw);
+        MB_CUDA_LAUNCH_CHECK("k_train_gemm<DW all layers>");
     }
     if (params != nullptr) {
         AdamSegs segs;
