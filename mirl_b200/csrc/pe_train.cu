@@ -12,6 +12,8 @@
 #include "simt_mlp.cuh"
 #include "layer_gemm.cuh"
 #include "pe_kernels.h"
+#include "tc_gemm.h"
+#include <stdlib.h>
 
 namespace mb {
 
@@ -471,6 +473,26 @@ __global__ void k_adam(AdamSegs segs, float* __restrict__ p, float* __restrict__
     }
 }
 
+// activation slot == parameter member for training (members e0 .. e0+ne-1)
+static TgBatch tg_members(int e0, int ne) {
+    TgBatch tb{};
+    tb.nmem = ne;
+    tb.slot0 = e0;
+    for (int i = 0; i < ne; ++i) tb.member[i] = e0 + i;
+    for (int i = 0; i < kTgMaxOps; ++i) { tb.op[i].a_act = -1; tb.op[i].a_ones_row = -1; tb.op[i].out_act = -1; }
+    return tb;
+}
+
+// MB_TRAIN_GEMM=simt selects the fp32 SIMT GEMMs (layer_gemm.cuh / k_train_gemm) for A/B timing
+static bool train_gemm_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MB_TRAIN_GEMM");
+        v = (e != nullptr && e[0] == 's') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -491,6 +513,7 @@ int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, floa
 
     float* gcur = w.gA;
     float* gnext = w.gB;
+    const bool use_tc = train_gemm_tc() && kept_deltas(d, B) && d.activation == MB_ACT_SWISH;
     if (B * ne <= 65536) {
         // small batch: one launch per layer spreads the work over all SMs
         {
@@ -500,6 +523,21 @@ int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, floa
             MB_CUDA_LAUNCH_CHECK("k_train_prep");
         }
         for (int l = 0; l < L; ++l) {
+            if (use_tc) {
+                TgBatch tb = tg_members(e0, ne);
+                tb.nops = 1;
+                TgOp& o = tb.op[0];
+                o.mode = TG_FWD;
+                o.M = (int)B; o.N = d.sizes[l + 1]; o.R = d.sizes[l];
+                o.a = l == 0 ? w.x0 : w.z[l - 1]; o.lda = o.R; o.a_ss = (int64_t)B * o.R;
+                o.a_act = l == 0 ? -1 : d.activation;         // layers consume stored PRE-activations
+                o.b = m.params + w_offset(d, l); o.ldb = o.N; o.b_ms = (int64_t)o.R * o.N;
+                o.bias = m.params + b_offset(d, l); o.bias_ms = o.N;
+                o.out = l + 1 < L ? w.z[l] : gnext; o.ldo = o.N; o.out_ss = (int64_t)B * o.N;
+                int rc = launch_tc_gemm(tb, s);
+                if (rc) return rc;
+                continue;
+            }
             LayerArgs a;
             a.B = (int)B; a.K = d.sizes[l]; a.N = d.sizes[l + 1];
             a.A = l == 0 ? w.x0 : w.z[l - 1];
@@ -535,47 +573,82 @@ int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, floa
                                                                loss_terms);
         MB_CUDA_LAUNCH_CHECK("k_train_fwd");
     }
-    const bool batched_dw = kept_deltas(d, B) && B * ne <= kSmallBatchRows;
-    GemmBatch dw{};
-    dw.e0 = e0; dw.ne = ne; dw.nl = 0; dw.B = B; dw.loss_terms = loss_terms;
-    int maxK = 0, maxN = 0;
-    for (int l = L - 1; l >= 0; --l) {
-        const int K = d.sizes[l], N = d.sizes[l + 1];
-        const float* Wl = m.params + w_offset(d, l);
-        GemmLayer gl{};
-        gl.K = K; gl.N = N; gl.hin = l == 0 ? w.x0 : w.z[l - 1]; gl.hin_is_z = l > 0; gl.g = gcur; gl.W = Wl;
-        gl.wd = cfg.weight_decay[l]; gl.out = grads + w_offset(d, l); gl.dbias = grads + b_offset(d, l);
+    if (use_tc) {
+        // tcgen05 path: dX chain layer by layer, then every weight gradient in one launch
+        TgBatch dwb = tg_members(e0, ne);
+        for (int l = L - 1; l >= 0; --l) {
+            const int K = d.sizes[l], N = d.sizes[l + 1];
+            TgOp& o = dwb.op[dwb.nops++];
+            o.mode = TG_DW;
+            o.M = K + 1; o.N = N; o.R = (int)B;
+            o.a = l == 0 ? w.x0 : w.z[l - 1]; o.lda = K; o.a_ss = (int64_t)B * K; o.a_trans = 1;
+            o.a_act = l == 0 ? -1 : d.activation;
+            o.a_ones_row = K;                                   // all-ones row: db = column sums of delta
+            o.b = gcur; o.ldb = N; o.b_ss = (int64_t)B * N;
+            o.w = m.params + w_offset(d, l); o.w_ms = (int64_t)K * N; o.wd = cfg.weight_decay[l];
+            o.out = grads + w_offset(d, l); o.ldo = N; o.out_ms = (int64_t)K * N;
+            o.out_ones = grads + b_offset(d, l); o.out_ones_ms = N;
+            o.l2_acc = loss_terms + 1;
+            if (l > 0) {
+                TgBatch xb = tg_members(e0, ne);
+                xb.nops = 1;
+                TgOp& x = xb.op[0];
+                x.mode = TG_DX;
+                x.M = (int)B; x.N = K; x.R = N;
+                x.a = gcur; x.lda = N; x.a_ss = (int64_t)B * N;
+                x.b = m.params + w_offset(d, l); x.ldb = N; x.b_ms = (int64_t)K * N; x.b_trans = 1;
+                x.z = w.z[l - 1]; x.ldz = K; x.z_ss = (int64_t)B * K;
+                x.out = w.gl[l - 1]; x.ldo = K; x.out_ss = (int64_t)B * K;
+                int rc = launch_tc_gemm(xb, s);
+                if (rc) return rc;
+                gcur = w.gl[l - 1];
+            }
+        }
+        int rc = launch_tc_gemm(dwb, s);
+        if (rc) return rc;
+    } else {
+        const bool batched_dw = kept_deltas(d, B) && B * ne <= kSmallBatchRows;
+        GemmBatch dw{};
+        dw.e0 = e0; dw.ne = ne; dw.nl = 0; dw.B = B; dw.loss_terms = loss_terms;
+        int maxK = 0, maxN = 0;
+        for (int l = L - 1; l >= 0; --l) {
+            const int K = d.sizes[l], N = d.sizes[l + 1];
+            const float* Wl = m.params + w_offset(d, l);
+            GemmLayer gl{};
+            gl.K = K; gl.N = N; gl.hin = l == 0 ? w.x0 : w.z[l - 1]; gl.hin_is_z = l > 0; gl.g = gcur; gl.W = Wl;
+            gl.wd = cfg.weight_decay[l]; gl.out = grads + w_offset(d, l); gl.dbias = grads + b_offset(d, l);
+            if (batched_dw) {
+                dw.l[dw.nl++] = gl;
+                maxK = K > maxK ? K : maxK;
+                maxN = N > maxN ? N : maxN;
+            } else {
+                GemmBatch one{};
+                one.e0 = e0; one.ne = ne; one.nl = 1; one.B = B; one.loss_terms = loss_terms; one.l[0] = gl;
+                dim3 gw((unsigned)((N + kGT - 1) / kGT), (unsigned)((K + kGT - 1) / kGT), (unsigned)ne);
+                k_train_gemm<false><<<gw, 256, 0, s>>>(one);
+                MB_CUDA_LAUNCH_CHECK("k_train_gemm<DW>");
+            }
+            if (l > 0) {
+                // with kept deltas every layer's delta has its own buffer (the weight-gradient GEMMs
+                // read them later); otherwise two buffers ping-pong
+                float* dst = batched_dw ? w.gl[l - 1] : gnext;
+                GemmBatch dx{};
+                dx.e0 = e0; dx.ne = ne; dx.nl = 1; dx.B = B; dx.loss_terms = nullptr;
+                dx.l[0].K = K; dx.l[0].N = N; dx.l[0].g = gcur; dx.l[0].W = Wl; dx.l[0].zprev = w.z[l - 1];
+                dx.l[0].out = dst;
+                dim3 gx((unsigned)((K + kGT - 1) / kGT), (unsigned)((B + kGT - 1) / kGT), (unsigned)ne);
+                k_train_gemm<true><<<gx, 256, 0, s>>>(dx);
+                MB_CUDA_LAUNCH_CHECK("k_train_gemm<DX>");
+                if (batched_dw) gcur = dst;
+                else { float* t = gcur; gcur = gnext; gnext = t; }
+            }
+        }
         if (batched_dw) {
-            dw.l[dw.nl++] = gl;
-            maxK = K > maxK ? K : maxK;
-            maxN = N > maxN ? N : maxN;
-        } else {
-            GemmBatch one{};
-            one.e0 = e0; one.ne = ne; one.nl = 1; one.B = B; one.loss_terms = loss_terms; one.l[0] = gl;
-            dim3 gw((unsigned)((N + kGT - 1) / kGT), (unsigned)((K + kGT - 1) / kGT), (unsigned)ne);
-            k_train_gemm<false><<<gw, 256, 0, s>>>(one);
-            MB_CUDA_LAUNCH_CHECK("k_train_gemm<DW>");
+            // all weight gradients (layers x members independent GEMMs) in one launch
+            dim3 gw((unsigned)((maxN + kGT - 1) / kGT), (unsigned)((maxK + kGT - 1) / kGT), (unsigned)(dw.nl * ne));
+            k_train_gemm<false><<<gw, 256, 0, s>>>(dw);
+            MB_CUDA_LAUNCH_CHECK("k_train_gemm<DW all layers>");
         }
-        if (l > 0) {
-            // with kept deltas every layer's delta has its own buffer (the weight-gradient GEMMs
-            // read them later); otherwise two buffers ping-pong
-            float* dst = batched_dw ? w.gl[l - 1] : gnext;
-            GemmBatch dx{};
-            dx.e0 = e0; dx.ne = ne; dx.nl = 1; dx.B = B; dx.loss_terms = nullptr;
-            dx.l[0].K = K; dx.l[0].N = N; dx.l[0].g = gcur; dx.l[0].W = Wl; dx.l[0].zprev = w.z[l - 1];
-            dx.l[0].out = dst;
-            dim3 gx((unsigned)((K + kGT - 1) / kGT), (unsigned)((B + kGT - 1) / kGT), (unsigned)ne);
-            k_train_gemm<true><<<gx, 256, 0, s>>>(dx);
-            MB_CUDA_LAUNCH_CHECK("k_train_gemm<DX>");
-            if (batched_dw) gcur = dst;
-            else { float* t = gcur; gcur = gnext; gnext = t; }
-        }
-    }
-    if (batched_dw) {
-        // all weight gradients (layers x members independent GEMMs) in one launch
-        dim3 gw((unsigned)((maxN + kGT - 1) / kGT), (unsigned)((maxK + kGT - 1) / kGT), (unsigned)(dw.nl * ne));
-        k_train_gemm<false><<<gw, 256, 0, s>>>(dw);
-        MB_CUDA_LAUNCH_CHECK("k_train_gemm<DW all layers>");
     }
     if (params != nullptr) {
         AdamSegs segs;
