@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "simt_mlp.cuh"
 #include "layer_gemm.cuh"
+#include "tc_gemm.h"
+#include <stdlib.h>
 #include "pe_kernels.h"
 
 namespace mb {
@@ -191,6 +193,16 @@ size_t critic_workspace_bytes(const mb_mlp_desc& d, int64_t B) {
     return (size_t)(2 * (int64_t)d.ensemble_size * B * w + (int64_t)d.ensemble_size * B * d.sizes[d.num_layers]) * 4 + 256;
 }
 
+// MB_CRITIC_GEMM=simt keeps every layer on the fp32 SIMT GEMM (A/B timing)
+static bool critic_gemm_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MB_CRITIC_GEMM");
+        v = (e != nullptr && e[0] == 's') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // Runs the stack for `nmem` members; returns the final layer's output [nmem][B][N_out] (in ws
 // unless `final_out` is given).
 static int layered_forward(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
@@ -214,6 +226,24 @@ static int layered_forward(const mb_mlp_desc& d, const float* params, const floa
         a.slot0 = 0;
         a.nmem = nmem;
         for (int i = 0; i < nmem; ++i) a.member[i] = members[i];
+        if (l > 0 && critic_gemm_tc()) {
+            // hidden / output layers on the tensor cores (bf16x3, tc_gemm.cu); layer 0 keeps the
+            // SIMT kernel: its 23-wide input is the fused [obs | act] concatenation
+            TgBatch tb{};
+            tb.nops = 1; tb.nmem = nmem; tb.slot0 = 0;
+            for (int i = 0; i < nmem; ++i) tb.member[i] = members[i];
+            TgOp& o = tb.op[0];
+            o.mode = TG_FWD;
+            o.M = (int)B; o.N = a.N; o.R = a.K;
+            o.a = a.A; o.lda = a.K; o.a_ss = a.a_slot_stride; o.a_act = -1; o.a_ones_row = -1;
+            o.b = a.W; o.ldb = a.N; o.b_ms = (int64_t)a.K * a.N;
+            o.bias = a.bias; o.bias_ms = a.N;
+            o.out_act = a.out_act;
+            o.out = a.out; o.ldo = a.N; o.out_ss = (int64_t)B * a.N;
+            int rc = launch_tc_gemm(tb, s);
+            if (rc) return rc;
+            continue;
+        }
         int rc = launch_layer(a, l == 0 ? &ci : nullptr, s);
         if (rc) return rc;
     }

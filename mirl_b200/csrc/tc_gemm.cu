@@ -19,10 +19,11 @@
 #include "common.cuh"
 #include "pe_kernels.h"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace mb {
 
-constexpr int kTgThreads = 256;
+constexpr int kTgThreads = 512;            // 4 warps per SM sub-partition: the staging code is latency bound
 constexpr int kTgKC = 64;                 // reduction elements per stage = 4 UMMA k-steps
 constexpr int kTgAPlane = kUmmaM * kTgKC * 2;   // bytes of one A plane (hi or lo) of a stage: 16 KB
 
@@ -63,36 +64,27 @@ __device__ __forceinline__ void tg_load8(const float* __restrict__ src, int64_t 
     }
 }
 
-// Stage `tile_rows` x 64 of an operand: items (row, 8-element k-chunk), lanes own consecutive rows.
-template <int BATCH>
-__device__ __forceinline__ void tg_stage(uint32_t hi_plane, uint32_t lo_plane, int tile_rows, const float* __restrict__ src,
-                                         int64_t ld, int trans, int act, int row0, int rows_valid, int ones_row,
-                                         int r0, int R) {
-    const int items = tile_rows * (kTgKC / 8);
-    const uint32_t lbo = (uint32_t)tile_rows * 16u;
-    for (int base = 0; base < items; base += BATCH * kTgThreads) {
-        float v[BATCH][8];
+// Stage a tile_rows x 64 block of an operand.  Every thread owns NI items (row, 8-element k-chunk)
+// whose coordinates do not depend on the stage, with lanes on consecutive rows: all global loads
+// of the thread are issued before the first conversion.
+struct TgItem { int row, j; };
+template <int NI>
+__device__ __forceinline__ void tg_stage(uint32_t hi_plane, uint32_t lo_plane, uint32_t lbo, const TgItem (&it)[NI],
+                                         const float* __restrict__ src, int64_t ld, int strided, int act, int row0,
+                                         int rows_valid, int ones_row, int r0, int R) {
+    float v[NI][8];
 #pragma unroll
-        for (int q = 0; q < BATCH; ++q) {                        // all loads of the batch in flight first
-            const int it = base + q * kTgThreads + (int)threadIdx.x;
-            if (it < items) {
-                const int row = it % tile_rows, j = it / tile_rows;
-                tg_load8(src, ld, trans, row0 + row, rows_valid, ones_row, r0 + 8 * j, R, v[q]);
-            }
+    for (int q = 0; q < NI; ++q)
+        if (it[q].row >= 0) tg_load8(src, ld, strided, row0 + it[q].row, rows_valid, ones_row, r0 + 8 * it[q].j, R, v[q]);
+#pragma unroll
+    for (int q = 0; q < NI; ++q) {
+        if (it[q].row < 0) continue;
+        if (act >= 0 && row0 + it[q].row != ones_row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[q][i] = act == MB_ACT_RELU ? fmaxf(v[q][i], 0.f) : fast_swish(v[q][i]);
         }
-#pragma unroll
-        for (int q = 0; q < BATCH; ++q) {
-            const int it = base + q * kTgThreads + (int)threadIdx.x;
-            if (it < items) {
-                const int row = it % tile_rows, j = it / tile_rows;
-                if (act >= 0 && row0 + row != ones_row) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[q][i] = act == MB_ACT_RELU ? fmaxf(v[q][i], 0.f) : fast_swish(v[q][i]);
-                }
-                const uint32_t off = (uint32_t)j * lbo + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-                split_store8(v[q], hi_plane + off, lo_plane + off);
-            }
-        }
+        const uint32_t off = (uint32_t)it[q].j * lbo + (uint32_t)(it[q].row >> 3) * 128u + (uint32_t)(it[q].row & 7) * 16u;
+        split_store8(v[q], hi_plane + off, lo_plane + off);
     }
 }
 
@@ -136,11 +128,25 @@ k_tc_gemm(TgBatch gb, int nt_max) {
     const int R = op.R;
     const int nch = (R + kTgKC - 1) / kTgKC;
 
+    // item coordinates (fixed for the whole kernel): A 128 x 8 items, B NT x 8 items (NT <= 128)
+    constexpr int kItems = kUmmaM * (kTgKC / 8) / kTgThreads;         // 2
+    TgItem ia[kItems], ib[kItems];
+#pragma unroll
+    for (int q = 0; q < kItems; ++q) {
+        const int it = (int)threadIdx.x + q * kTgThreads;
+        ia[q].row = it & (kUmmaM - 1);
+        ia[q].j = it / kUmmaM;
+        ib[q].row = it < NT * (kTgKC / 8) ? it % NT : -1;
+        ib[q].j = it / NT;
+    }
+    const int a_act = op.a_act, a_strided = op.a_trans, a_ones = op.a_ones_row, b_strided = op.b_trans ? 0 : 1;
+    const int64_t lda = op.lda, ldb = op.ldb;
+    const int Nn = op.N;
     auto stage = [&](int c, int s) {
         const int r0 = c * kTgKC;
-        tg_stage<4>(a_hi(s), a_lo(s), kUmmaM, A, op.lda, op.a_trans, op.a_act, m0, a_rows, op.a_ones_row, r0, R);
-        // tg_load8's flag means "reduction index is the strided one": that is b_trans == 0 for B'
-        tg_stage<4>(b_hi(s), b_lo(s), NT, Bm, op.ldb, op.b_trans ? 0 : 1, -1, n0, op.N, -1, r0, R);
+        tg_stage<kItems>(a_hi(s), a_lo(s), kUmmaM * 16u, ia, A, lda, a_strided, a_act, m0, a_rows, a_ones, r0, R);
+        // "reduction index is the strided one" is b_trans == 0 for B'
+        tg_stage<kItems>(b_hi(s), b_lo(s), (uint32_t)NT * 16u, ib, Bm, ldb, b_strided, -1, n0, Nn, -1, r0, R);
     };
 
     stage(0, 0);
@@ -182,76 +188,108 @@ k_tc_gemm(TgBatch gb, int nt_max) {
         }
         tc_fence_before();
         __syncthreads();
-    }
+        }
     {
         const int s = (nch - 1) & 1;
         mbar_wait_relaxed(bar0 + 8u * (uint32_t)s, s == 0 ? ph0 : ph1);
         tc_fence_after();
     }
 
-    // ---- epilogue: thread = row (TMEM lane), warps w and w+4 share a lane quarter and split the columns
-    const int q = warp & 3, half = warp >> 2;
-    const int m = m0 + q * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float l2 = 0.f;
-    for (int cb = half; cb * 16 < NT; cb += 2) {
-        uint32_t acc[16];
-        tc_ld16(tmem + lane_addr + (uint32_t)(cb * 16), acc);
-        tc_wait_ld();
-        const int nb = n0 + cb * 16;
-        if (nb >= op.N) continue;
-        float v[16];
+    // ---- epilogue.  Phase 1: accumulators TMEM -> registers (thread = row) -> shared memory (the
+    // operand ring is free now) as a [128][NT + 4] fp32 tile.  Phase 2: warps walk the rows with
+    // lanes along the columns, so the per-element operands (bias / z / w) and the result move as
+    // coalesced 16-byte accesses; the tail op of the mode is applied here.
+    const int LDT = NT + 4;                                                // floats; 16-byte rows, conflict-free
+    const uint32_t tile = base;
+    {
+        const int q = warp & 3, grp = warp >> 2;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t rowp = tile + (uint32_t)((q * 32 + lane) * LDT) * 4u;
+        for (int cb = grp; cb * 16 < NT; cb += kTgThreads / 128) {
+            uint32_t acc[16];
+            tc_ld16(tmem + lane_addr + (uint32_t)(cb * 16), acc);
+            tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
-        if (op.mode == TG_FWD) {
-            if (m < op.M) {
-                const float* bias = op.bias + (int64_t)e * op.bias_ms;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (nb + i < op.N) {
-                        const float x = v[i] + __ldg(bias + nb + i);
-                        v[i] = op.out_act < 0 ? x : (op.out_act == MB_ACT_RELU ? fmaxf(x, 0.f) : fast_swish(x));
-                    }
-                }
-            }
-        } else if (op.mode == TG_DX) {
-            if (m < op.M) {
-                const float* z = op.z + (int64_t)slot * op.z_ss + (int64_t)m * op.ldz + nb;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (nb + i < op.N) {
-                        const float zz = __ldg(z + i);
-                        const float sg = rcp_ftz(1.0f + ex2_ftz(zz * -1.4426950408889634f));
-                        v[i] *= sg * (1.f + zz * (1.f - sg));
-                    }
-                }
-            }
-        } else {                                                           // TG_DW
-            if (m < op.a_ones_row) {
-                const float* w = op.w + (int64_t)e * op.w_ms + (int64_t)m * op.N + nb;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (nb + i < op.N) {
-                        const float ww = __ldg(w + i);
-                        v[i] += op.wd * ww;
-                        l2 += 0.5f * op.wd * ww * ww;
-                    }
-                }
-            }
+            for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + (uint32_t)(cb * 16 + 4 * i) * 4u),
+                             "r"(acc[4 * i]), "r"(acc[4 * i + 1]), "r"(acc[4 * i + 2]), "r"(acc[4 * i + 3]) : "memory");
         }
-        float* dst = nullptr;
-        if (op.mode == TG_DW && m == op.a_ones_row) dst = op.out_ones + (int64_t)e * op.out_ones_ms + nb;
-        else if (m < (op.mode == TG_DW ? op.a_ones_row : op.M))
-            dst = op.out + (int64_t)slot * op.out_ss + (int64_t)e * op.out_ms + (int64_t)m * op.ldo + nb;
-        if (dst != nullptr) {
-            if (nb + 16 <= op.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    }
+    tc_fence_before();
+    __syncthreads();
+    const int mode = op.mode, M = op.M, out_act = op.out_act, ones_row = op.a_ones_row;
+    const float wd = op.wd;
+    const int row_lim = mode == TG_DW ? ones_row : M;                     // rows with a regular output
+    const int col = lane * 4;                                             // this lane's 4 columns of the tile
+    const int nb = n0 + col;
+    const bool col_ok = col < NT && nb < Nn;
+    const bool full = nb + 4 <= Nn;
+    float l2 = 0.f;
+    float4 cb4 = make_float4(0.f, 0.f, 0.f, 0.f);                          // FWD: bias of these columns
+    if (mode == TG_FWD && col_ok) {
+        const float* p = op.bias + (int64_t)e * op.bias_ms + nb;
+        if (full && (reinterpret_cast<uintptr_t>(p) & 15) == 0) cb4 = __ldg(reinterpret_cast<const float4*>(p));
+        else { cb4.x = __ldg(p); if (nb + 1 < Nn) cb4.y = __ldg(p + 1); if (nb + 2 < Nn) cb4.z = __ldg(p + 2); if (nb + 3 < Nn) cb4.w = __ldg(p + 3); }
+    }
+    auto ld4 = [&](const float* p) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (full && (reinterpret_cast<uintptr_t>(p) & 15) == 0) x = __ldg(reinterpret_cast<const float4*>(p));
+        else { x.x = __ldg(p); if (nb + 1 < Nn) x.y = __ldg(p + 1); if (nb + 2 < Nn) x.z = __ldg(p + 2); if (nb + 3 < Nn) x.w = __ldg(p + 3); }
+        return x;
+    };
+    const float* zb = mode == TG_DX ? op.z + (int64_t)slot * op.z_ss : nullptr;
+    const float* wb = mode == TG_DW ? op.w + (int64_t)e * op.w_ms : nullptr;
+    float* ob = op.out + (int64_t)slot * op.out_ss + (int64_t)e * op.out_ms;
+    const int64_t ldz = op.ldz, ldo = op.ldo;
+    constexpr int kRU = 4;                                                 // rows in flight per warp
+    for (int rb = warp * kRU; rb < kUmmaM; rb += (kTgThreads / 32) * kRU) {
+        float4 c[kRU], v[kRU];
+        bool live[kRU], plain[kRU];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int u = 0; u < kRU; ++u) {                                    // all loads first
+            const int r = rb + u, m = m0 + r;
+            plain[u] = mode == TG_DW && m == ones_row;                     // bias-gradient row: no tail op
+            live[u] = (m < row_lim || plain[u]) && col_ok;
+            c[u] = cb4;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!live[u]) continue;
+            if (mode == TG_DX) c[u] = ld4(zb + (int64_t)m * ldz + nb);
+            else if (mode == TG_DW && !plain[u]) c[u] = ld4(wb + (int64_t)m * Nn + nb);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                         : "r"(tile + (uint32_t)(r * LDT + col) * 4u));
+        }
+#pragma unroll
+        for (int u = 0; u < kRU; ++u) {
+            if (!live[u]) continue;
+            const int m = m0 + rb + u;
+            float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            const float cc[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+            if (mode == TG_FWD) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float x = vv[i] + cc[i];
+                    vv[i] = out_act < 0 ? x : (out_act == MB_ACT_RELU ? fmaxf(x, 0.f) : fast_swish(x));
+                }
+            } else if (mode == TG_DX) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float sg = rcp_ftz(1.0f + ex2_ftz(cc[i] * -1.4426950408889634f));
+                    vv[i] *= sg * (1.f + cc[i] * (1.f - sg));
+                }
+            } else if (!plain[u]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                              // c = 0 beyond N: no contribution
+                    vv[i] += wd * cc[i];
+                    l2 += 0.5f * wd * cc[i] * cc[i];
+                }
+            }
+            float* dst = (plain[u] ? op.out_ones + (int64_t)e * op.out_ones_ms : ob + (int64_t)m * ldo) + nb;
+            if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                *reinterpret_cast<float4*>(dst) = make_float4(vv[0], vv[1], vv[2], vv[3]);
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (nb + i < op.N) dst[i] = v[i];
+                for (int i = 0; i < 4; ++i)
+                    if (nb + i < Nn) dst[i] = vv[i];
             }
         }
     }
