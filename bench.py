@@ -154,6 +154,10 @@ def secondary_metrics(dev, world, rank, timed):
         ms = timed(lambda: None, 200, 20) / 200
     out["model_train_samples_per_s"] = E * B / (ms * 1e-3)
     out["model_train_ms_per_step"] = ms
+    # forward + dX + dW = 3 GEMM passes of 2*sum(K_l*N_l) flops per sample (4x200 MLP, 23 -> 36)
+    mlp_macs = 23 * 200 + 3 * 200 * 200 + 200 * 36
+    out["model_train_tflops"] = 3 * 2 * mlp_macs * E * B / (ms * 1e-3) / 1e12
+    out["model_train_roofline_frac"] = out["model_train_tflops"] / peaks()["tensor"]
     out["model_train_config"] = "7 members x batch 256 (bootstrap batches), fused fwd+NLL+bwd+Adam, members sharded over %d GPU(s)" % world
     q, _ = make_critic("redq", 71, device=dev)
     t, _ = make_critic("tqc", 81, device=dev)
@@ -162,8 +166,10 @@ def secondary_metrics(dev, world, rank, timed):
     r, d, lp = T(x["rewards"], dev), T(x["terminals"], dev), T(x["log_prob"], dev)
     ms = timed(lambda: q.q_target(o, a, r, d, lp, alpha=0.2, sample_number=2, batchwise_sample=True), 200, 20) / 200
     out["redq_targets_per_s"] = world * B / (ms * 1e-3)
+    out["redq_tflops"] = 2 * 2 * (23 * 256 + 256 * 256 + 256) * B / (ms * 1e-3) / 1e12      # 2 drawn members
     ms = timed(lambda: t.atoms_target(o, a, r, d, lp, alpha=0.2, percentage_drop=8), 200, 20) / 200
     out["tqc_targets_per_s"] = world * B / (ms * 1e-3)
+    out["tqc_tflops"] = 5 * 2 * (23 * 512 + 2 * 512 * 512 + 512 * 25) * B / (ms * 1e-3) / 1e12
     out["critic_config"] = "batch 256; REDQ 10x(2x256) random-2 min + TD; TQC 5x(3x512)x25 drop 10 + TD; replicas"
     return out
 
