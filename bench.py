@@ -170,6 +170,18 @@ def secondary_metrics(dev, world, rank, timed):
     ms = timed(lambda: t.atoms_target(o, a, r, d, lp, alpha=0.2, percentage_drop=8), 200, 20) / 200
     out["tqc_targets_per_s"] = world * B / (ms * 1e-3)
     out["tqc_tflops"] = 5 * 2 * (23 * 512 + 2 * 512 * 512 + 512 * 25) * B / (ms * 1e-3) / 1e12
+    # configs/offline_mopo.json: penalised rollout step (all elites per row + max-var penalty)
+    mm, _ = make_pe_model(cases.MBPO, 11, "hopper", device=dev)
+    mm.remember_loss(LOSS_VEC7)
+    Bm = 100_000
+    gm = torch.Generator(device=dev).manual_seed(77)
+    om = torch.randn(Bm, 17, device=dev, generator=gm)
+    am = torch.rand(Bm, 6, device=dev, generator=gm) * 2 - 1
+    em = torch.randn(Bm, 18, device=dev, generator=gm)
+    im = torch.from_numpy(np.random.RandomState(5).choice(mm.elite_indices, Bm).astype(np.uint8)).to(dev)
+    ms = timed(lambda: mm.step(om, am, indices=im, noise=em, return_distribution=True, penalty_type="max_var"), 20, 3) / 20
+    out["mopo_penalised_transitions_per_s"] = world * Bm / (ms * 1e-3)
+    out["mopo_config"] = "100k states, 5 elites evaluated per row (tcgen05 forward mode) + max_var penalty, per GPU replica"
     out["critic_config"] = "batch 256; REDQ 10x(2x256) random-2 min + TD; TQC 5x(3x512)x25 drop 10 + TD; replicas"
     return out
 

@@ -139,6 +139,24 @@ int mb_pe_rollout_step_dist(const mb_pe_model* m, const float* obs, const float*
                             int penalty_kind, float penalty_coef, float* penalty,
                             float* penalized_reward, void* stream);
 
+/* The same step with the all-elite forward on the tensor cores (tcgen05 rollout kernel in forward
+ * mode, then one elementwise kernel for the outputs above).  Needs m->tc_pack and a workspace of
+ * mb_pe_dist_workspace_bytes(m, B, n_elite) bytes ([n_elite][B][2(O+1)] floats). */
+size_t mb_pe_dist_workspace_bytes(const mb_pe_model* m, int64_t B, int n_elite);
+int mb_pe_rollout_step_dist_tc(const mb_pe_model* m, const float* obs, const float* act,
+                               const uint8_t* member_idx, const float* noise, int64_t B, int done_kind,
+                               const int32_t* elites_host, int n_elite, float* next_obs, float* reward,
+                               float* done, float* delta_mean, float* delta_std, float* next_obs_mean,
+                               float* reward_mean, float* reward_std, int penalty_kind,
+                               float penalty_coef, float* penalty, float* penalized_reward,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* All-member forward on the tensor cores (normalised inputs): out[k][b] = [mean (O+1) | clamped
+ * log-std (O+1)] of member members_host[k] -- the quantities of mb_pe_forward, interleaved per
+ * row.  per_member != 0: obs / act are [E][B][.] (row block e belongs to member e). */
+int mb_pe_forward_tc(const mb_pe_model* m, const float* obs, const float* act, int per_member, int64_t B,
+                     const int32_t* members_host, int n_members, float* out, void* stream);
+
 /* ---- ensemble forward: per-member Gaussian mean / log-std (pe_model.py:110-151) -----------
  * x is obs/act already split: obs[.][O], act[.][A]; per_member=0 -> inputs [B][.] shared by
  * all members, 1 -> [E][B][.].  normalize!=0 applies the obs/action Normalizers.

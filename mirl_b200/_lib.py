@@ -55,6 +55,10 @@ SIGNATURES = {
     "mb_pe_draw_members": (c_int, [P, ctypes.c_char_p, c_int, c_int64, P, P, c_size_t, P]),
     "mb_pe_rollout_step_rows": (c_int, [POINTER(PeModel), c_int, P, c_int64, P, c_int64, P, P, c_int64, c_int,
                                         POINTER(c_void_p), c_int, c_int64, c_int64, c_int, P, c_size_t, P]),
+    "mb_pe_dist_workspace_bytes": (c_size_t, [POINTER(PeModel), c_int64, c_int]),
+    "mb_pe_rollout_step_dist_tc": (c_int, [POINTER(PeModel), P, P, P, P, c_int64, c_int, POINTER(c_int32), c_int,
+                                           P, P, P, P, P, P, P, P, c_int, c_float, P, P, P, c_size_t, P]),
+    "mb_pe_forward_tc": (c_int, [POINTER(PeModel), P, P, c_int, c_int64, POINTER(c_int32), c_int, P, P]),
     "mb_pe_rollout_step_dist": (c_int, [POINTER(PeModel), P, P, P, P, c_int64, c_int,
                                         POINTER(c_int32), c_int, P, P, P, P, P, P, P, P, c_int,
                                         c_float, P, P, P]),

@@ -189,6 +189,62 @@ int mb_pe_rollout_step_dist(const mb_pe_model* m, const float* obs, const float*
                                        penalty, penalized_reward, (cudaStream_t)stream);
 }
 
+size_t mb_pe_dist_workspace_bytes(const mb_pe_model* m, int64_t B, int n_elite) {
+    if (m == nullptr || B < 1 || n_elite < 1) return 0;
+    return (size_t)n_elite * (size_t)B * 2 * (size_t)(m->obs_dim + 1) * sizeof(float) + 256;
+}
+
+int mb_pe_rollout_step_dist_tc(const mb_pe_model* m, const float* obs, const float* act,
+                               const uint8_t* member_idx, const float* noise, int64_t B, int done_kind,
+                               const int32_t* elites_host, int n_elite, float* next_obs, float* reward,
+                               float* done, float* delta_mean, float* delta_std, float* next_obs_mean,
+                               float* reward_mean, float* reward_std, int penalty_kind,
+                               float penalty_coef, float* penalty, float* penalized_reward,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate_model(m, "mb_pe_rollout_step_dist_tc");
+    if (rc) return rc;
+    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "mb_pe_rollout_step_dist_tc: B out of range");
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(obs && act && member_idx && noise && next_obs && reward && done,
+                 "mb_pe_rollout_step_dist_tc: null tensor");
+    MB_CHECK_ARG(m->tc_pack != nullptr, "mb_pe_rollout_step_dist_tc: needs tc_pack");
+    MB_CHECK_ARG(elites_host && n_elite >= 1 && n_elite <= m->mlp.ensemble_size,
+                 "mb_pe_rollout_step_dist_tc: bad elite list");
+    for (int i = 0; i < n_elite; ++i)
+        MB_CHECK_ARG(elites_host[i] >= 0 && elites_host[i] < m->mlp.ensemble_size,
+                     "mb_pe_rollout_step_dist_tc: elite id %d out of range", elites_host[i]);
+    MB_CHECK_ARG(penalty_kind >= MB_PENALTY_NONE && penalty_kind <= MB_PENALTY_MAX_VAR,
+                 "mb_pe_rollout_step_dist_tc: unknown penalty kind %d", penalty_kind);
+    if (workspace == nullptr || workspace_bytes < mb_pe_dist_workspace_bytes(m, B, n_elite)) {
+        set_error("mb_pe_rollout_step_dist_tc: workspace %zu < %zu bytes", workspace_bytes,
+                  mb_pe_dist_workspace_bytes(m, B, n_elite));
+        return MB_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    float* fwd = reinterpret_cast<float*>(workspace);
+    rc = launch_pe_forward_tc(to_dev(m), m->tc_pack, obs, act, 0, B, elites_host, n_elite, fwd, s);
+    if (rc) return rc;
+    return launch_pe_dist_finish(to_dev(m), elites_host, n_elite, fwd, obs, member_idx, noise, B, done_kind,
+                                 next_obs, reward, done, delta_mean, delta_std, next_obs_mean, reward_mean,
+                                 reward_std, penalty_kind, penalty_coef, penalty, penalized_reward, s);
+}
+
+int mb_pe_forward_tc(const mb_pe_model* m, const float* obs, const float* act, int per_member, int64_t B,
+                     const int32_t* members_host, int n_members, float* out, void* stream) {
+    int rc = validate_model(m, "mb_pe_forward_tc");
+    if (rc) return rc;
+    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "mb_pe_forward_tc: B out of range");
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(obs && act && out && members_host, "mb_pe_forward_tc: null tensor");
+    MB_CHECK_ARG(m->tc_pack != nullptr, "mb_pe_forward_tc: needs tc_pack");
+    MB_CHECK_ARG(n_members >= 1 && n_members <= m->mlp.ensemble_size, "mb_pe_forward_tc: bad member count %d", n_members);
+    for (int i = 0; i < n_members; ++i)
+        MB_CHECK_ARG(members_host[i] >= 0 && members_host[i] < m->mlp.ensemble_size,
+                     "mb_pe_forward_tc: member id %d out of range", members_host[i]);
+    return launch_pe_forward_tc(to_dev(m), m->tc_pack, obs, act, per_member, B, members_host, n_members, out,
+                                (cudaStream_t)stream);
+}
+
 int mb_pe_forward(const mb_pe_model* m, const float* obs, const float* act, int per_member,
                   int normalize, int64_t B, float* mean, float* logstd, void* stream) {
     int rc = validate_model(m, "mb_pe_forward");

@@ -81,6 +81,18 @@ struct RowsOut {
                               //    then contiguous and leave as one bulk copy per destination
 };
 
+// All-member forward mode of the tcgen05 rollout kernel: instead of the bucket plan the tiles walk
+// rows [0, B) of every listed member in order, and the head writes each row's
+// [mean D | clamped log-std D] (normalised space) as one 2D-float row of out[slot][B][2D].
+struct TcForward {
+    int mode;                 // 0 = rollout step, 1 = all-member forward
+    float* out;               // [n_members][B][2D]
+    int64_t B;
+    int64_t in_member_rows;   // 0: inputs shared by all members; B: inputs are [E][B][.]
+    int total[kMaxMembers];   // B for listed members, 0 otherwise
+    int slot_of[kMaxMembers]; // output slot of member e
+};
+
 // np.random.choice(elite, B) on the device, bit-exact with NumPy's legacy MT19937 stream (member_draw.cu)
 size_t draw_workspace_bytes(int64_t B, int n);
 int launch_draw_members(uint32_t* state, const uint8_t* elites, int n, int64_t B, uint8_t* out, void* ws,
@@ -119,6 +131,15 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, int
                          const float* act, int64_t act_stride, const uint8_t* idx, const float* noise,
                          int64_t B, int done_kind, float* next_obs, float* reward, float* done,
                          const RowsOut& rows, void* ws, cudaStream_t s);
+// all-member forward on the tensor cores: out[slot][B][2D] = [mean | clamped log-std] of members[slot]
+int launch_pe_forward_tc(const PeDev& m, const void* pack, const float* obs, const float* act, int per_member,
+                         int64_t B, const int* members, int n_members, float* out, cudaStream_t s);
+bool tc_rollout_supported(const mb_mlp_desc& d);
+int launch_pe_dist_finish(const PeDev& m, const int32_t* elites, int n_elite, const float* fwd, const float* obs,
+                          const uint8_t* idx, const float* noise, int64_t B, int done_kind, float* next_obs,
+                          float* reward, float* done, float* delta_mean, float* delta_std, float* next_obs_mean,
+                          float* reward_mean, float* reward_std, int penalty_kind, float penalty_coef,
+                          float* penalty, float* penalized_reward, cudaStream_t s);
 
 // ---- model training (pe_train.cu)
 size_t train_workspace_bytes(const mb_mlp_desc& d, int64_t B);

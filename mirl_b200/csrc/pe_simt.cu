@@ -420,6 +420,100 @@ int launch_pe_forward_simt(const PeDev& m, const float* obs, const float* act, i
     return MB_OK;
 }
 
+// ---- MOPO / return_distribution tail over a precomputed all-elite forward --------------------
+// fwd[k][b][2D] = [mean | clamped log-std] of elite k for row b (normalised space, written by the
+// tcgen05 forward).  One warp per row, lanes = output columns (D <= 32): the same outputs as
+// k_pe_rollout_dist_simt (pe_model.py:255-282, mopo_collector.py:42-53).
+__global__ void __launch_bounds__(256)
+k_pe_dist_finish(PeDev m, EliteList el, const float* __restrict__ fwd, const float* __restrict__ obs,
+                 const uint8_t* __restrict__ member_idx, const float* __restrict__ noise, int64_t B,
+                 int done_kind, float* __restrict__ next_obs, float* __restrict__ reward,
+                 float* __restrict__ done, float* __restrict__ delta_mean, float* __restrict__ delta_std,
+                 float* __restrict__ next_obs_mean, float* __restrict__ reward_mean,
+                 float* __restrict__ reward_std, int penalty_kind, float penalty_coef,
+                 float* __restrict__ penalty, float* __restrict__ penalized_reward) {
+    __shared__ float nrow[8][32];
+    const int O = m.O, A = m.A, D = O + 1;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float* dmean = m.norm + 2 * O + 2 * A;
+    const float* dstd = dmean + O;
+    const int j = lane;
+    const bool in_o = j < O, in_d = j < D;
+    const float scale = in_o ? dstd[j] + kNormEps : 0.f;
+    const float dm0 = in_o ? dmean[j] : 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + w; r < B; r += (int64_t)gridDim.x * 8) {
+        const float raw = in_o ? obs[r * O + j] : 0.f;
+        const int mine_e = member_idx[r];
+        const float eps = in_d ? noise[r * D + j] : 0.f;
+        float wmean = 0.f, wm2 = 0.f, svar = 0.f, mxn = 0.f, rew = 0.f;
+        nrow[w][lane] = 0.f;
+        for (int k = 0; k < el.n; ++k) {
+            const float* f = fwd + ((int64_t)k * B + r) * (2 * D);
+            const float mu = in_d ? f[j] : 0.f;
+            const float sd = in_d ? expf(f[D + j]) : 0.f;
+            const bool mine = el.id[k] == mine_e;
+            const float sv = eps * sd + mu;
+            const int64_t o3 = (int64_t)k * B + r;
+            float sq = 0.f;
+            if (in_o) {
+                const float dmv = mu * scale + dm0;
+                const float ds = sd * scale;
+                const float nm = dmv + raw;
+                if (delta_mean) delta_mean[o3 * O + j] = dmv;
+                if (delta_std) delta_std[o3 * O + j] = ds;
+                if (next_obs_mean) next_obs_mean[o3 * O + j] = nm;
+                const float dlt = nm - wmean;                      // Welford over elites (torch.var, unbiased)
+                const float nmean = wmean + dlt / (float)(k + 1);
+                wm2 += dlt * (nm - nmean);
+                wmean = nmean;
+                sq = ds * ds;
+                svar += sq;
+                if (mine) {
+                    const float v = raw + (sv * scale + dm0);
+                    nrow[w][j] = v;
+                    next_obs[r * O + j] = v;
+                }
+            } else if (j == O) {
+                if (reward_mean) reward_mean[o3] = mu;
+                if (reward_std) reward_std[o3] = sd;
+                if (mine) { rew = sv; reward[r] = sv; }
+            }
+            for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            mxn = fmaxf(mxn, sqrtf(sq));
+        }
+        __syncwarp();
+        float pen = in_o ? svar / (float)el.n + wm2 / (float)(el.n - 1) : 0.f;
+        for (int o = 16; o; o >>= 1) pen += __shfl_xor_sync(0xffffffffu, pen, o);
+        rew = __shfl_sync(0xffffffffu, rew, O);
+        if (lane == 0) {
+            done[r] = done_fn(done_kind, nrow[w], O);
+            if (penalty_kind != MB_PENALTY_NONE) {
+                const float p = penalty_kind == MB_PENALTY_MAX_VAR ? mxn : pen;
+                if (penalty) penalty[r] = p;
+                if (penalized_reward) penalized_reward[r] = rew - penalty_coef * p;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int launch_pe_dist_finish(const PeDev& m, const int32_t* elites, int n_elite, const float* fwd, const float* obs,
+                          const uint8_t* idx, const float* noise, int64_t B, int done_kind, float* next_obs,
+                          float* reward, float* done, float* delta_mean, float* delta_std, float* next_obs_mean,
+                          float* reward_mean, float* reward_std, int penalty_kind, float penalty_coef,
+                          float* penalty, float* penalized_reward, cudaStream_t s) {
+    EliteList el;
+    el.n = n_elite;
+    for (int i = 0; i < n_elite; ++i) el.id[i] = elites[i];
+    const int64_t blocks = (B + 7) / 8;
+    const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
+    k_pe_dist_finish<<<grid, 256, 0, s>>>(m, el, fwd, obs, idx, noise, B, done_kind, next_obs, reward, done,
+                                          delta_mean, delta_std, next_obs_mean, reward_mean, reward_std,
+                                          penalty_kind, penalty_coef, penalty, penalized_reward);
+    MB_CUDA_LAUNCH_CHECK("k_pe_dist_finish");
+    return MB_OK;
+}
+
 int launch_pe_rollout_dist_simt(const PeDev& m, const int32_t* elites, int n_elite, const float* obs,
                                 const float* act, const uint8_t* idx, const float* noise, int64_t B,
                                 int done_kind, float* next_obs, float* reward, float* done,

@@ -192,7 +192,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 const float* __restrict__ noise,
                 const int* __restrict__ perm, const int* __restrict__ totals,
                 int64_t seg, int done_kind, float* __restrict__ next_obs,
-                float* __restrict__ reward, float* __restrict__ done, RowsOut rows, int dbg) {
+                float* __restrict__ reward, float* __restrict__ done, RowsOut rows, TcForward fwd, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -208,7 +208,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     // the rows are laid out exactly like the destination (stride = destination row stride).
     const int W = 2 * O + A + 2;
     const bool bulk_rows = rows.n > 0 && !rows.ordered;
-    const int WS = bulk_rows ? (int)rows.stride : (W | 1);
+    const int WS = fwd.mode != 0 ? 2 * D : bulk_rows ? (int)rows.stride : (W | 1);   // forward mode: [mean D | log-std D]
     float* hrow = xin + kTcTM * IN;                               // [TM][WS]
     // constants, padded to 32 so the consumers are branch-free:
     //   cmean/cinv[j]: input column j = [obs | act | ones | pad]: x_norm = (x - cmean) * cinv, with
@@ -238,7 +238,13 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
         if ((dbg & 8) && blockIdx.x == 0 && (i) < 4 && lane == 0) tl[(i)][(slot)] = clock64(); \
     } while (0)
     __shared__ TileIndex tix;
-    if (threadIdx.x < 32) tile_index_build(tix, totals, m.mlp.ensemble_size, kTcTM);
+    __shared__ int fwd_total[kMaxMembers];
+    const bool direct = fwd.mode != 0;          // rows of every listed member in order, no bucket plan
+    if (threadIdx.x < 32) {
+        if (direct) fwd_total[threadIdx.x] = fwd.total[threadIdx.x];
+        __syncwarp();
+        tile_index_build(tix, direct ? fwd_total : totals, direct ? kMaxMembers : m.mlp.ensemble_size, kTcTM);
+    }
     __syncthreads();
     const int ntiles = tix.toff[kMaxMembers];
     const int n_my = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -289,10 +295,11 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
         //   stage_tile  : normalise, ones column, bf16 hi/lo split, layer-0 A operand, a_ready
         auto load_inputs = [&](int i) {
             const int4 ti = tile_at(tix, kTcTM, blockIdx.x + i * gridDim.x);
-            const int xrow = row < ti.z ? perm[(size_t)ti.x * seg + ti.y + row] : -1;
+            const int xrow = row >= ti.z ? -1 : direct ? ti.y + row : perm[(size_t)ti.x * seg + ti.y + row];
             if (xrow >= 0) {
-                const float* op = obs + (size_t)xrow * obs_stride;
-                const float* ap = act + (size_t)xrow * act_stride;
+                const size_t irow = (size_t)xrow + (direct ? (size_t)ti.x * (size_t)fwd.in_member_rows : 0);
+                const float* op = obs + irow * obs_stride;
+                const float* ap = act + irow * act_stride;
                 for (int j = 0; j < O; ++j) cp_async4(xr + j, op + j);
                 for (int j = 0; j < A; ++j) cp_async4(xr + O + j, ap + j);
             }
@@ -500,15 +507,15 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
         for (int i = 0; i < n_my; ++i) {
             const int g = i * L + L - 1;
             const int4 ti = tile_at(tix, kTcTM, blockIdx.x + i * gridDim.x);
-            const int r = row < ti.z ? perm[(size_t)ti.x * seg + ti.y + row] : -1;
+            const int r = row >= ti.z ? -1 : direct ? ti.y + row : perm[(size_t)ti.x * seg + ti.y + row];
             // the previous tile's rows must have left shared memory before they are refilled
-            if (bulk_rows && ht == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if ((bulk_rows || direct) && ht == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             // [32 max_logstd | 32 min_logstd] of the tile's member -> hc (all four head warps are
             // past the previous tile's use of hc once they meet at the named barrier below)
             const float* hb = reinterpret_cast<const float*>(pack + (size_t)ti.x * s.member_bytes + s.const_off);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (ht < 64) cp_async4(hc + ht, hb + ht);
-            if (r >= 0) {
+            if (r >= 0 && !direct) {
                 const float* eps = noise + (size_t)r * D;
                 const float* op = obs + (size_t)r * obs_stride;
                 for (int j = 0; j < D; ++j) cp_async4(epsr + j, eps + j);
@@ -538,6 +545,32 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(h_free);
+            if (direct) {
+                // all-member forward: this row's [mean | clamped log-std] -> shared memory, the
+                // tile's rows are consecutive in out[slot][B][2D]: one bulk store per tile
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    if (blk * 16 < D) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const int j = blk * 16 + jj;
+                            if (j < D) {
+                                ro[j] = __uint_as_float(acc[blk][jj]);
+                                ro[D + j] = fast_clamp_logstd(__uint_as_float(acc[2 + blk][jj]), hc[j], hc[32 + j]);
+                            }
+                        }
+                    }
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (ht == 0) {
+                    float* dst = fwd.out + ((size_t)fwd.slot_of[ti.x] * (size_t)fwd.B + (size_t)ti.y) * (size_t)WS;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(dst), "r"(smem_u32(hrow)), "r"((uint32_t)ti.z * (uint32_t)WS * 4u) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
+            }
             // straight-line over the columns; only loads/stores are predicated (pad columns carry
             // zeros through the maths)
 #pragma unroll
@@ -613,7 +646,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             }
             if (warp == kTcHeadWarp0) TL(i, 25);
         }
-        if (bulk_rows && ht == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if ((bulk_rows || direct) && ht == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -670,9 +703,40 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, int
     prof_begin(st);
     k_pe_rollout_tc<<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, obs_stride,
                                                     act, act_stride, noise, p.perm, p.totals, p.seg, done_kind,
-                                                    next_obs, reward, done, rows, dbg);
+                                                    next_obs, reward, done, rows, TcForward{}, dbg);
     prof_end(st);
     MB_CUDA_LAUNCH_CHECK("k_pe_rollout_tc");
+    return MB_OK;
+}
+
+bool tc_rollout_supported(const mb_mlp_desc& d) { return tc_shape(d).ok; }
+
+int launch_pe_forward_tc(const PeDev& m, const void* pack, const float* obs, const float* act, int per_member,
+                         int64_t B, const int* members, int n_members, float* out, cudaStream_t st) {
+    TcShape s = tc_shape(m.mlp);
+    if (!s.ok) { set_error("tcgen05 kernels do not support this model shape"); return MB_EUNSUPPORTED; }
+    TcForward fwd{};
+    fwd.mode = 1;
+    fwd.out = out;
+    fwd.B = B;
+    fwd.in_member_rows = per_member ? B : 0;
+    for (int k = 0; k < n_members; ++k) {
+        fwd.total[members[k]] = (int)B;
+        fwd.slot_of[members[k]] = k;
+    }
+    const size_t smem = tc_smem_bytes(s, m.O, m.A);
+    cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("k_pe_rollout_tc smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms -= reserved_sms();
+    const int64_t ntiles = (int64_t)n_members * ((B + kTcTM - 1) / kTcTM);
+    const int grid = ntiles < sms ? (int)ntiles : sms;
+    k_pe_rollout_tc<<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, m.O, act, m.A,
+                                                    nullptr, nullptr, nullptr, 0, MB_DONE_CHEETAH, nullptr, nullptr,
+                                                    nullptr, RowsOut{}, fwd, 0);
+    MB_CUDA_LAUNCH_CHECK("k_pe_rollout_tc(forward)");
     return MB_OK;
 }
 

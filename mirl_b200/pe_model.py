@@ -336,13 +336,19 @@ class B200PEModel(Component, nn.Module):
         if penalty_type is not None:
             pen = torch.empty(B, 1, device=dev)
             pr = torch.empty(B, 1, device=dev)
-        _lib.check(L.mb_pe_rollout_step_dist(
-            ctypes.byref(m), _lib.ptr(obs), _lib.ptr(action), _lib.ptr(idx), _lib.ptr(noise), B, kind,
-            el, n, _lib.ptr(next_obs), _lib.ptr(reward), _lib.ptr(done),
-            _lib.ptr(out["ensemble_delta_mean"]), _lib.ptr(out["ensemble_delta_std"]),
-            _lib.ptr(out["ensemble_next_obs_mean"]), _lib.ptr(out["ensemble_reward_mean"]),
-            _lib.ptr(out["ensemble_reward_std"]), _lib.PENALTY[penalty_type], float(penalty_coef),
-            _lib.ptr(pen), _lib.ptr(pr), _lib.stream()))
+        args = (_lib.ptr(obs), _lib.ptr(action), _lib.ptr(idx), _lib.ptr(noise), B, kind,
+                el, n, _lib.ptr(next_obs), _lib.ptr(reward), _lib.ptr(done),
+                _lib.ptr(out["ensemble_delta_mean"]), _lib.ptr(out["ensemble_delta_std"]),
+                _lib.ptr(out["ensemble_next_obs_mean"]), _lib.ptr(out["ensemble_reward_mean"]),
+                _lib.ptr(out["ensemble_reward_std"]), _lib.PENALTY[penalty_type], float(penalty_coef),
+                _lib.ptr(pen), _lib.ptr(pr))
+        if self._resolve_kernel() == "tcgen05":
+            # all-elite forward on the tensor cores, then one elementwise kernel
+            m = self._c_model(self._tc_pack())
+            ws = self._workspace(L.mb_pe_dist_workspace_bytes(ctypes.byref(m), B, n))
+            _lib.check(L.mb_pe_rollout_step_dist_tc(ctypes.byref(m), *args, _lib.ptr(ws), ws.numel(), _lib.stream()))
+        else:
+            _lib.check(L.mb_pe_rollout_step_dist(ctypes.byref(m), *args, _lib.stream()))
         # key order and aliasing follow pe_model.py:255-282
         info["ensemble_delta_mean"] = out["ensemble_delta_mean"]
         info["ensemble_next_obs_mean"] = out["ensemble_next_obs_mean"]
@@ -441,6 +447,15 @@ class B200PEModel(Component, nn.Module):
         B, E, D = obs.shape[-2], self.ensemble_size, self.obs_size + 1
         if per_member:
             assert obs.shape[0] == E and action.shape[0] == E
+        if normalize and self._resolve_kernel() == "tcgen05":
+            # tensor-core forward: [E][B][mean D | log-std D]; the two halves are returned as views
+            m = self._c_model(self._tc_pack())
+            both = torch.empty(E, B, 2 * D, device=dev)
+            mem = (ctypes.c_int32 * E)(*range(E))
+            if B > 0:
+                _lib.check(_lib.lib().mb_pe_forward_tc(ctypes.byref(m), _lib.ptr(obs), _lib.ptr(action),
+                                                       int(per_member), B, mem, E, _lib.ptr(both), _lib.stream()))
+            return both[..., :D], both[..., D:]
         mean = torch.empty(E, B, D, device=dev)
         logstd = torch.empty(E, B, D, device=dev)
         m = self._c_model(None)

@@ -25,19 +25,42 @@ def _kernel_or_skip(m, kernel):
         pytest.skip("tcgen05 kernel not built for this shape")
 
 
-def test_forward_matches_reference_fixture():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_forward_matches_reference_fixture(kernel):
     g = golden("pe_forward_mbpo.npz")
-    m, _ = make_pe_model(cases.MBPO, 11)
+    m, _ = make_pe_model(cases.MBPO, 11, kernel=kernel)
+    _kernel_or_skip(m, kernel)
     o, a = cases.rollout_inputs(12, 200)
     mean, ls = m.predict_distribution(T(o, "cuda"), T(a, "cuda"))
+    assert mean.shape == ls.shape == (7, 200, 18)
     assert_close(mean, g["mean"], what="mean")
     assert_close(ls, g["logstd"], what="logstd")
-    # SIMT fp32 is the same arithmetic class as the reference: report the margin too
-    assert norm_rel(mean, g["mean64"]) < 1e-5
+    # margin against the float64 reference: SIMT fp32 is the reference's own arithmetic class,
+    # the tensor-core path is the bf16x3 split (~2^-16 per product)
+    assert norm_rel(mean, g["mean64"]) < (1e-5 if kernel == "simt" else 5e-5)
 
 
-def test_forward_per_member_inputs_match_oracle():
-    m, p = make_pe_model(cases.MBPO, 11)
+@pytest.mark.parametrize("B", [1, 127, 129, 4099])
+def test_forward_tc_ragged_batches_match_simt(B):
+    """All-member forward on the tensor cores (rollout kernel in forward mode, tiles walk every
+    member's rows in order) against the SIMT forward, shared and per-member inputs."""
+    ms, _ = make_pe_model(cases.MBPO, 11, kernel="simt")
+    mt, _ = make_pe_model(cases.MBPO, 11, kernel="tcgen05")
+    _kernel_or_skip(mt, "tcgen05")
+    o, a = cases.rollout_inputs(900 + B, B)
+    for oo, aa in ((T(o, "cuda"), T(a, "cuda")),
+                   (T(o, "cuda")[None].repeat(7, 1, 1) * torch.arange(1, 8, device="cuda")[:, None, None] * 0.3,
+                    T(a, "cuda")[None].repeat(7, 1, 1))):
+        m1, l1 = ms.predict_distribution(oo, aa)
+        m2, l2 = mt.predict_distribution(oo, aa)
+        assert_close(m2, m1, what="mean")
+        assert_close(l2, l1, what="logstd")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_forward_per_member_inputs_match_oracle(kernel):
+    m, p = make_pe_model(cases.MBPO, 11, kernel=kernel)
+    _kernel_or_skip(m, kernel)
     bt = cases.train_batch(41, 7, 129)
     pt = to_torch(p)
     x = torch.cat([po.normalize(T(bt["observations"]), pt["obs_mean"], pt["obs_std"]),
@@ -85,9 +108,11 @@ def test_rollout_step_without_elites_draws_like_reference(kernel):
     assert_close(r, g["reward"], what="reward")
 
 
-def test_return_distribution_and_mopo_penalty():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_return_distribution_and_mopo_penalty(kernel):
     g = golden("pe_step_dist_mopo.npz")
-    m, _ = make_pe_model(cases.MOPO, 31, "hopper")
+    m, _ = make_pe_model(cases.MOPO, 31, "hopper", kernel=kernel)
+    _kernel_or_skip(m, kernel)
     m.remember_loss(LOSS_VEC10)
     assert list(m.elite_indices) == list(g["elite_indices"])
     o, a = cases.rollout_inputs(32, 128, env="hopper")
