@@ -32,6 +32,17 @@
 // on a_ready[ks]; the MMA warp starts layer l+1 on block 0 while the epilogue is still working
 // on the later blocks, accumulating into the OTHER of two TMEM accumulators.
 //
+// Two more modes share the pipeline.  Pool rows (mb_pe_rollout_step_rows): the head assembles the
+// collector's [obs | act | next_obs | reward | done] row in shared memory and either stores rows in
+// batch order or, in bucket order, sends the whole tile as one bulk copy (TMA store) per
+// destination -- the local pool and peer GPUs' pools over NVLink.  Forward mode (TcForward): the
+// tiles walk rows [0, B) of every listed member in order and the head bulk-stores
+// [mean | clamped log-std] rows: the all-member forward behind predict_distribution and the MOPO
+// penalised step.
+//
+// MB_TC_DEBUG (timing experiments, numerics wrong for 1/2/4/16): 1 one MMA per k-step, 2 no weight
+// copies, 4 no swish, 8 print a clock64 timeline of CTA 0's first tiles, 16 skip the input fence.
+//
 // mbarrier discipline: a waiter must observe EVERY phase of a barrier it waits on (parity
 // aliasing otherwise), so each consumer group has its own barrier(s): d_full (epilogue warps, all
 // hidden layers + the staging class on the last), d_last (head warps), h_free (MMA warp).
@@ -657,10 +668,8 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             for (int l = 0; l < L; ++l) printf("L%d %lld %lld | ", l, tl[i][2 * l] - t0, tl[i][2 * l + 1] - t0);
             printf("\n        EPI(dfull,done)   ");
             for (int l = 0; l + 1 < L; ++l) printf("L%d %lld %lld | ", l, tl[i][16 + 2 * l] - t0, tl[i][17 + 2 * l] - t0);
-            printf("\n        HEAD(dlast,done) %lld %lld  STAGE(dfull,done) %lld %lld  L2 waits: a_ready %lld w_full %lld\n",
-                   tl[i][24] - t0, tl[i][25] - t0, tl[i][33] - t0, tl[i][34] - t0, tl[i][36], tl[i][37]);
-            printf("        MMA L2 ks=10: top %lld a_ready %lld w_full %lld issued %lld synced %lld\n",
-                   tl[i][26] - t0, tl[i][27] - t0, tl[i][28] - t0, tl[i][29] - t0, tl[i][30] - t0);
+            printf("\n        HEAD(dlast,done) %lld %lld  STAGE(dfull,done) %lld %lld\n",
+                   tl[i][24] - t0, tl[i][25] - t0, tl[i][33] - t0, tl[i][34] - t0);
         }
     }
     if (warp == kTcMmaWarp) {
