@@ -94,7 +94,16 @@ k_tc_gemm(TgBatch gb, int nt_max) {
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float red[kTgThreads / 32];
-    const TgOp& op = gb.op[blockIdx.z / gb.nmem];
+    // this CTA's descriptor -> shared memory once (indexing the kernel-parameter array with a
+    // run-time index makes every later field access a slow indexed constant load)
+    __shared__ TgOp sop;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&gb.op[blockIdx.z / gb.nmem]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sop);
+        for (int i = threadIdx.x; i < (int)(sizeof(TgOp) / 4); i += kTgThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const TgOp& op = sop;
     const int zi = (int)(blockIdx.z % gb.nmem);
     const int e = gb.member[zi], slot = gb.slot0 + zi;
     const int NT = tg_ntile(op.N);
@@ -189,6 +198,21 @@ k_tc_gemm(TgBatch gb, int nt_max) {
         tc_fence_before();
         __syncthreads();
         }
+    // epilogue constants and this lane's bias columns are fetched before the last MMAs are waited for
+    const int mode = op.mode, M = op.M, out_act = op.out_act, ones_row = op.a_ones_row;
+    const float wd = op.wd;
+    const int row_lim = mode == TG_DW ? ones_row : M;                     // rows with a regular output
+    const int col = lane * 4;                                             // this lane's 4 columns of the tile
+    const int nb = n0 + col;
+    const bool col_ok = col < NT && nb < Nn;
+    const bool full = nb + 4 <= Nn;
+    float l2 = 0.f;
+    float4 cb4 = make_float4(0.f, 0.f, 0.f, 0.f);                          // FWD: bias of these columns
+    if (mode == TG_FWD && col_ok) {
+        const float* p = op.bias + (int64_t)e * op.bias_ms + nb;
+        if (full && (reinterpret_cast<uintptr_t>(p) & 15) == 0) cb4 = __ldg(reinterpret_cast<const float4*>(p));
+        else { cb4.x = __ldg(p); if (nb + 1 < Nn) cb4.y = __ldg(p + 1); if (nb + 2 < Nn) cb4.z = __ldg(p + 2); if (nb + 3 < Nn) cb4.w = __ldg(p + 3); }
+    }
     {
         const int s = (nch - 1) & 1;
         mbar_wait_relaxed(bar0 + 8u * (uint32_t)s, s == 0 ? ph0 : ph1);
@@ -217,20 +241,6 @@ k_tc_gemm(TgBatch gb, int nt_max) {
     }
     tc_fence_before();
     __syncthreads();
-    const int mode = op.mode, M = op.M, out_act = op.out_act, ones_row = op.a_ones_row;
-    const float wd = op.wd;
-    const int row_lim = mode == TG_DW ? ones_row : M;                     // rows with a regular output
-    const int col = lane * 4;                                             // this lane's 4 columns of the tile
-    const int nb = n0 + col;
-    const bool col_ok = col < NT && nb < Nn;
-    const bool full = nb + 4 <= Nn;
-    float l2 = 0.f;
-    float4 cb4 = make_float4(0.f, 0.f, 0.f, 0.f);                          // FWD: bias of these columns
-    if (mode == TG_FWD && col_ok) {
-        const float* p = op.bias + (int64_t)e * op.bias_ms + nb;
-        if (full && (reinterpret_cast<uintptr_t>(p) & 15) == 0) cb4 = __ldg(reinterpret_cast<const float4*>(p));
-        else { cb4.x = __ldg(p); if (nb + 1 < Nn) cb4.y = __ldg(p + 1); if (nb + 2 < Nn) cb4.z = __ldg(p + 2); if (nb + 3 < Nn) cb4.w = __ldg(p + 3); }
-    }
     auto ld4 = [&](const float* p) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (full && (reinterpret_cast<uintptr_t>(p) & 15) == 0) x = __ldg(reinterpret_cast<const float4*>(p));
@@ -241,7 +251,7 @@ k_tc_gemm(TgBatch gb, int nt_max) {
     const float* wb = mode == TG_DW ? op.w + (int64_t)e * op.w_ms : nullptr;
     float* ob = op.out + (int64_t)slot * op.out_ss + (int64_t)e * op.out_ms;
     const int64_t ldz = op.ldz, ldo = op.ldo;
-    constexpr int kRU = 4;                                                 // rows in flight per warp
+    constexpr int kRU = 8;                                                 // rows in flight per warp (128 rows / 16 warps)
     for (int rb = warp * kRU; rb < kUmmaM; rb += (kTgThreads / 32) * kRU) {
         float4 c[kRU], v[kRU];
         bool live[kRU], plain[kRU];
