@@ -248,6 +248,45 @@ def test_redq_target_matches_reference_fixture():
     assert_close(y, g["td_target"], what="td target")
 
 
+@pytest.mark.parametrize("B", [1, 37, 129, 300, 1000])
+def test_critic_ragged_batches_match_oracle(B):
+    """REDQ (2x256) and TQC (3x512 x 25 atoms) forward at batch sizes that are not multiples of
+    the 128-row UMMA tile: hidden/output layers run on the tcgen05 GEMM (partial row tiles, N
+    tiles of 128/128/16/32 columns, reductions of 4 and 8 stages)."""
+    x = cases.critic_inputs(700 + B, B)
+    o, a = T(x["obs"], "cuda"), T(x["act"], "cuda")
+    q, (W, b) = make_critic("redq", 71)
+    _, info = q.value(o, a, only_return_ensemble=True)
+    ref = co.ensemble_q([T(w) for w in W], [T(v) for v in b], T(x["obs"]), T(x["act"]))
+    assert_close(info["ensemble_value"], ref, what="redq ensemble")
+    t, (W, b) = make_critic("tqc", 81)
+    v, info = t.value(o, a, return_atoms=True, percentage_drop=8)
+    rv, ratoms = co.tqc_atoms([T(w) for w in W], [T(v_) for v_ in b], T(x["obs"]), T(x["act"]), percentage_drop=8)
+    assert_close(v, rv, what="tqc value")
+    assert_close(info["value_atoms"], ratoms, what="tqc atoms")
+
+
+@pytest.mark.parametrize("B", [5, 100, 257])
+def test_train_gradients_ragged_batches_match_oracle(B):
+    """Analytic gradients through the tcgen05 forward / dX / dW GEMMs at batch sizes that leave
+    partial 128-row tiles and partial 64-element reduction stages in the dW GEMM."""
+    m, p = make_pe_model(cases.MBPO, 11)
+    bt = _batch(43 + B, 7, B)
+    grads, el, terms = _grads(m, bt, False)
+    pt = to_torch(p)
+    cb = {k: v.cpu() for k, v in bt.items()}
+    ref = po.model_loss_grads(pt, cb["observations"], cb["actions"], cb["deltas"], cb["rewards"], cb["terminals"],
+                              ignore_terminal_state=False, weight_decay=cases.WEIGHT_DECAY)
+    assert_close(terms.sum(), ref["loss"], what="loss")
+    assert_close(el, ref["ensemble_loss"], what="ensemble loss")
+    mod = m.module
+    for l in range(5):
+        assert norm_rel(mod.weight(l, flat=grads), ref["W"][l]) < 1e-3, "dW%d" % l
+        assert norm_rel(mod.bias(l, flat=grads).reshape(ref["b"][l].shape), ref["b"][l]) < 1e-3, "db%d" % l
+    assert norm_rel(mod.logstd_bound(0, flat=grads).reshape(ref["max_logstd"].shape), ref["max_logstd"]) < 1e-3
+    assert norm_rel(mod.logstd_bound(1, flat=grads).reshape(ref["min_logstd"].shape), ref["min_logstd"]) < 1e-3
+
+
 def test_tqc_target_matches_reference_fixture():
     g = golden("tqc.npz")
     q, _ = make_critic("tqc", 81)
