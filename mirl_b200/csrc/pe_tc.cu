@@ -243,6 +243,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcMaxStages + kTcMaxKs + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool ts = !(dbg & 64);             // A_hi of layers >= 1 in tensor memory (.ts MMAs); 64 = all-smem operands
     __shared__ long long tl[4][40];          // debug timeline (MB_TC_DEBUG & 8), CTA 0 only
 #define TL(i, slot)                                                                       \
     do {                                                                                  \
@@ -369,8 +370,19 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 #pragma unroll
                     for (int t = 0; t < 16; ++t)
                         v[t] = (dbg & 4) ? __uint_as_float(cur[t]) : fast_swish(__uint_as_float(cur[t]));
-                    split_store8(v, sA_hi + (2 * ks) * 2048u + row_off, sA_lo + (2 * ks) * 2048u + row_off);
-                    split_store8(v + 8, sA_hi + (2 * ks + 1) * 2048u + row_off, sA_lo + (2 * ks + 1) * 2048u + row_off);
+                    if (ts) {
+                        // hi half of the next A operand goes back into TENSOR memory, in place over
+                        // the first 8 of the 16 accumulator columns this warp has just consumed
+                        // (the MMA then reads it with the .ts form: no shared-memory traffic for
+                        // two of the three MMAs of a k-step); lo half -> shared memory as before
+                        uint32_t h[8];
+                        split16_hi_regs_lo_smem(v, h, sA_lo + (2 * ks) * 2048u + row_off, sA_lo + (2 * ks + 1) * 2048u + row_off);
+                        tc_st8(dcol + ks * 16, h);
+                        tc_wait_st();
+                    } else {
+                        split_store8(v, sA_hi + (2 * ks) * 2048u + row_off, sA_lo + (2 * ks) * 2048u + row_off);
+                        split_store8(v + 8, sA_hi + (2 * ks + 1) * 2048u + row_off, sA_lo + (2 * ks + 1) * 2048u + row_off);
+                    }
                     fence_proxy_async();
                     tc_fence_before();
                     __syncwarp();
@@ -447,6 +459,23 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     const uint64_t b_lo = b_hi + lo_off;
                     const bool two = ks + 1 < nks;
                     if (elect_one()) {
+                        if (ts && l > 0) {
+                            // A_hi of this layer sits in the OTHER accumulator buffer, k-step ks at
+                            // columns [16 ks, 16 ks + 8) (written in place by the previous epilogue)
+                            const uint32_t at = tmem + (uint32_t)(((g - 1) & 1) * 256) + (uint32_t)ks * 16u;
+                            tc_mma_bf16_ts(d_tmem, at, b_hi, idesc, ks > 0 ? 1u : 0u);
+                            if (!(dbg & 1)) {
+                                tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+                                tc_mma_bf16_ts(d_tmem, at, b_lo, idesc, 1u);
+                            }
+                            if (two) {
+                                tc_mma_bf16_ts(d_tmem, at + 16u, b_hi + ks_off, idesc, 1u);
+                                if (!(dbg & 1)) {
+                                    tc_mma_bf16(d_tmem, a_lo + 256, b_hi + ks_off, idesc, 1u);
+                                    tc_mma_bf16_ts(d_tmem, at + 16u, b_lo + ks_off, idesc, 1u);
+                                }
+                            }
+                        } else {
                         tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
                         if (!(dbg & 1)) {
                             tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
@@ -458,6 +487,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                                 tc_mma_bf16(d_tmem, a_lo + 256, b_hi + ks_off, idesc, 1u);
                                 tc_mma_bf16(d_tmem, a_hi + 256, b_lo + ks_off, idesc, 1u);
                             }
+                        }
                         }
                         tc_commit(w_empty(stage));
                         if (ks + 2 >= nks) {

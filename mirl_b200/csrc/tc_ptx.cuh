@@ -88,6 +88,23 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// A operand from tensor memory (".ts" form): [a_tmem] = 128 lanes x 8 columns per k-step, two bf16
+// per 32-bit column
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
@@ -134,6 +151,18 @@ __device__ __forceinline__ void split_store8(const float* v, uint32_t hi_addr, u
     }
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+}
+// split 16 fp32 values into packed bf16 hi (8 words, to registers) and lo (two 16-byte core-matrix rows)
+__device__ __forceinline__ void split16_hi_regs_lo_smem(const float* v, uint32_t (&h)[8], uint32_t lo_addr0, uint32_t lo_addr1) {
+    uint32_t l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        h[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
+        const float ha = __uint_as_float(h[i] << 16), hb = __uint_as_float(h[i] & 0xffff0000u);
+        l[i] = cvt_bf16x2(v[2 * i] - ha, v[2 * i + 1] - hb);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr0), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr1), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
 }
 // softplus / clamp with MUFU-based exp/log for the head (absolute error ~1e-7 on a log-std)
 __device__ __forceinline__ float fast_softplus(float x) { return x > 20.0f ? x : __logf(1.0f + __expf(x)); }
