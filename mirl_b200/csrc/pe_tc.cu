@@ -371,19 +371,26 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     for (int t = 0; t < 16; ++t)
                         v[t] = (dbg & 4) ? __uint_as_float(cur[t]) : fast_swish(__uint_as_float(cur[t]));
                     if (ts) {
-                        // hi half of the next A operand goes back into TENSOR memory, in place over
-                        // the first 8 of the 16 accumulator columns this warp has just consumed
-                        // (the MMA then reads it with the .ts form: no shared-memory traffic for
-                        // two of the three MMAs of a k-step); lo half -> shared memory as before
-                        uint32_t h[8];
-                        split16_hi_regs_lo_smem(v, h, sA_lo + (2 * ks) * 2048u + row_off, sA_lo + (2 * ks + 1) * 2048u + row_off);
+                        // The next layer's A operand goes back into TENSOR memory, in place over
+                        // the 16 accumulator columns this warp has just consumed: bf16 hi pairs in
+                        // columns [16ks, 16ks+8), lo pairs in [16ks+8, 16ks+16).  All three MMAs of
+                        // a k-step then use the .ts form (A from TMEM, only B from shared memory):
+                        // no shared-memory stores, no proxy fence, no extra TMEM columns.
+                        uint32_t h[8], lo[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            h[t] = cvt_bf16x2(v[2 * t], v[2 * t + 1]);
+                            const float ha = __uint_as_float(h[t] << 16), hb = __uint_as_float(h[t] & 0xffff0000u);
+                            lo[t] = cvt_bf16x2(v[2 * t] - ha, v[2 * t + 1] - hb);
+                        }
                         tc_st8(dcol + ks * 16, h);
+                        tc_st8(dcol + ks * 16 + 8, lo);
                         tc_wait_st();
                     } else {
                         split_store8(v, sA_hi + (2 * ks) * 2048u + row_off, sA_lo + (2 * ks) * 2048u + row_off);
                         split_store8(v + 8, sA_hi + (2 * ks + 1) * 2048u + row_off, sA_lo + (2 * ks + 1) * 2048u + row_off);
                     }
-                    fence_proxy_async();
+                    if (!ts) fence_proxy_async();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_ready(ks / kTcClasses));
@@ -460,18 +467,19 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     const bool two = ks + 1 < nks;
                     if (elect_one()) {
                         if (ts && l > 0) {
-                            // A_hi of this layer sits in the OTHER accumulator buffer, k-step ks at
-                            // columns [16 ks, 16 ks + 8) (written in place by the previous epilogue)
+                            // A of this layer sits in the OTHER accumulator buffer, k-step ks at columns
+                            // [16 ks, 16 ks + 8) (hi) and [16 ks + 8, 16 ks + 16) (lo), written in place by
+                            // the previous layer's epilogue
                             const uint32_t at = tmem + (uint32_t)(((g - 1) & 1) * 256) + (uint32_t)ks * 16u;
                             tc_mma_bf16_ts(d_tmem, at, b_hi, idesc, ks > 0 ? 1u : 0u);
                             if (!(dbg & 1)) {
-                                tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+                                tc_mma_bf16_ts(d_tmem, at + 8u, b_hi, idesc, 1u);
                                 tc_mma_bf16_ts(d_tmem, at, b_lo, idesc, 1u);
                             }
                             if (two) {
                                 tc_mma_bf16_ts(d_tmem, at + 16u, b_hi + ks_off, idesc, 1u);
                                 if (!(dbg & 1)) {
-                                    tc_mma_bf16(d_tmem, a_lo + 256, b_hi + ks_off, idesc, 1u);
+                                    tc_mma_bf16_ts(d_tmem, at + 24u, b_hi + ks_off, idesc, 1u);
                                     tc_mma_bf16_ts(d_tmem, at + 16u, b_lo + ks_off, idesc, 1u);
                                 }
                             }
