@@ -61,7 +61,7 @@ namespace mb {
 constexpr int kTcHeadWarp0 = 0;        // warps 0-3
 constexpr int kTcEpiWarp0 = 4;         // warps 4-19
 #ifndef MB_TC_CLASSES
-#define MB_TC_CLASSES 3
+#define MB_TC_CLASSES 2
 #endif
 constexpr int kTcClasses = MB_TC_CLASSES;   // column-block classes (warps per TMEM lane quarter)
 constexpr int kTcEpiWarps = 4 * kTcClasses;
@@ -71,7 +71,10 @@ constexpr int kTcMmaWarp = kTcProdWarp + 1;
 constexpr int kTcThreads = (kTcMmaWarp + 1) * 32;
 constexpr int kTcTM = 128;            // rows per tile (UMMA M)
 constexpr int kTcMaxKs = 16;          // k-steps per layer supported (HP <= 256)
-constexpr int kTcMaxStages = 3;       // ring slots (two k-steps each)
+#ifndef MB_TC_STAGES
+#define MB_TC_STAGES 3
+#endif
+constexpr int kTcMaxStages = MB_TC_STAGES;   // ring slots (two k-steps each)
 constexpr int kTcSmemLimit = 227 * 1024;
 // x with x*sigmoid(x) == 1: the "ones" column of the next layer's A operand
 constexpr float kSwishOne = 1.2784645427610738f;
@@ -106,7 +109,7 @@ static int ru16(int x) { return (x + 15) & ~15; }
 
 
 static size_t tc_smem_bytes(const TcShape& s, int O, int A) {
-    size_t a = (size_t)2 * kTcTM * s.HP * 2;          // A hi + lo
+    size_t a = (size_t)2 * kTcTM * s.K0P * 2;         // layer-0 A operand hi + lo (later layers: tensor memory)
     size_t ring = (size_t)s.stages * s.slot;
     size_t misc = (size_t)kTcTM * ((O + A) + (2 * O + A + 2 + kRowPadMax)) * 4 + (size_t)(128 + 64) * 4 +
                   1024;              // staging, head pool rows (any allowed row stride), constants, barriers
@@ -208,7 +211,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const int O = m.O, A = m.A, D = O + 1, L = s.L, IN = O + A;
-    const uint32_t a_bytes = (uint32_t)kTcTM * s.HP * 2;          // one of hi / lo
+    const uint32_t a_bytes = (uint32_t)kTcTM * s.K0P * 2;         // layer-0 operand, one of hi / lo
     const uint32_t sA_hi = smem_base;
     const uint32_t sA_lo = sA_hi + a_bytes;
     const uint32_t sRing = sA_lo + a_bytes;
@@ -243,7 +246,6 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcMaxStages + kTcMaxKs + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool ts = !(dbg & 64);             // A_hi of layers >= 1 in tensor memory (.ts MMAs); 64 = all-smem operands
     __shared__ long long tl[4][40];          // debug timeline (MB_TC_DEBUG & 8), CTA 0 only
 #define TL(i, slot)                                                                       \
     do {                                                                                  \
@@ -370,27 +372,21 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 #pragma unroll
                     for (int t = 0; t < 16; ++t)
                         v[t] = (dbg & 4) ? __uint_as_float(cur[t]) : fast_swish(__uint_as_float(cur[t]));
-                    if (ts) {
-                        // The next layer's A operand goes back into TENSOR memory, in place over
-                        // the 16 accumulator columns this warp has just consumed: bf16 hi pairs in
-                        // columns [16ks, 16ks+8), lo pairs in [16ks+8, 16ks+16).  All three MMAs of
-                        // a k-step then use the .ts form (A from TMEM, only B from shared memory):
-                        // no shared-memory stores, no proxy fence, no extra TMEM columns.
-                        uint32_t h[8], lo[8];
+                    // The next layer's A operand goes back into TENSOR memory, in place over
+                    // the 16 accumulator columns this warp has just consumed: bf16 hi pairs in
+                    // columns [16ks, 16ks+8), lo pairs in [16ks+8, 16ks+16).  All three MMAs of
+                    // a k-step then use the .ts form (A from TMEM, only B from shared memory):
+                    // no shared-memory stores, no proxy fence, no extra TMEM columns.
+                    uint32_t h[8], lo[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            h[t] = cvt_bf16x2(v[2 * t], v[2 * t + 1]);
-                            const float ha = __uint_as_float(h[t] << 16), hb = __uint_as_float(h[t] & 0xffff0000u);
-                            lo[t] = cvt_bf16x2(v[2 * t] - ha, v[2 * t + 1] - hb);
-                        }
-                        tc_st8(dcol + ks * 16, h);
-                        tc_st8(dcol + ks * 16 + 8, lo);
-                        tc_wait_st();
-                    } else {
-                        split_store8(v, sA_hi + (2 * ks) * 2048u + row_off, sA_lo + (2 * ks) * 2048u + row_off);
-                        split_store8(v + 8, sA_hi + (2 * ks + 1) * 2048u + row_off, sA_lo + (2 * ks + 1) * 2048u + row_off);
+                    for (int t = 0; t < 8; ++t) {
+                        h[t] = cvt_bf16x2(v[2 * t], v[2 * t + 1]);
+                        const float ha = __uint_as_float(h[t] << 16), hb = __uint_as_float(h[t] & 0xffff0000u);
+                        lo[t] = cvt_bf16x2(v[2 * t] - ha, v[2 * t + 1] - hb);
                     }
-                    if (!ts) fence_proxy_async();
+                    tc_st8(dcol + ks * 16, h);
+                    tc_st8(dcol + ks * 16 + 8, lo);
+                    tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_ready(ks / kTcClasses));
@@ -466,7 +462,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     const uint64_t b_lo = b_hi + lo_off;
                     const bool two = ks + 1 < nks;
                     if (elect_one()) {
-                        if (ts && l > 0) {
+                        if (l > 0) {
                             // A of this layer sits in the OTHER accumulator buffer, k-step ks at columns
                             // [16 ks, 16 ks + 8) (hi) and [16 ks + 8, 16 ks + 16) (lo), written in place by
                             // the previous layer's epilogue
@@ -628,6 +624,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) {
                         const int j = blk * 16 + jj;
+                        if (j >= D && !(dbg & 32)) continue;                    // uniform: pad columns cost nothing
                         const bool in_d = r >= 0 && j < D, in_o = r >= 0 && j < O;
                         const float mu = __uint_as_float(acc[blk][jj]);         // bias already in the GEMM
                         const float ls = fast_clamp_logstd(__uint_as_float(acc[2 + blk][jj]), hc[j], hc[32 + j]);
