@@ -65,6 +65,7 @@ constexpr int kTcEpiWarp0 = 4;         // warps 4-19
 #endif
 constexpr int kTcClasses = MB_TC_CLASSES;   // column-block classes (warps per TMEM lane quarter)
 constexpr int kTcEpiWarps = 4 * kTcClasses;
+constexpr int kTcRound = 2;             // 16-column blocks per a_ready round = k-steps per MMA iteration
 constexpr int kTcStageClass = kTcClasses - 1;   // epilogue class that also stages the next tile's inputs
 constexpr int kTcProdWarp = kTcEpiWarp0 + kTcEpiWarps;
 constexpr int kTcMmaWarp = kTcProdWarp + 1;
@@ -265,7 +266,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < s.stages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
-        for (int i = 0; i < kTcMaxKs; ++i) mbar_init(a_ready(i), kTcEpiWarps);   // one arrival per warp per round
+        for (int i = 0; i < kTcMaxKs; ++i) mbar_init(a_ready(i), 4 * kTcRound);  // one arrival per (block, lane quarter) of the round
         mbar_init(x_ready, 4);
         mbar_init(d_full(0), 1);
         mbar_init(d_full(1), 1);
@@ -361,7 +362,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 uint32_t r0[16], r1[16];
                 // one 16-column block: wait for its TMEM load, prefetch the next one, then
                 // swish + bf16 hi/lo split -> next layer's A operand (k-step ks).  Blocks are
-                // published per ROUND (the kTcClasses blocks ks = r*kTcClasses + c, one per class):
+                // published per ROUND of kTcRound consecutive blocks (block ks belongs to class ks % kTcClasses):
                 // every epilogue warp arrives on a_ready[r] exactly once per layer, with or
                 // without a block of its own in that round, so the MMA warp polls one barrier per
                 // round instead of one per k-step.
@@ -389,7 +390,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(a_ready(ks / kTcClasses));
+                    if (lane == 0) mbar_arrive(a_ready(ks / kTcRound));
                 };
                 if (c < s.nksh) tc_ld16(dcol + c * 16, r0);
                 int ks = c;
@@ -397,11 +398,12 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     do_block(ks, r0, r1);
                     if (ks + kTcClasses < s.nksh) do_block(ks + kTcClasses, r1, r0);
                 }
-                // rounds in which this class has no block (only the last one can be partial)
+                // a round expects kTcRound blocks x 4 quarters; the blocks missing from the last,
+                // partial round are arrived for by the class that would have owned them
                 if (lane == 0) {
-                    const int rounds = (s.nksh + kTcClasses - 1) / kTcClasses;
-                    const int mine = (s.nksh - c + kTcClasses - 1) / kTcClasses;    // blocks this class processed
-                    for (int r = mine; r < rounds; ++r) mbar_arrive(a_ready(r));
+                    const int padded = (s.nksh + kTcRound - 1) / kTcRound * kTcRound;
+                    for (int b = s.nksh; b < padded; ++b)
+                        if (b % kTcClasses == c) mbar_arrive(a_ready(b / kTcRound));
                 }
                 if (warp == kTcEpiWarp0) TL(i, 17 + l * 2);
             }
@@ -450,7 +452,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 int rounds_seen = 0;                  // a_ready rounds of this layer already observed
                 for (int ks = 0; ks < nks; ks += 2) {
                     if (l > 0) {                      // rounds covering k-steps ks and ks+1
-                        const int need = (ks + 1 < nks ? ks + 1 : ks) / kTcClasses;
+                        const int need = (ks + 1 < nks ? ks + 1 : ks) / kTcRound;
                         for (; rounds_seen <= need; ++rounds_seen) {
                             while (!mbar_try_wait(a_ready(rounds_seen), (aphase >> rounds_seen) & 1u)) {}
                             aphase ^= 1u << rounds_seen;
