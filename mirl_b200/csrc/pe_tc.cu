@@ -369,21 +369,27 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 auto do_block = [&](int ks, uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
                     tc_wait_ld();
                     if (ks + kTcClasses < s.nksh) tc_ld16(dcol + (ks + kTcClasses) * 16, nxt);
-                    float v[16];
-#pragma unroll
-                    for (int t = 0; t < 16; ++t)
-                        v[t] = (dbg & 4) ? __uint_as_float(cur[t]) : fast_swish(__uint_as_float(cur[t]));
-                    // The next layer's A operand goes back into TENSOR memory, in place over
-                    // the 16 accumulator columns this warp has just consumed: bf16 hi pairs in
-                    // columns [16ks, 16ks+8), lo pairs in [16ks+8, 16ks+16).  All three MMAs of
-                    // a k-step then use the .ts form (A from TMEM, only B from shared memory):
-                    // no shared-memory stores, no proxy fence, no extra TMEM columns.
+                    // swish + bf16 hi/lo split on PAIRS of elements (packed fp32 arithmetic)
                     uint32_t h[8], lo[8];
+                    const uint64_t kNegLog2e = pack2(-1.4426950408889634f, -1.4426950408889634f);
+                    const uint64_t kOne = pack2(1.0f, 1.0f);
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
-                        h[t] = cvt_bf16x2(v[2 * t], v[2 * t + 1]);
-                        const float ha = __uint_as_float(h[t] << 16), hb = __uint_as_float(h[t] & 0xffff0000u);
-                        lo[t] = cvt_bf16x2(v[2 * t] - ha, v[2 * t + 1] - hb);
+                        const uint64_t z = pack2(__uint_as_float(cur[2 * t]), __uint_as_float(cur[2 * t + 1]));
+                        float e0, e1;
+                        unpack2(mul2(z, kNegLog2e), e0, e1);
+                        const uint64_t y = add2(pack2(ex2_ftz(e0), ex2_ftz(e1)), kOne);
+                        float y0, y1;
+                        unpack2(y, y0, y1);
+                        uint64_t a = mul2(z, pack2(rcp_ftz(y0), rcp_ftz(y1)));            // swish(z)
+                        if (dbg & 4) a = z;
+                        float a0, a1;
+                        unpack2(a, a0, a1);
+                        h[t] = cvt_bf16x2(a0, a1);
+                        const uint64_t hf = pack2(__uint_as_float(h[t] << 16), __uint_as_float(h[t] & 0xffff0000u));
+                        float l0, l1;
+                        unpack2(sub2(a, hf), l0, l1);
+                        lo[t] = cvt_bf16x2(l0, l1);
                     }
                     tc_st8(dcol + ks * 16, h);
                     tc_st8(dcol + ks * 16 + 8, lo);

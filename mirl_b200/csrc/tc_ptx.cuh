@@ -134,6 +134,32 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 __device__ __forceinline__ float fast_swish(float z) {
     return z * rcp_ftz(1.0f + ex2_ftz(z * -1.4426950408889634f));
 }
+// ---- packed fp32 pairs (sm_100 FMUL2 / FADD2 / FFMA2): one issue slot for two lanes of work.  The
+// epilogue is issue/latency bound (moving MUFU work to the FMA pipe made it slower), so fewer
+// instructions per element is what pays.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 // {hi(b) : hi(a)} packed bf16x2 (a in the low half = lower address)
 __device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
     uint32_t d;
