@@ -16,21 +16,24 @@
 // weights are pre-split and pre-arranged (k_tc_pack) in exactly the UMMA shared-memory layout
 // (K-major, no swizzle, 8x8 core matrices), one contiguous "stage" per 16-deep k-step, so the
 // producer warp streams them from L2 with plain 1-D bulk async copies (cp.async.bulk ->
-// UBLKCP) into a ring; no tensor maps.  Activations never leave the SM: the epilogue warps read
-// the accumulator from TMEM (tcgen05.ld), apply swish, split to bf16 hi/lo and write the next
-// layer's A operand straight into shared memory in UMMA layout.
+// UBLKCP) into a ring; no tensor maps.  Activations never leave TENSOR memory: the epilogue warps
+// read a 16-column block of the accumulator (tcgen05.ld), apply swish, split to bf16 hi/lo and
+// write the packed halves back with tcgen05.st in place over the columns they have just consumed
+// -- which is k-step k of the next layer's A operand, read by the MMAs in the .ts form (A from
+// TMEM, B from shared memory).  Only layer 0's 32-wide input operand goes through shared memory.
 //
-// Pipeline (576 threads, 1 CTA/SM, persistent over tiles):
-//   warps 0-3   head: last-layer epilogue (clamp, sample, de-normalise, done) of tile t while the
-//               other warps already run tile t+1
-//   warps 4-15  epilogue, 3 classes x 4 TMEM lane quarters: warp w owns TMEM lanes 32*(w%4).. and the
-//               16-column blocks ks = c (mod 3), c = (w-4)/4; the last class (warps 12-15) additionally
-//               stages the next tile's inputs.  (2, 4 and 5 classes were measured slower.)
-//   warp  16    weight producer (one elected lane)
-//   warp  17    MMA issuer (warp-uniform control flow, one elected lane issues) + TMEM allocation
-// The epilogue of layer l publishes its output per 16-column block (= one k-step of layer l+1)
-// on a_ready[ks]; the MMA warp starts layer l+1 on block 0 while the epilogue is still working
-// on the later blocks, accumulating into the OTHER of two TMEM accumulators.
+// Pipeline (448 threads, 1 CTA/SM, persistent over tiles):
+//   warps 0-3   head: last-layer epilogue (clamp, sample, de-normalise, done, pool rows) of tile t
+//               while the other warps already run tile t+1
+//   warps 4-11  epilogue, 2 classes x 4 TMEM lane quarters: warp w owns TMEM lanes 32*(w%4).. and the
+//               16-column blocks ks = c (mod 2), c = (w-4)/4; the last class additionally stages the
+//               next tile's inputs.  (1, 3 and 4 classes were measured slower.)
+//   warp  12    weight producer (one elected lane)
+//   warp  13    MMA issuer (warp-uniform control flow, one elected lane issues) + TMEM allocation
+// The epilogue of layer l publishes its output per round of two 16-column blocks (= the two k-steps
+// of one MMA iteration) on a_ready[round]; the MMA warp starts layer l+1 on round 0 while the
+// epilogue is still working on the later blocks, accumulating into the OTHER of two TMEM
+// accumulators (whose previous contents, the A operand of layer l, are dead by then).
 //
 // Two more modes share the pipeline.  Pool rows (mb_pe_rollout_step_rows): the head assembles the
 // collector's [obs | act | next_obs | reward | done] row in shared memory and either stores rows in
