@@ -11,6 +11,7 @@ B200MBPOCollector     MBPOCollector                                mirl/agents/m
 B200MOPOCollector     MOPOCollector                                mirl/agents/mbpo/mopo_collector.py
 B200EnsembleQValue    EnsembleQValue                               mirl/values/ensemble_value.py
 B200TQCQValue         TQCQValue                                    mirl/values/distributional_value.py
+B200DevicePool        SimplePool (imagined-data pool, in HBM)      mirl/pools/simple_pool.py
 ====================  ===========================================  ============================
 
 All computation goes through ``libmirl_b200.so`` (``include/mirl_b200.h``); there is no PyTorch
@@ -20,6 +21,7 @@ from .pe_model import B200PEModel                      # noqa: F401
 from .pe_model_trainer import B200PEModelTrainer       # noqa: F401
 from .values import B200EnsembleQValue, B200TQCQValue  # noqa: F401
 from .collectors import B200MBPOCollector, B200MOPOCollector  # noqa: F401
+from .pools import B200DevicePool                      # noqa: F401
 
 __all__ = ["B200PEModel", "B200PEModelTrainer", "B200EnsembleQValue", "B200TQCQValue",
-           "B200MBPOCollector", "B200MOPOCollector"]
+           "B200MBPOCollector", "B200MOPOCollector", "B200DevicePool"]

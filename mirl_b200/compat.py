@@ -36,6 +36,28 @@ if _reference_importable():
     except ImportError:                                         # reference present, deps missing
         HAVE_REFERENCE = False
 
+# ``pool`` items derive from mirl.pools.base_pool.Pool (mirl/pools/base_pool.py:5-32)
+Pool = None
+if HAVE_REFERENCE:
+    try:
+        from mirl.pools.base_pool import Pool                   # noqa: F401
+    except Exception:                                           # pragma: no cover
+        Pool = None
+if Pool is None:
+
+    class Pool(object):
+        """mirl/pools/base_pool.py:5-32 (interface only)."""
+
+        def __init__(self, env):
+            pass
+
+        def start_new_path(self, o):
+            pass
+
+        def end_a_path(self, next_o):
+            pass
+
+
 if not HAVE_REFERENCE:
 
     class Component:

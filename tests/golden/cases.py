@@ -110,3 +110,18 @@ def mlp_state_dict(W, b, module_prefix="module."):
             sd["%snet.%d.weight_net%d" % (module_prefix, 2 * l, e)] = W[l][e]
             sd["%snet.%d.bias_net%d" % (module_prefix, 2 * l, e)] = b[l][e]
     return sd
+
+
+# ---- SimplePool fixture (tests/golden/pool.npz) ------------------------------------------------
+POOL_ADDS = [300, 450, 200, 400, 1, 650]        # capacity 1000: the 3rd add reaches the end, later ones wrap
+
+
+def pool_samples(seed, n, obs=OBS, act=ACT):
+    rs = np.random.RandomState(seed)
+    return {
+        "observations": rs.standard_normal((n, obs)).astype(np.float32),
+        "actions": rs.uniform(-1, 1, (n, act)).astype(np.float32),
+        "next_observations": rs.standard_normal((n, obs)).astype(np.float32),
+        "rewards": rs.standard_normal((n, 1)).astype(np.float32),
+        "terminals": (rs.uniform(size=(n, 1)) < 0.1).astype(np.float32),
+    }

@@ -262,10 +262,41 @@ def gen_keys():
         json.dump(out, f, indent=0)
 
 
+def gen_pool():
+    """SimplePool (mirl/pools/simple_pool.py) as a ring buffer: adds that wrap, sampled batches
+    (global NumPy generator), get_data ordering after the wrap, resize."""
+    from mirl.pools.simple_pool import SimplePool
+    env = ref_shim.FakeEnv("cheetah")
+    pool = SimplePool(env, max_size=1000)
+    out = {}
+    np.random.seed(91)
+    for i, n in enumerate(cases.POOL_ADDS):
+        pool.add_samples(cases.pool_samples(910 + i, n))
+        b = pool.random_batch(64)
+        out["size_%d" % i] = np.array([pool.get_size(), pool._stop])
+        for k, v in b.items():
+            out["batch_%d_%s" % (i, k)] = v
+    for k, v in pool.get_data().items():                 # order-sensitive checksums (norm, random projection)
+        out["data_" + k] = proj(T(v), 7)
+    pool.resize(1500)
+    pool.add_samples(cases.pool_samples(990, 300))
+    out["size_resized"] = np.array([pool.get_size(), pool._stop])
+    for k, v in pool.get_data().items():
+        out["data_resized_" + k] = proj(T(v), 8)
+    b = pool.random_batch(32, keys=["observations", "rewards"])
+    for k, v in b.items():
+        out["batch_resized_" + k] = v
+    np.savez(os.path.join(HERE, "pool.npz"), **out)
+
+
 def main():
     ref_shim.install()
     torch.set_num_threads(1)        # bitwise-stable reductions for the fixtures
-    gen_forward(); gen_step(); gen_dist(); gen_loss(); gen_train(); gen_critics(); gen_keys()
+    only = os.environ.get("GOLDEN_ONLY")
+    if only:                        # e.g. GOLDEN_ONLY=pool regenerates one fixture
+        globals()["gen_" + only]()
+    else:
+        gen_forward(); gen_step(); gen_dist(); gen_loss(); gen_train(); gen_critics(); gen_keys(); gen_pool()
     for f in sorted(os.listdir(HERE)):
         if f.endswith((".npz", ".json")):
             print("%8d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))

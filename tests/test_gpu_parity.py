@@ -464,3 +464,60 @@ def test_full_size_properties(kernel):
     ref = o[:n] + m.delta_processor.recover(sel[:, :17])
     assert_close(no0, ref, what="zero-noise next_obs")
     assert_close(r0, sel[:, 17:], what="zero-noise reward")
+
+
+def test_device_pool_matches_reference_simple_pool():
+    """B200DevicePool against the reference SimplePool run (tests/golden/pool.npz): ring inserts that
+    wrap, sampled batches from the same NumPy stream (bit-exact: pure data movement), get_data
+    order after the wrap, resize."""
+    import mirl_b200
+    from tests.helpers_gpu import FakeEnv
+    g = golden("pool.npz")
+    pool = mirl_b200.B200DevicePool(FakeEnv("cheetah"), max_size=1000)
+    np.random.seed(91)
+    for i, n in enumerate(cases.POOL_ADDS):
+        pool.add_samples(cases.pool_samples(910 + i, n))
+        b = pool.random_batch(64)
+        assert [pool.get_size(), pool._stop] == list(g["size_%d" % i])
+        for k, v in b.items():
+            assert np.array_equal(v, g["batch_%d_%s" % (i, k)]), (i, k)
+    for k, v in pool.get_data().items():
+        assert np.allclose(proj(torch.from_numpy(v), 7), g["data_" + k], rtol=1e-12), k
+    pool.resize(1500)
+    pool.add_samples(cases.pool_samples(990, 300))
+    assert [pool.get_size(), pool._stop] == list(g["size_resized"])
+    for k, v in pool.get_data().items():
+        assert np.allclose(proj(torch.from_numpy(v), 8), g["data_resized_" + k], rtol=1e-12), k
+    bt = pool.random_batch_torch(32, keys=["observations", "rewards"])
+    assert all(v.is_cuda for v in bt.values())
+    for k, v in bt.items():
+        assert np.array_equal(v.cpu().numpy(), g["batch_resized_" + k]), k
+
+
+def test_device_pool_filled_by_the_rollout_kernel():
+    """reserve() + step_rows: the rollout kernel writes its transitions straight into the pool's
+    ring; sampling then returns rows of the fused step (same multiset as step() + add_samples)."""
+    import mirl_b200
+    from tests.helpers_gpu import FakeEnv
+    m, _ = make_pe_model(cases.MBPO, 11, "hopper")
+    m.remember_loss(LOSS_VEC7)
+    B = 1500
+    pool = mirl_b200.B200DevicePool(FakeEnv("hopper"), max_size=4000, row_stride=m.row_stride())
+    ref = mirl_b200.B200DevicePool(FakeEnv("hopper"), max_size=4000, row_stride=m.row_stride())
+    o, a = cases.rollout_inputs(333, B, env="hopper")
+    o, a = T(o, "cuda"), T(a, "cuda")
+    rs = np.random.RandomState(3)
+    for h in range(2):
+        idx = rs.choice(m.elite_indices, B)
+        eps = T(rs.standard_normal((B, 18)).astype(np.float32), "cuda")
+        no, r, d, _ = m.step(o, a, indices=idx, noise=eps)
+        ref.add_samples({"observations": o, "actions": a, "next_observations": no, "rewards": r, "terminals": d})
+        start = pool.reserve(B)
+        assert start == h * B
+        m.step_rows(o, a, pool.rows, row_offset=start, indices=idx, noise=eps, ordered=False)
+        o = no
+    assert pool.reserve(B) is None and pool.get_size() == ref.get_size() == 2 * B
+    for h in range(2):
+        got = pool.rows[h * B:(h + 1) * B, :42]
+        want = ref.rows[h * B:(h + 1) * B, :42]
+        assert np.array_equal(_sorted_rows(got), _sorted_rows(want))
