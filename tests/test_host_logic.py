@@ -170,6 +170,7 @@ def test_reference_factory_resolves_our_classes():
         "assert get_item_class('component', 'B200MBPOCollector') is mirl_b200.B200MBPOCollector\n"
         "assert get_item_class('value', 'B200EnsembleQValue') is mirl_b200.B200EnsembleQValue\n"
         "assert get_item_class('value', 'B200TQCQValue') is mirl_b200.B200TQCQValue\n"
+        "assert get_item_class('pool', 'B200DevicePool') is mirl_b200.B200DevicePool\n"
         "print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
