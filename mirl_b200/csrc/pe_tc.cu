@@ -44,7 +44,8 @@
 // penalised step.
 //
 // MB_TC_DEBUG (timing experiments, numerics wrong for 1/2/4/16): 1 one MMA per k-step, 2 no weight
-// copies, 4 no swish, 8 print a clock64 timeline of CTA 0's first tiles, 16 skip the input fence.
+// copies, 4 identity instead of swish (the arithmetic still runs), 8 print a clock64 timeline of
+// CTA 0's first tiles, 16 skip the input fence.
 //
 // mbarrier discipline: a waiter must observe EVERY phase of a barrier it waits on (parity
 // aliasing otherwise), so each consumer group has its own barrier(s): d_full (epilogue warps, all
@@ -635,7 +636,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) {
                         const int j = blk * 16 + jj;
-                        if (j >= D && !(dbg & 32)) continue;                    // uniform: pad columns cost nothing
+                        if (j >= D) continue;                                   // uniform: pad columns cost nothing
                         const bool in_d = r >= 0 && j < D, in_o = r >= 0 && j < O;
                         const float mu = __uint_as_float(acc[blk][jj]);         // bias already in the GEMM
                         const float ls = fast_clamp_logstd(__uint_as_float(acc[2 + blk][jj]), hc[j], hc[32 + j]);
