@@ -189,7 +189,11 @@ int mb_pe_loss(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs,
  * no host-side state, so it can be captured once in a CUDA graph and replayed every step).
  * Batch tensors are [E][B][.].
  * ensemble_loss[E] (entries of this slice written), loss_terms[3] += {sum_e loss_e, l2, bound}
- * over this slice (zeroed by the call). */
+ * over this slice (zeroed by the call).
+ * m->tc_pack, when non-NULL (mb_pe_tc_pack_bytes bytes), is used as SCRATCH: the call re-packs the
+ * current weights into it and runs the whole forward as one launch of the tcgen05 tile kernel
+ * (pre-activations saved for the backward pass); with NULL the forward is one GEMM launch per
+ * layer.  A rollout pack must be rebuilt after training either way (the weights changed). */
 size_t mb_pe_train_workspace_bytes(const mb_pe_model* m, int64_t B);
 int mb_pe_train_step(const mb_pe_model* m, const mb_train_cfg* cfg, float* params,
                      float* exp_avg, float* exp_avg_sq, int64_t step, int32_t* step_counter,

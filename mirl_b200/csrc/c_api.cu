@@ -294,7 +294,7 @@ static int train_common(const char* who, const mb_pe_model* m, const mb_train_cf
         set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, mb_pe_train_workspace_bytes(m, B));
         return MB_EWORKSPACE;
     }
-    return launch_pe_train(to_dev(m), *cfg, params, exp_avg, exp_avg_sq, step, step_counter, obs, act, delta, reward, done,
+    return launch_pe_train(to_dev(m), const_cast<void*>(m->tc_pack), *cfg, params, exp_avg, exp_avg_sq, step, step_counter, obs, act, delta, reward, done,
                            B, e0, e1, grads, ensemble_loss, loss_terms, workspace, (cudaStream_t)stream);
 }
 

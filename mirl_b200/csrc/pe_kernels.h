@@ -91,7 +91,11 @@ struct TcForward {
     int64_t in_member_rows;   // 0: inputs shared by all members; B: inputs are [E][B][.]
     int total[kMaxMembers];   // B for listed members, 0 otherwise
     int slot_of[kMaxMembers]; // output slot of member e
+    int raw_head;             // head row holds the RAW log-std instead of the clamped one (training)
 };
+// training forward (separate kernel instantiation): pre-activations of hidden layer l, which the
+// backward pass needs, are saved to z[l][member][B][H]
+struct TcZSave { float* z[MB_MAX_LAYERS]; };
 
 // np.random.choice(elite, B) on the device, bit-exact with NumPy's legacy MT19937 stream (member_draw.cu)
 size_t draw_workspace_bytes(int64_t B, int n);
@@ -143,11 +147,15 @@ int launch_pe_dist_finish(const PeDev& m, const int32_t* elites, int n_elite, co
 
 // ---- model training (pe_train.cu)
 size_t train_workspace_bytes(const mb_mlp_desc& d, int64_t B);
-int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, float* exp_avg,
+int launch_pe_train(const PeDev& m, void* tc_pack, const mb_train_cfg& cfg, float* params, float* exp_avg,
                     float* exp_avg_sq, int64_t step, int32_t* step_counter, const float* obs, const float* act,
                     const float* delta, const float* reward, const float* done, int64_t B,
                     int e0, int e1, float* grads_out, float* ensemble_loss, float* loss_terms,
                     void* ws, cudaStream_t s);
+// training forward of members [e0, e0+ne) in ONE launch of the tcgen05 tile kernel: re-packs the
+// (just updated) weights, saves every hidden layer's pre-activations and the raw head output
+int launch_pe_train_fwd_tc(const PeDev& m, void* pack, const float* obs, const float* act, int64_t B, int e0,
+                           int ne, float* const* zsave, float* head_raw, cudaStream_t s);
 
 // ---- critic targets (critic.cu)
 size_t critic_workspace_bytes(const mb_mlp_desc& d, int64_t B);

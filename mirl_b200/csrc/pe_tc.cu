@@ -205,13 +205,15 @@ __global__ void k_tc_pack(mb_mlp_desc d, TcShape s, const float* __restrict__ pa
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
+template <bool kZSave>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const float* __restrict__ obs,
                 int64_t obs_stride, const float* __restrict__ act, int64_t act_stride,
                 const float* __restrict__ noise,
                 const int* __restrict__ perm, const int* __restrict__ totals,
                 int64_t seg, int done_kind, float* __restrict__ next_obs,
-                float* __restrict__ reward, float* __restrict__ done, RowsOut rows, TcForward fwd, int dbg) {
+                float* __restrict__ reward, float* __restrict__ done, RowsOut rows, TcForward fwd, TcZSave zs,
+                int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -357,10 +359,22 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
             if (n_my > 1) xrow_next = load_inputs(1);
         }
         for (int i = 0; i < n_my; ++i) {
+            // training forward: where this thread's row lives in the saved pre-activations
+            int64_t zrow = -1;
+            if constexpr (kZSave) {
+                const int4 ti = tile_at(tix, kTcTM, blockIdx.x + i * gridDim.x);
+                if (row < ti.z) zrow = (int64_t)ti.x * fwd.B + ti.y + row;
+            }
             for (int l = 0; l + 1 < L; ++l) {
                 const int g = i * L + l;
                 mbar_wait_relaxed(d_full(g & 1), (g >> 1) & 1);
                 tc_fence_after();
+                float* zl = nullptr;
+                int zw = 0;
+                if constexpr (kZSave) {
+                    zw = m.mlp.sizes[l + 1];
+                    if (zrow >= 0) zl = zs.z[l] + zrow * zw;
+                }
                 if (warp == kTcEpiWarp0) TL(i, 16 + l * 2);
                 const uint32_t dcol = tmem + lane_addr + (uint32_t)((g & 1) * 256);
                 uint32_t r0[16], r1[16];
@@ -373,6 +387,19 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 auto do_block = [&](int ks, uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
                     tc_wait_ld();
                     if (ks + kTcClasses < s.nksh) tc_ld16(dcol + (ks + kTcClasses) * 16, nxt);
+                    if (kZSave && zl != nullptr) {          // 16 pre-activations of this row (bias included)
+                        if ((zw & 3) == 0) {
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4)
+                                if (ks * 16 + 4 * q4 + 4 <= zw)
+                                    *reinterpret_cast<uint4*>(zl + ks * 16 + 4 * q4) =
+                                        make_uint4(cur[4 * q4], cur[4 * q4 + 1], cur[4 * q4 + 2], cur[4 * q4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 16; ++t)
+                                if (ks * 16 + t < zw) zl[ks * 16 + t] = __uint_as_float(cur[t]);
+                        }
+                    }
                     // swish + bf16 hi/lo split on PAIRS of elements (packed fp32 arithmetic)
                     uint32_t h[8], lo[8];
                     const uint64_t kNegLog2e = pack2(-1.4426950408889634f, -1.4426950408889634f);
@@ -613,7 +640,8 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                             const int j = blk * 16 + jj;
                             if (j < D) {
                                 ro[j] = __uint_as_float(acc[blk][jj]);
-                                ro[D + j] = fast_clamp_logstd(__uint_as_float(acc[2 + blk][jj]), hc[j], hc[32 + j]);
+                                const float raw_ls = __uint_as_float(acc[2 + blk][jj]);
+                                ro[D + j] = fwd.raw_head ? raw_ls : fast_clamp_logstd(raw_ls, hc[j], hc[32 + j]);
                             }
                         }
                     }
@@ -745,7 +773,7 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, int
     const size_t smem = tc_smem_bytes(s, m.O, m.A);
     static size_t configured = 0;
     if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("k_pe_rollout_tc smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
         configured = smem;
     }
@@ -757,15 +785,55 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, int
     const char* dbg_env = getenv("MB_TC_DEBUG");        // timing experiments only (wrong numerics)
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     prof_begin(st);
-    k_pe_rollout_tc<<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, obs_stride,
-                                                    act, act_stride, noise, p.perm, p.totals, p.seg, done_kind,
-                                                    next_obs, reward, done, rows, TcForward{}, dbg);
+    k_pe_rollout_tc<false><<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, obs_stride,
+                                                           act, act_stride, noise, p.perm, p.totals, p.seg, done_kind,
+                                                           next_obs, reward, done, rows, TcForward{}, TcZSave{}, dbg);
     prof_end(st);
     MB_CUDA_LAUNCH_CHECK("k_pe_rollout_tc");
     return MB_OK;
 }
 
 bool tc_rollout_supported(const mb_mlp_desc& d) { return tc_shape(d).ok; }
+
+template <bool kZSave>
+static int launch_tc_forward(const PeDev& m, const TcShape& s, const void* pack, const float* obs, const float* act,
+                             const TcForward& fwd, const TcZSave& zs, int n_members, cudaStream_t st) {
+    const size_t smem = tc_smem_bytes(s, m.O, m.A);
+    cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc<kZSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("k_pe_rollout_tc smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms -= reserved_sms();
+    const int64_t ntiles = (int64_t)n_members * ((fwd.B + kTcTM - 1) / kTcTM);
+    const int grid = ntiles < sms ? (int)ntiles : sms;
+    k_pe_rollout_tc<kZSave><<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, m.O, act,
+                                                            m.A, nullptr, nullptr, nullptr, 0, MB_DONE_CHEETAH, nullptr,
+                                                            nullptr, nullptr, RowsOut{}, fwd, zs, 0);
+    MB_CUDA_LAUNCH_CHECK("k_pe_rollout_tc(forward)");
+    return MB_OK;
+}
+
+int launch_pe_train_fwd_tc(const PeDev& m, void* pack, const float* obs, const float* act, int64_t B, int e0,
+                           int ne, float* const* zsave, float* head_raw, cudaStream_t st) {
+    TcShape s = tc_shape(m.mlp);
+    if (!s.ok) { set_error("tcgen05 kernels do not support this model shape"); return MB_EUNSUPPORTED; }
+    int rc = launch_tc_pack(m, pack, st);
+    if (rc) return rc;
+    TcForward fwd{};
+    fwd.mode = 1;
+    fwd.out = head_raw;
+    fwd.B = B;
+    fwd.in_member_rows = B;
+    fwd.raw_head = 1;
+    for (int e = e0; e < e0 + ne; ++e) {
+        fwd.total[e] = (int)B;
+        fwd.slot_of[e] = e;
+    }
+    TcZSave zs{};
+    for (int l = 0; l + 1 < m.mlp.num_layers; ++l) zs.z[l] = zsave[l];
+    return launch_tc_forward<true>(m, s, pack, obs, act, fwd, zs, ne, st);
+}
 
 int launch_pe_forward_tc(const PeDev& m, const void* pack, const float* obs, const float* act, int per_member,
                          int64_t B, const int* members, int n_members, float* out, cudaStream_t st) {
@@ -780,20 +848,7 @@ int launch_pe_forward_tc(const PeDev& m, const void* pack, const float* obs, con
         fwd.total[members[k]] = (int)B;
         fwd.slot_of[members[k]] = k;
     }
-    const size_t smem = tc_smem_bytes(s, m.O, m.A);
-    cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("k_pe_rollout_tc smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    sms -= reserved_sms();
-    const int64_t ntiles = (int64_t)n_members * ((B + kTcTM - 1) / kTcTM);
-    const int grid = ntiles < sms ? (int)ntiles : sms;
-    k_pe_rollout_tc<<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, m.O, act, m.A,
-                                                    nullptr, nullptr, nullptr, 0, MB_DONE_CHEETAH, nullptr, nullptr,
-                                                    nullptr, RowsOut{}, fwd, 0);
-    MB_CUDA_LAUNCH_CHECK("k_pe_rollout_tc(forward)");
-    return MB_OK;
+    return launch_tc_forward<false>(m, s, pack, obs, act, fwd, TcZSave{}, n_members, st);
 }
 
 }  // namespace mb

@@ -500,7 +500,7 @@ static int set_smem(K kernel, size_t bytes) {
     return MB_OK;
 }
 
-int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, float* exp_avg,
+int launch_pe_train(const PeDev& m, void* tc_pack, const mb_train_cfg& cfg, float* params, float* exp_avg,
                     float* exp_avg_sq, int64_t step, int32_t* step_counter, const float* obs, const float* act,
                     const float* delta, const float* reward, const float* done, int64_t B,
                     int e0, int e1, float* grads_out, float* ensemble_loss, float* loss_terms,
@@ -522,7 +522,14 @@ int launch_pe_train(const PeDev& m, const mb_train_cfg& cfg, float* params, floa
                                                                        ensemble_loss, loss_terms);
             MB_CUDA_LAUNCH_CHECK("k_train_prep");
         }
-        for (int l = 0; l < L; ++l) {
+        // One launch for the whole forward when the fused tile kernel covers the shape: the
+        // rollout kernel's pipeline in forward mode, saving pre-activations and the raw head row
+        const bool fused_fwd = use_tc && tc_pack != nullptr && tc_rollout_supported(d);
+        if (fused_fwd) {
+            int rc = launch_pe_train_fwd_tc(m, tc_pack, obs, act, B, e0, ne, w.z, gnext, s);
+            if (rc) return rc;
+        }
+        for (int l = 0; l < L && !fused_fwd; ++l) {
             if (use_tc) {
                 TgBatch tb = tg_members(e0, ne);
                 tb.nops = 1;

@@ -84,6 +84,7 @@ class B200PEModelTrainer(Component):
         self._loss_terms = None
         self._ensemble_loss = None
         self._best = None
+        self._pack = None
 
     # ---- fused step ------------------------------------------------------------------------------
     def _state_to(self, dev):
@@ -93,10 +94,22 @@ class B200PEModelTrainer(Component):
             self._ensemble_loss = torch.zeros(self.model.ensemble_size, device=dev)
             self._loss_terms = torch.zeros(3, device=dev)
 
-    def _launch(self, t, B, step_counter):
-        """Enqueue the fused step on the current stream (one C-ABI call = 18 kernel launches)."""
+    def _scratch_pack(self):
+        """Scratch operand pack for the fused tcgen05 forward of the training step (re-packed from the
+        current weights inside every step); None when the tile kernel does not cover the shape."""
         model, L = self.model, _lib.lib()
-        m = model._c_model(None)
+        if not model._tc_supported():
+            return None
+        dev = model.device
+        if self._pack is None or self._pack.device != dev:
+            m = model._c_model(None)
+            self._pack = torch.empty(L.mb_pe_tc_pack_bytes(ctypes.byref(m)), dtype=torch.uint8, device=dev)
+        return self._pack
+
+    def _launch(self, t, B, step_counter):
+        """Enqueue the fused step on the current stream (one C-ABI call, ~10 kernel launches)."""
+        model, L = self.model, _lib.lib()
+        m = model._c_model(self._scratch_pack())
         cfg = model.train_cfg(self.ignore_terminal_state, self.lr, self.betas, self.eps)
         e0, e1 = self.members
         _lib.check(L.mb_pe_train_step(
