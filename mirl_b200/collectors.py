@@ -57,12 +57,41 @@ class B200MBPOCollector(Component):
                 stop = torch.zeros((o.shape[0], 1), device=o.device)
                 for j in range(depth):
                     a, _ = self.policy.action(o)
-                    next_o, r, d, info = self.model.step(o, a, **self.step_kwargs)
-                    d = stop + d - stop * d                           # stop or d
-                    o, stop = self.add_sample(stop, o, a, next_o, r, d, info, j, cur_epoch)
+                    fused = self._fused_step(o, a)
+                    if fused is not None:                             # rows already in the device pool
+                        next_o, d = fused
+                        if self.rollout_terminal_state:
+                            o, stop = next_o, d
+                        else:
+                            ind = self._get_live_ind(d)
+                            o, stop = next_o[ind], d[ind]
+                    else:
+                        next_o, r, d, info = self.model.step(o, a, **self.step_kwargs)
+                        d = stop + d - stop * d                       # stop or d
+                        o, stop = self.add_sample(stop, o, a, next_o, r, d, info, j, cur_epoch)
                     if self._all_stopped(stop):
                         break
         self._n_image_times_total += 1
+
+    def _fused_step(self, o, a):
+        """Device-resident fast path: when the imagined pool is a ``B200DevicePool`` the rollout kernel
+        writes this step's transitions straight into the pool's ring (``reserve`` + ``step_rows``),
+        replacing ``model.step`` + five ``.cpu().numpy()`` copies + ``add_samples``
+        (mbpo_collector.py:69-83).  Valid when every row of the batch is live, which the loop
+        guarantees in the default configuration (terminated rows are dropped before the next step);
+        returns ``None`` for the configurations that need the reference-shaped path."""
+        from .pools import B200DevicePool
+        pool = self.imagined_data_pool
+        if (not isinstance(pool, B200DevicePool) or self.step_kwargs or self.rollout_terminal_state
+                or (self.shard and mbdist.world()[1] > 1) or not hasattr(self.model, "step_rows")
+                or pool.row_stride != self.model.row_stride() or o.shape[0] == 0):
+            return None
+        n = o.shape[0]
+        start = pool.reserve(n)
+        if start is None:                                             # block would wrap around the ring
+            return None
+        next_o, _, d = self.model.step_rows(o.contiguous(), a.contiguous(), pool.rows, row_offset=start, ordered=True)
+        return next_o, d
 
     def _all_stopped(self, stop):
         n = torch.tensor([float(len(stop)), float(torch.sum(stop)) if len(stop) else 0.0],

@@ -521,3 +521,39 @@ def test_device_pool_filled_by_the_rollout_kernel():
         got = pool.rows[h * B:(h + 1) * B, :42]
         want = ref.rows[h * B:(h + 1) * B, :42]
         assert np.array_equal(_sorted_rows(got), _sorted_rows(want))
+
+
+def test_collector_with_device_pool_equals_reference_shaped_path():
+    """B200MBPOCollector over a B200DevicePool (rollout kernel inserts rows in place, no host copy)
+    stores exactly the transitions the reference-shaped path (model.step + add_samples of host
+    copies) stores, for hopper rollouts where trajectories terminate and are compacted away."""
+    import mirl_b200
+    from mirl_b200.collectors import B200MBPOCollector
+    from tests.helpers_gpu import FakeEnv
+
+    class Policy:
+        def action(self, o):
+            g = torch.Generator(device="cuda").manual_seed(int(o.shape[0]))
+            return torch.rand(o.shape[0], 6, device="cuda", generator=g) * 2 - 1, {}
+
+    class StartPool:
+        def random_batch_torch(self, n, keys=None):
+            o, _ = cases.rollout_inputs(444, n, env="hopper")
+            return {"observations": T(o)}
+
+    m, _ = make_pe_model(cases.MBPO, 11, "hopper")
+    m.remember_loss(LOSS_VEC7)
+    pools = []
+    for kind in ("device", "reference-shaped"):
+        im = mirl_b200.B200DevicePool(FakeEnv("hopper"), max_size=4 * 3000 * 20, row_stride=m.row_stride())
+        c = B200MBPOCollector(m, Policy(), StartPool(), im, depth_schedule=4, number_sample=3000, bathch_size=1500)
+        if kind != "device":
+            c._fused_step = lambda o, a: None
+        np.random.seed(5)
+        torch.manual_seed(5)
+        c.imagine(0)
+        pools.append(im)
+    a, b = pools
+    assert a.get_size() == b.get_size() and 3000 < a.get_size() <= 4 * 3000
+    assert torch.equal(a.rows[:a.get_size(), :42], b.rows[:b.get_size(), :42])
+    assert float(a.rows[:a.get_size(), 41].sum()) > 0          # some trajectories did terminate
