@@ -443,18 +443,17 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                         if (b % kTcClasses == c) mbar_arrive(a_ready(b / kTcRound));
                 }
                 if (warp == kTcEpiWarp0) TL(i, 17 + l * 2);
+                // The layer-0 operand in shared memory is dead as soon as layer 0's accumulator is
+                // complete (observed above): the staging class converts the NEXT tile's inputs now,
+                // a whole tile ahead of their use, and starts the loads of the tile after it.
+                if (l == 0 && c == kTcStageClass && i + 1 < n_my) {
+                    if (warp == kTcEpiWarp0 + 4 * kTcStageClass) TL(i, 33);
+                    stage_tile(xrow_next, i);
+                    if (warp == kTcEpiWarp0 + 4 * kTcStageClass) TL(i, 34);
+                    if (i + 2 < n_my) xrow_next = load_inputs(i + 2);
+                }
             }
-            // ---- last layer belongs to the head warps; class 1 stages the next tile once the
-            // accumulator is complete (the layer's MMAs no longer read the A operand), then
-            // immediately starts the loads of the tile after it
-            if (c == kTcStageClass && i + 1 < n_my) {
-                const int g = i * L + L - 1;
-                mbar_wait(d_full(g & 1), (g >> 1) & 1);        // critical path: tight poll
-                if (warp == kTcEpiWarp0 + 4 * kTcStageClass) TL(i, 33);
-                stage_tile(xrow_next, i);
-                if (warp == kTcEpiWarp0 + 4 * kTcStageClass) TL(i, 34);
-                if (i + 2 < n_my) xrow_next = load_inputs(i + 2);
-            }
+            // the last layer's accumulator belongs to the head warps
         }
     } else if (warp == kTcMmaWarp) {
         // ================================ MMA ISSUER ============================================
