@@ -377,6 +377,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 }
                 if (warp == kTcEpiWarp0) TL(i, 16 + l * 2);
                 const uint32_t dcol = tmem + lane_addr + (uint32_t)((g & 1) * 256);
+                const int one_ks = (s.H & 1) ? -1 : s.H >> 4, one_t = (s.H & 15) >> 1;   // block / word of column H
                 uint32_t r0[16], r1[16];
                 // one 16-column block: wait for its TMEM load, prefetch the next one, then
                 // swish + bf16 hi/lo split -> next layer's A operand (k-step ks).  Blocks are
@@ -425,6 +426,17 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     tc_st8(dcol + ks * 16, h);
                     tc_st8(dcol + ks * 16 + 8, lo);
                     tc_wait_st();
+                    // The bias column of the next A operand (column H) is rewritten as EXACTLY 1
+                    // instead of swish(kSwishOne * previous ones): that constant is only a bf16 hi+lo
+                    // pair in the pack (2^-17 relative) and its error grew 1.28x per layer, 6e-5 at
+                    // the head (1.7e-4 on a raw log-std with bias -3, 3e-5 with this fix).  For even H
+                    // the word holding column H is a constant -- {hi(H+1) = 0 : hi(H) = 1.0} -- because
+                    // column H+1 is padding; odd widths keep the swish-generated value.
+                    if (ks == one_ks) {
+                        tc_st1(dcol + ks * 16 + one_t, 0x00003f80u);
+                        tc_st1(dcol + ks * 16 + 8 + one_t, 0u);
+                        tc_wait_st();
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_ready(ks / kTcRound));
@@ -752,6 +764,19 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 }
 
 // ---- host launchers -----------------------------------------------------------------------------
+// The opt-in dynamic shared-memory limit of an instantiation only ever grows: different model shapes
+// share the kernel, and lowering the attribute would make a later launch of a larger shape fail.
+template <bool kZSave>
+static int tc_ensure_smem(size_t smem) {
+    static size_t configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc<kZSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("k_pe_rollout_tc smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
+        configured = smem;
+    }
+    return MB_OK;
+}
+
 int launch_tc_pack(const PeDev& m, void* pack, cudaStream_t st) {
     TcShape s = tc_shape(m.mlp);
     if (!s.ok) { set_error("tcgen05 rollout kernel does not support this model shape"); return MB_EUNSUPPORTED; }
@@ -770,12 +795,7 @@ int launch_pe_rollout_tc(const PeDev& m, const void* pack, const float* obs, int
     BucketPlan p = bucket_rows(idx, B, m.mlp.ensemble_size, kTcTM, ws, st);
     MB_CUDA_LAUNCH_CHECK("bucket_rows");
     const size_t smem = tc_smem_bytes(s, m.O, m.A);
-    static size_t configured = 0;
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("k_pe_rollout_tc smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
-        configured = smem;
-    }
+    if (int rc = tc_ensure_smem<false>(smem)) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -798,8 +818,7 @@ template <bool kZSave>
 static int launch_tc_forward(const PeDev& m, const TcShape& s, const void* pack, const float* obs, const float* act,
                              const TcForward& fwd, const TcZSave& zs, int n_members, cudaStream_t st) {
     const size_t smem = tc_smem_bytes(s, m.O, m.A);
-    cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc<kZSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("k_pe_rollout_tc smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
+    if (int rc = tc_ensure_smem<kZSave>(smem)) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

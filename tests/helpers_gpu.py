@@ -19,10 +19,10 @@ class FakeEnv:
         self.action_space = FakeEnv._Space(act_dim)
 
 
-def make_pe_model(cfg, seed, env="cheetah", device="cuda", kernel=None):
+def make_pe_model(cfg, seed, env="cheetah", device="cuda", kernel=None, obs=cases.OBS, act=cases.ACT):
     import mirl_b200
-    p = cases.pe_params(seed, cfg)
-    m = mirl_b200.B200PEModel(FakeEnv(env), known=["done"], ensemble_size=cfg["E"],
+    p = cases.pe_params(seed, cfg, obs=obs, act=act)
+    m = mirl_b200.B200PEModel(FakeEnv(env, obs, act), known=["done"], ensemble_size=cfg["E"],
                               elite_number=cfg["elites"], hidden_layers=list(cfg["hidden"]),
                               activation=cfg["act"], connection="simple", reward_coef=1,
                               bound_reg_coef=2e-2,
