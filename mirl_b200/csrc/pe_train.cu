@@ -440,23 +440,23 @@ k_train_gemm(GemmBatch gb) {
 // ---- Adam (torch.optim.Adam defaults, no weight decay / amsgrad) ----------------------------
 struct AdamSegs { int n; int64_t off[2 * MB_MAX_LAYERS + 2]; int64_t len[2 * MB_MAX_LAYERS + 2]; };
 
-__global__ void k_step_inc(int32_t* step_counter) { *step_counter += 1; }
+// Advances the device-resident step count and derives Adam's two bias-correction scalars from it
+// ONCE (double-precision pow is slow on this part; every k_adam block used to redo it).
+__global__ void k_step_inc(int32_t* step_counter, float* scal, float lr, float beta1, float beta2) {
+    *step_counter += 1;
+    const double t = (double)*step_counter;
+    scal[0] = (float)((double)lr / (1.0 - pow((double)beta1, t)));
+    scal[1] = (float)sqrt(1.0 - pow((double)beta2, t));
+}
 
-// step_dev != nullptr: bias corrections come from the device-resident step counter (graph replay)
+// scal != nullptr: bias corrections come from the device-resident step counter (graph replay)
 __global__ void k_adam(AdamSegs segs, float* __restrict__ p, float* __restrict__ m1,
                        float* __restrict__ m2, const float* __restrict__ g, float beta1,
                        float beta2, float eps, float step_size, float bc2_sqrt,
-                       const int32_t* __restrict__ step_dev, float lr) {
-    __shared__ float sh[2];
-    if (step_dev != nullptr) {
-        if (threadIdx.x == 0) {
-            const double t = (double)*step_dev;
-            sh[0] = (float)((double)lr / (1.0 - pow((double)beta1, t)));
-            sh[1] = (float)sqrt(1.0 - pow((double)beta2, t));
-        }
-        __syncthreads();
-        step_size = sh[0];
-        bc2_sqrt = sh[1];
+                       const float* __restrict__ scal) {
+    if (scal != nullptr) {                   // graph replay: scalars written by k_step_inc
+        step_size = scal[0];
+        bc2_sqrt = scal[1];
     }
     const int s = blockIdx.y;
     const int64_t off = segs.off[s], len = segs.len[s];
@@ -674,12 +674,14 @@ int launch_pe_train(const PeDev& m, void* tc_pack, const mb_train_cfg& cfg, floa
         const double bc2 = 1.0 - pow((double)cfg.beta2, hstep);
         const int64_t nb = (maxlen + 255) / 256;
         dim3 ga((unsigned)(nb < 1184 ? nb : 1184), (unsigned)segs.n);
+        float* scal = nullptr;
         if (step_counter) {
-            k_step_inc<<<1, 1, 0, s>>>(step_counter);
+            scal = w.grads + round_up4(param_count(d, true));          // inside the workspace's tail slack
+            k_step_inc<<<1, 1, 0, s>>>(step_counter, scal, cfg.lr, cfg.beta1, cfg.beta2);
             MB_CUDA_LAUNCH_CHECK("k_step_inc");
         }
         k_adam<<<ga, 256, 0, s>>>(segs, params, exp_avg, exp_avg_sq, grads, cfg.beta1, cfg.beta2, cfg.eps,
-                                  (float)(cfg.lr / bc1), (float)sqrt(bc2), step_counter, cfg.lr);
+                                  (float)(cfg.lr / bc1), (float)sqrt(bc2), scal);
         MB_CUDA_LAUNCH_CHECK("k_adam");
     }
     (void)E;
