@@ -240,6 +240,8 @@ def main():
     from mirl_b200 import _lib
     L = _lib.lib()
     model, _ = build_model(dev)
+    model.speculative_draw = os.environ.get("MB_SPEC_DRAW", "1") == "1"          # A/B switches of the e2e leg
+    model.draw_overlap_sms = int(os.environ.get("MB_DRAW_SMS", "1"))
     kernel = model._resolve_kernel()
     B, H, O, A, D = ROWS, HORIZON, 17, 6, 18
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -299,36 +301,56 @@ def main():
     np.random.seed(4321 + rank)
     torch.manual_seed(4321 + rank)
 
-    # Public-API loop a user writes: actions arrive from pinned host memory every horizon step, the
-    # model draws members (NumPy stream) and noise (torch) itself like PEModel.step, and every
-    # step's [next_obs | reward | done] goes back to pinned host memory.  The D2H of step h runs on
-    # a copy stream under the H2D + rollout of step h+1 (two row buffers).
+    # Public-API loop a user writes: start states and actions live in pinned HOST memory, the model
+    # draws members (NumPy stream) and noise (torch) itself like PEModel.step, and every step's
+    # [next_obs | reward | done] goes back to pinned host memory.  PCIe is full duplex, so the
+    # batch is rolled in row chunks: the H2D copies run ahead on one copy stream in the order the
+    # rollouts consume them, the D2H of every (chunk, step) runs on another under the next rollout
+    # (two row buffers), and the link carries both directions at once.
     W = 2 * O + A + 2
-    e2e_rows = torch.empty(2, B, W, device=dev)
-    copy_stream = torch.cuda.Stream(dev)
+    n_chunks = max(1, int(os.environ.get("MB_E2E_CHUNKS", "2")))
+    bounds = [B * c // n_chunks for c in range(n_chunks + 1)]
+    Bc = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
+    e2e_rows = torch.empty(2, Bc, W, device=dev)
+    d_obs0 = torch.empty(B, O, device=dev)
+    d_acts = torch.empty(H, B, A, device=dev)
+    in_stream, copy_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+    in_ready = [[torch.cuda.Event() for _ in range(H)] for _ in range(n_chunks)]
 
     def e2e_step():
         main = torch.cuda.current_stream()
-        o = h_obs0.to(dev, non_blocking=True)
-        for h in range(H):
-            a = h_acts[h].to(dev, non_blocking=True)
-            buf = e2e_rows[h & 1]
-            main.wait_event(copy_done[h & 1])      # its previous contents have left for the host
-            o, _, _ = model.step_rows(o, a, buf)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev)
-                h_out[h].copy_(buf[:, O + A:], non_blocking=True)
-                copy_done[h & 1].record(copy_stream)
+        in_stream.wait_stream(main)                # the device inputs of the previous call are free
+        with torch.cuda.stream(in_stream):
+            for c in range(n_chunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                d_obs0[lo:hi].copy_(h_obs0[lo:hi], non_blocking=True)
+                for h in range(H):
+                    d_acts[h, lo:hi].copy_(h_acts[h, lo:hi], non_blocking=True)
+                    in_ready[c][h].record(in_stream)
+        k = 0
+        for c in range(n_chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            o = d_obs0[lo:hi]
+            for h in range(H):
+                buf = e2e_rows[k & 1, :hi - lo]
+                main.wait_event(in_ready[c][h])
+                main.wait_event(copy_done[k & 1])  # its previous contents have left for the host
+                o, _, _ = model.step_rows(o, d_acts[h, lo:hi], buf)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev)
+                    h_out[h, lo:hi].copy_(buf[:, O + A:], non_blocking=True)
+                    copy_done[k & 1].record(copy_stream)
+                k += 1
         copy_stream.synchronize()                  # the caller owns the transitions now
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_ms = timed(e2e_step, e2e_steps, 3) / e2e_steps
     e2e = {"value": world * B * H / (e2e_ms * 1e-3), "unit": "transitions/s",
-           "h2d_bytes_per_step": B * O * 4 + H * (B * A * 4 + 627 * 4),
-           "d2h_bytes_per_step": H * B * (O + 2) * 4, "ms_per_step": e2e_ms}
+           "h2d_bytes_per_step": B * O * 4 + H * (B * A * 4 + n_chunks * 627 * 4),
+           "d2h_bytes_per_step": H * B * (O + 2) * 4, "ms_per_step": e2e_ms, "row_chunks": n_chunks}
 
     # ---- roofline of the dominant kernel (events inside the C ABI around that kernel only) -------
     roof = None

@@ -93,8 +93,9 @@ int mb_pe_rollout_step(const mb_pe_model* m, int kernel, const float* obs, const
 
 /* Random-elite selection of PEModel.step, `np.random.choice(elite, B)` (pe_model.py:165-169), on
  * the device and bit-exact with NumPy's legacy global RandomState: the MT19937 stream with
- * randint's masked rejection.  mt_state is device uint32[627]: [0,624) key and [624] pos as
- * returned by np.random.get_state(); both are advanced in place to where NumPy would be after the
+ * randint's masked rejection.  mt_state is device-accessible uint32[627] -- device memory, or
+ * pinned host memory, which keeps the state off the copy engines (no queueing behind the caller's
+ * bulk transfers): [0,624) key and [624] pos as returned by np.random.get_state(); both are advanced in place to where NumPy would be after the
  * draws (write them back with np.random.set_state to keep host code reproducible), and
  * [625],[626] receive the low/high word of the number of members produced.  That number is B
  * unless the word budget of the workspace (expected attempts + 12 sigma) ran out -- then the
@@ -262,9 +263,10 @@ int mb_peer_pool_open(const unsigned char* handle, void** dev_ptr);
 int mb_peer_pool_close(void* dev_ptr);
 int mb_peer_pool_free(void* dev_ptr);
 
-/* Persistent kernels launch one CTA per SM.  When a collective has to overlap with them (rollout
- * sharded over GPUs: NCCL all-gather of the generated transitions), leave `n` SMs free for the
- * communication kernels.  0 (default) = use every SM. */
+/* Persistent kernels launch one CTA per SM.  When other kernels have to run under them -- the
+ * single-CTA MT19937 generator of the next call's member draw (mb_pe_draw_members on a second
+ * stream), or the communication kernels of a collective -- leave `n` SMs free for them.
+ * 0 (default) = use every SM. */
 int mb_set_reserved_sms(int n);
 
 /* ---- instrumentation for bench.py's roofline leg (not used on the product path) ---------------

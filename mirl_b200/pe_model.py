@@ -147,6 +147,12 @@ class B200PEModel(Component, nn.Module):
         self._ws = None
         self._draw_ws = None
         self._draw_stream = None
+        self._draw_state = None
+        self._draw_spec = None
+        self._draw_last_shape = None
+        self.speculative_draw = True
+        self._drew_on_device = False
+        self.draw_overlap_sms = 1
 
     # ---- reference bookkeeping ---------------------------------------------------------------
     def remember_loss(self, loss):
@@ -231,8 +237,10 @@ class B200PEModel(Component, nn.Module):
         elite = self.elite_indices
         if elite is None:
             elite = list(np.arange(self.ensemble_size))               # pe_model.py:167-168
+        self._drew_on_device = False
         if indices is None:
             if B >= self.device_draw_min_rows and len(elite) <= 64:
+                self._drew_on_device = True
                 return self.draw_members(B)
             indices = np.random.choice(elite, B)                      # pe_model.py:169
         if torch.is_tensor(indices):
@@ -240,50 +248,94 @@ class B200PEModel(Component, nn.Module):
         idx8 = np.ascontiguousarray(np.asarray(indices).astype(np.uint8))
         return torch.from_numpy(idx8).to(self.device, non_blocking=True)
 
+    def _reserve_for_draw(self, L):
+        """The rollout kernel is persistent (one CTA per SM) and the generator of the member draw
+        is one CTA on a side stream: when this model draws the members itself, the rollout leaves
+        ``draw_overlap_sms`` SMs free so that the NEXT call's draw runs under this call's rollout
+        instead of behind it (measured: rollout + draw 1.57 -> 1.05 ms per 1e6 rows)."""
+        L.mb_set_reserved_sms(self.draw_overlap_sms if self._drew_on_device else 0)
+
+    def _draw_launch(self, blk, key, pos, el, n, out):
+        """Queue one member draw on the draw stream.  The generator state travels through a PINNED
+        host block the kernels read and write in place (mapped memory, same pointer on both
+        sides): no copy-engine transfer, so neither direction queues behind bulk H2D / D2H copies
+        the caller has in flight."""
+        L = _lib.lib()
+        side = self._draw_stream
+        host = blk.numpy().view(np.uint32)
+        host[:624], host[624] = key, pos
+        host[625:] = 0
+        nbytes = L.mb_pe_draw_members_workspace_bytes(n, len(el))
+        with torch.cuda.stream(side):
+            if self._draw_ws is None or self._draw_ws.numel() < nbytes or self._draw_ws.device != out.device:
+                self._draw_ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=out.device)
+            _lib.check(L.mb_pe_draw_members(ctypes.c_void_p(blk.data_ptr()), el, len(el), n, _lib.ptr(out),
+                                            _lib.ptr(self._draw_ws), self._draw_ws.numel(),
+                                            ctypes.c_void_p(side.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return ev
+
     def draw_members(self, B):
         """``np.random.choice(elite, B)`` (pe_model.py:165-169) generated on the device from
         NumPy's own global MT19937 state: the returned uint8 indices are bit-identical to the
         host call and ``np.random`` is left in the state that call would leave it in.  Costs one
-        small D2H read of the 625-word state (a stream sync) instead of a 10-25 ms host loop per
-        million rows."""
+        read of the 627-word state block (an event wait) instead of a 10-25 ms host loop per
+        million rows.
+
+        The draw runs on its own stream.  When two consecutive calls asked for the same (B,
+        elites), the NEXT draw is queued speculatively from the state this one leaves; a later
+        call uses it only if ``np.random`` is still exactly in that state (nobody else drew) and
+        asks for the same shape, so the result is the one a fresh draw would give -- but it was
+        generated under the previous rollout, off the host's critical path."""
         elite = self.elite_indices
         if elite is None:
             elite = list(np.arange(self.ensemble_size))
         dev = self.device
-        L = _lib.lib()
         st = np.random.get_state()
         assert st[0] == "MT19937"
         key, pos = st[1], int(st[2])
         el = bytes(int(e) for e in elite)
-        # The draw depends on host state only, so it runs on its own stream: the state read-back
-        # below then waits for the draw kernels alone, not for rollout work queued earlier.
         main = torch.cuda.current_stream(dev)
         if self._draw_stream is None:
             self._draw_stream = torch.cuda.Stream(dev)
+            self._draw_state = [torch.zeros(627, dtype=torch.int32).pin_memory() for _ in range(2)]
         side = self._draw_stream
-        with torch.cuda.stream(side):
-            out = torch.empty(B, dtype=torch.uint8, device=dev)
-            done = 0
-            while done < B:  # one pass unless the word budget (mean + 12 sigma attempts) ran out
-                host = np.zeros(627, dtype=np.uint32)
-                host[:624], host[624] = key, pos
-                state = torch.from_numpy(host.view(np.int32)).to(dev)
-                n = B - done
-                nbytes = L.mb_pe_draw_members_workspace_bytes(n, len(el))
-                if self._draw_ws is None or self._draw_ws.numel() < nbytes or self._draw_ws.device != dev:
-                    self._draw_ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
-                _lib.check(L.mb_pe_draw_members(_lib.ptr(state), el, len(el), n, _lib.ptr(out[done:]),
-                                                _lib.ptr(self._draw_ws), self._draw_ws.numel(),
-                                                ctypes.c_void_p(side.cuda_stream)))
-                back = state.cpu().numpy().view(np.uint32)
+        shape = (B, el, str(dev))
+        spec, self._draw_spec = self._draw_spec, None
+        out, done, blk = None, 0, self._draw_state[0]
+        if spec is not None:
+            spec["event"].synchronize()            # nothing may still write its state block
+            if spec["shape"] == shape and spec["pos"] == pos and np.array_equal(spec["key"], key):
+                out, blk = spec["out"], spec["blk"]
+                ev = spec["event"]
+                host = blk.numpy().view(np.uint32)
                 if len(el) > 1:
-                    key, pos = back[:624].copy(), int(back[624])
-                produced = int(back[625]) | (int(back[626]) << 32)
-                assert 0 < produced <= n
-                done += produced
-        main.wait_stream(side)
+                    key, pos = host[:624].copy(), int(host[624])
+                done = int(host[625]) | (int(host[626]) << 32)
+                assert 0 < done <= B
+        if out is None:
+            with torch.cuda.stream(side):
+                out = torch.empty(B, dtype=torch.uint8, device=dev)
+        while done < B:      # one pass unless the word budget (mean + 12 sigma attempts) ran out
+            ev = self._draw_launch(blk, key, pos, el, B - done, out[done:])
+            ev.synchronize()
+            host = blk.numpy().view(np.uint32)
+            if len(el) > 1:
+                key, pos = host[:624].copy(), int(host[624])
+            produced = int(host[625]) | (int(host[626]) << 32)
+            assert 0 < produced <= B - done
+            done += produced
+        main.wait_event(ev)
         out.record_stream(main)
         np.random.set_state((st[0], key, pos, st[3], st[4]))
+        if self.speculative_draw and shape == self._draw_last_shape and len(el) > 1:
+            other = self._draw_state[1] if blk is self._draw_state[0] else self._draw_state[0]
+            with torch.cuda.stream(side):
+                nxt = torch.empty(B, dtype=torch.uint8, device=dev)
+            self._draw_spec = {"shape": shape, "key": np.array(key, copy=True), "pos": pos, "out": nxt, "blk": other,
+                               "event": self._draw_launch(other, key, pos, el, B, nxt)}
+        self._draw_last_shape = shape
         return out
 
     # ---- rollout -------------------------------------------------------------------------------
@@ -316,10 +368,12 @@ class B200PEModel(Component, nn.Module):
             pack = self._tc_pack() if kname == "tcgen05" else None
             m = self._c_model(pack)
             ws = self._workspace(L.mb_pe_rollout_workspace_bytes(ctypes.byref(m), B))
+            self._reserve_for_draw(L)
             _lib.check(L.mb_pe_rollout_step(
                 ctypes.byref(m), _lib.KERNEL[kname], _lib.ptr(obs), _lib.ptr(action), _lib.ptr(idx),
                 _lib.ptr(noise), B, kind, _lib.ptr(next_obs), _lib.ptr(reward), _lib.ptr(done),
                 _lib.ptr(ws), ws.numel(), _lib.stream()))
+            L.mb_set_reserved_sms(0)
             return next_obs, reward, done, info
         elites = self.elite_indices
         if elites is None:
@@ -419,11 +473,13 @@ class B200PEModel(Component, nn.Module):
             m = self._c_model(pack)
             ws = self._workspace(L.mb_pe_rollout_workspace_bytes(ctypes.byref(m), B))
             arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+            self._reserve_for_draw(L)
             _lib.check(L.mb_pe_rollout_step_rows(
                 ctypes.byref(m), _lib.KERNEL[kname], obs.data_ptr(), obs.stride(0), action.data_ptr(),
                 action.stride(0), _lib.ptr(idx), _lib.ptr(noise), B, _lib.DONE_KIND[self.done_kind],
                 arr, len(ptrs), int(stride), int(row_offset), int(bool(ordered)), _lib.ptr(ws), ws.numel(),
                 _lib.stream()))
+            L.mb_set_reserved_sms(0)
         rows = dests[0][row_offset:row_offset + B]
         return rows[:, O + A:2 * O + A], rows[:, 2 * O + A:2 * O + A + 1], rows[:, 2 * O + A + 1:W]
 

@@ -400,6 +400,40 @@ def test_device_member_draw_is_numpy_choice_bit_exact(seed, elites, B):
     assert np.array_equal(want_next[0], got_next[0]) and np.array_equal(want_next[1], got_next[1])
 
 
+def test_speculative_member_draws_follow_the_numpy_stream():
+    """Repeated draws of one shape are generated one call ahead (pe_model.draw_members); every
+    call must still return what np.random.choice returns at that point of the GLOBAL stream,
+    also when other host code draws in between (the queued draw is then dropped), when the batch
+    size changes, and when the stream is re-seeded."""
+    m, _ = make_pe_model(cases.SMALL, 11)
+    elites = [3, 1, 5, 0, 6]
+    m.elite_indices = list(elites)
+    plan = [40000, 40000, 40000, 40000, "host", 40000, 40000, 12345, 40000, 40000, "seed", 40000, 40000, 40000]
+    np.random.seed(31)
+    want = []
+    for p in plan:
+        if p == "host":
+            want.append(np.random.standard_normal(3))
+        elif p == "seed":
+            np.random.seed(77)
+        else:
+            want.append(np.random.choice(elites, p).astype(np.uint8))
+    want_tail = np.random.randint(0, 1 << 30, 4)
+    np.random.seed(31)
+    got, hits = [], 0
+    for p in plan:
+        if p == "host":
+            got.append(np.random.standard_normal(3))
+        elif p == "seed":
+            np.random.seed(77)
+        else:
+            hits += m._draw_spec is not None
+            got.append(m.draw_members(p).cpu().numpy())
+    assert hits >= 5                                  # the look-ahead actually ran
+    assert all(np.array_equal(w, g) for w, g in zip(want, got))
+    assert np.array_equal(want_tail, np.random.randint(0, 1 << 30, 4))
+
+
 def test_step_draws_members_on_device_for_large_batches():
     m, _ = make_pe_model(cases.MBPO, 11)
     m.remember_loss(LOSS_VEC7)
