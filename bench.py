@@ -240,7 +240,7 @@ def main():
     from mirl_b200 import _lib
     L = _lib.lib()
     model, _ = build_model(dev)
-    model.speculative_draw = os.environ.get("MB_SPEC_DRAW", "1") == "1"          # A/B switches of the e2e leg
+    model.draw_lookahead = int(os.environ.get("MB_DRAW_AHEAD", "2"))               # A/B switches of the e2e leg
     model.draw_overlap_sms = int(os.environ.get("MB_DRAW_SMS", "1"))
     kernel = model._resolve_kernel()
     B, H, O, A, D = ROWS, HORIZON, 17, 6, 18

@@ -106,6 +106,14 @@ size_t mb_pe_draw_members_workspace_bytes(int64_t B, int n_elites);
 int mb_pe_draw_members(uint32_t* mt_state, const uint8_t* elites_host, int n_elites, int64_t B,
                        uint8_t* member_idx, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same draw for a CHAIN of calls queued ahead of the host: mt_state is advanced in place (so
+ * the next queued call continues the stream without a host round trip) and state_snapshot
+ * (device-accessible uint32[627], may be NULL) additionally receives this call's final block, which
+ * the host reads when it consumes this draw.  B == 0 writes nothing. */
+int mb_pe_draw_members_chained(uint32_t* mt_state, uint32_t* state_snapshot, const uint8_t* elites_host,
+                               int n_elites, int64_t B, uint8_t* member_idx, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* The same step fused with the collector's pool-row assembly (MBPOCollector.add_sample,
  * mbpo_collector.py:69-83): every transition is written as one row
  * [obs | act | next_obs | reward | done | zero padding] of row_stride floats

@@ -53,6 +53,7 @@ SIGNATURES = {
                                    P, c_size_t, P]),
     "mb_pe_draw_members_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "mb_pe_draw_members": (c_int, [P, ctypes.c_char_p, c_int, c_int64, P, P, c_size_t, P]),
+    "mb_pe_draw_members_chained": (c_int, [P, P, ctypes.c_char_p, c_int, c_int64, P, P, c_size_t, P]),
     "mb_pe_rollout_step_rows": (c_int, [POINTER(PeModel), c_int, P, c_int64, P, c_int64, P, P, c_int64, c_int,
                                         POINTER(c_void_p), c_int, c_int64, c_int64, c_int, P, c_size_t, P]),
     "mb_pe_dist_workspace_bytes": (c_size_t, [POINTER(PeModel), c_int64, c_int]),

@@ -397,8 +397,9 @@ size_t mb_pe_draw_members_workspace_bytes(int64_t B, int n_elites) {
     return draw_workspace_bytes(B, n_elites);
 }
 
-int mb_pe_draw_members(uint32_t* mt_state, const uint8_t* elites_host, int n_elites, int64_t B,
-                       uint8_t* member_idx, void* workspace, size_t workspace_bytes, void* stream) {
+int mb_pe_draw_members_chained(uint32_t* mt_state, uint32_t* state_snapshot, const uint8_t* elites_host,
+                               int n_elites, int64_t B, uint8_t* member_idx, void* workspace,
+                               size_t workspace_bytes, void* stream) {
     MB_CHECK_ARG(mt_state && elites_host && n_elites >= 1 && n_elites <= 64,
                  "mb_pe_draw_members: need 1..64 elites and a state buffer (got %d)", n_elites);
     MB_CHECK_ARG(B >= 0 && B <= (int64_t)1 << 28, "mb_pe_draw_members: B %lld out of range", (long long)B);
@@ -408,7 +409,14 @@ int mb_pe_draw_members(uint32_t* mt_state, const uint8_t* elites_host, int n_eli
         set_error("mb_pe_draw_members: workspace %zu < %zu bytes", workspace_bytes, draw_workspace_bytes(B, n_elites));
         return MB_EWORKSPACE;
     }
-    return launch_draw_members(mt_state, elites_host, n_elites, B, member_idx, workspace, (cudaStream_t)stream);
+    return launch_draw_members(mt_state, state_snapshot, elites_host, n_elites, B, member_idx, workspace,
+                               (cudaStream_t)stream);
+}
+
+int mb_pe_draw_members(uint32_t* mt_state, const uint8_t* elites_host, int n_elites, int64_t B,
+                       uint8_t* member_idx, void* workspace, size_t workspace_bytes, void* stream) {
+    return mb_pe_draw_members_chained(mt_state, nullptr, elites_host, n_elites, B, member_idx, workspace,
+                                      workspace_bytes, stream);
 }
 
 // ---- peer-mapped pools (CUDA IPC): destinations of mb_pe_rollout_step_rows on other GPUs ---------

@@ -238,33 +238,44 @@ k_draw_scatter(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ st
 // state <- the block holding the B-th accepted word, pos just behind it; state[625..626] = number
 // of members produced (== B unless the word budget ran out: then the state is the end of the budget)
 __global__ void __launch_bounds__(256)
-k_draw_finish(uint32_t* __restrict__ state, const uint32_t* __restrict__ raw, int64_t nblocks,
-              const long long* __restrict__ offs, int64_t nchunks, const long long* __restrict__ jstar, int64_t B) {
+k_draw_finish(uint32_t* __restrict__ state, uint32_t* __restrict__ snap, const uint32_t* __restrict__ raw,
+              int64_t nblocks, const long long* __restrict__ offs, int64_t nchunks,
+              const long long* __restrict__ jstar, int64_t B) {
     const long long j = *jstar;
     const int64_t blk = j >= 0 ? j / kMtN : nblocks - 1;
     const uint32_t pos = j >= 0 ? (uint32_t)(j % kMtN) + 1u : (uint32_t)kMtN;
     const long long produced = j >= 0 ? (long long)B : offs[nchunks];
     __syncthreads();
-    for (int i = threadIdx.x; i < kMtN; i += 256) state[i] = raw[blk * kMtN + i];
+    for (int i = threadIdx.x; i < kMtN; i += 256) {
+        const uint32_t w = raw[blk * kMtN + i];
+        state[i] = w;
+        if (snap) snap[i] = w;
+    }
     if (threadIdx.x == 0) {
-        state[kMtN] = pos;
-        state[kMtN + 1] = (uint32_t)(produced & 0xffffffffll);
-        state[kMtN + 2] = (uint32_t)(produced >> 32);
+        const uint32_t lo = (uint32_t)(produced & 0xffffffffll), hi = (uint32_t)(produced >> 32);
+        state[kMtN] = pos; state[kMtN + 1] = lo; state[kMtN + 2] = hi;
+        if (snap) { snap[kMtN] = pos; snap[kMtN + 1] = lo; snap[kMtN + 2] = hi; }
     }
 }
 
-__global__ void k_draw_single(uint8_t v, int64_t B, uint8_t* __restrict__ out, uint32_t* __restrict__ state) {
+__global__ void k_draw_single(uint8_t v, int64_t B, uint8_t* __restrict__ out, uint32_t* __restrict__ state,
+                              uint32_t* __restrict__ snap) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        state[kMtN + 1] = (uint32_t)(B & 0xffffffffll);
-        state[kMtN + 2] = (uint32_t)(B >> 32);
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            state[kMtN + 1] = (uint32_t)(B & 0xffffffffll);
+            state[kMtN + 2] = (uint32_t)(B >> 32);
+        }
+        __syncthreads();
+        if (snap)
+            for (int i = threadIdx.x; i < kMtN + 3; i += blockDim.x) snap[i] = state[i];
     }
 }
 
-int launch_draw_members(uint32_t* state, const uint8_t* elites, int n, int64_t B, uint8_t* out, void* ws,
-                        cudaStream_t s) {
+int launch_draw_members(uint32_t* state, uint32_t* snap, const uint8_t* elites, int n, int64_t B, uint8_t* out,
+                        void* ws, cudaStream_t s) {
     if (n == 1) {                            // one elite: NumPy consumes no random words
-        k_draw_single<<<148, 256, 0, s>>>(elites[0], B, out, state);
+        k_draw_single<<<148, 256, 0, s>>>(elites[0], B, out, state, snap);
         MB_CUDA_LAUNCH_CHECK("k_draw_single");
         return MB_OK;
     }
@@ -282,7 +293,7 @@ int launch_draw_members(uint32_t* state, const uint8_t* elites, int n, int64_t B
     MB_CUDA_LAUNCH_CHECK("k_draw_scan");
     k_draw_scatter<<<(unsigned)p.nchunks, 256, 0, s>>>(p.raw, state, p.nwords, mask, rng, tab, p.offs, B, out, p.jstar);
     MB_CUDA_LAUNCH_CHECK("k_draw_scatter");
-    k_draw_finish<<<1, 256, 0, s>>>(state, p.raw, p.nblocks, p.offs, p.nchunks, p.jstar, B);
+    k_draw_finish<<<1, 256, 0, s>>>(state, snap, p.raw, p.nblocks, p.offs, p.nchunks, p.jstar, B);
     MB_CUDA_LAUNCH_CHECK("k_draw_finish");
     return MB_OK;
 }

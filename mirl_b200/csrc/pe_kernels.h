@@ -99,8 +99,8 @@ struct TcZSave { float* z[MB_MAX_LAYERS]; };
 
 // np.random.choice(elite, B) on the device, bit-exact with NumPy's legacy MT19937 stream (member_draw.cu)
 size_t draw_workspace_bytes(int64_t B, int n);
-int launch_draw_members(uint32_t* state, const uint8_t* elites, int n, int64_t B, uint8_t* out, void* ws,
-                        cudaStream_t s);
+int launch_draw_members(uint32_t* state, uint32_t* snap, const uint8_t* elites, int n, int64_t B, uint8_t* out,
+                        void* ws, cudaStream_t s);
 
 size_t bucket_workspace_bytes(int64_t B, int E);
 BucketPlan bucket_rows(const uint8_t* idx, int64_t B, int E, int TM, void* ws, cudaStream_t s);

@@ -9,6 +9,7 @@ omitted they are drawn exactly like the reference draws them (``np.random.choice
 global NumPy generator, pe_model.py:169, then ``torch.randn`` from the global torch generator of
 the tensor's device, pe_model.py:176), in the same order.
 """
+import collections
 import ctypes
 import os
 
@@ -148,9 +149,11 @@ class B200PEModel(Component, nn.Module):
         self._draw_ws = None
         self._draw_stream = None
         self._draw_state = None
-        self._draw_spec = None
+        self._draw_queue = collections.deque()
+        self._draw_snaps = []
+        self._draw_np_state = None
         self._draw_last_shape = None
-        self.speculative_draw = True
+        self.draw_lookahead = 2
         self._drew_on_device = False
         self.draw_overlap_sms = 1
 
@@ -255,39 +258,56 @@ class B200PEModel(Component, nn.Module):
         instead of behind it (measured: rollout + draw 1.57 -> 1.05 ms per 1e6 rows)."""
         L.mb_set_reserved_sms(self.draw_overlap_sms if self._drew_on_device else 0)
 
-    def _draw_launch(self, blk, key, pos, el, n, out):
-        """Queue one member draw on the draw stream.  The generator state travels through a PINNED
-        host block the kernels read and write in place (mapped memory, same pointer on both
-        sides): no copy-engine transfer, so neither direction queues behind bulk H2D / D2H copies
-        the caller has in flight."""
+    def _draw_launch(self, start, el, n, out):
+        """Queue one member draw on the draw stream.  The generator state lives in a PINNED host
+        block the kernels read and advance in place (mapped memory, same pointer on both sides):
+        no copy-engine transfer, so neither direction queues behind bulk H2D / D2H copies the
+        caller has in flight, and a draw queued behind another continues the stream with no host
+        round trip.  ``start`` = (key, pos) re-seeds the block from the host first (the draw
+        stream must be idle then); None chains on whatever the previous draw left.  Returns
+        (event, snapshot): the snapshot block receives this draw's final state."""
         L = _lib.lib()
         side = self._draw_stream
-        host = blk.numpy().view(np.uint32)
-        host[:624], host[624] = key, pos
-        host[625:] = 0
+        if start is not None:
+            host = self._draw_state.numpy().view(np.uint32)
+            host[:624], host[624] = start
+            host[625:] = 0
+        snap = self._draw_snaps.pop() if self._draw_snaps else torch.zeros(627, dtype=torch.int32).pin_memory()
         nbytes = L.mb_pe_draw_members_workspace_bytes(n, len(el))
         with torch.cuda.stream(side):
             if self._draw_ws is None or self._draw_ws.numel() < nbytes or self._draw_ws.device != out.device:
                 self._draw_ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=out.device)
-            _lib.check(L.mb_pe_draw_members(ctypes.c_void_p(blk.data_ptr()), el, len(el), n, _lib.ptr(out),
-                                            _lib.ptr(self._draw_ws), self._draw_ws.numel(),
-                                            ctypes.c_void_p(side.cuda_stream)))
+            _lib.check(L.mb_pe_draw_members_chained(
+                ctypes.c_void_p(self._draw_state.data_ptr()), ctypes.c_void_p(snap.data_ptr()), el, len(el), n,
+                _lib.ptr(out), _lib.ptr(self._draw_ws), self._draw_ws.numel(), ctypes.c_void_p(side.cuda_stream)))
             ev = torch.cuda.Event()
             ev.record(side)
-        return ev
+        return ev, snap
+
+    def _draw_result(self, ev, snap, el):
+        """Wait for a queued draw; -> (key, pos, produced) from its snapshot block (recycled)."""
+        ev.synchronize()
+        host = snap.numpy().view(np.uint32)
+        key, pos = (host[:624].copy(), int(host[624])) if len(el) > 1 else (None, None)
+        produced = int(host[625]) | (int(host[626]) << 32)
+        self._draw_snaps.append(snap)
+        return key, pos, produced
 
     def draw_members(self, B):
         """``np.random.choice(elite, B)`` (pe_model.py:165-169) generated on the device from
         NumPy's own global MT19937 state: the returned uint8 indices are bit-identical to the
         host call and ``np.random`` is left in the state that call would leave it in.  Costs one
-        read of the 627-word state block (an event wait) instead of a 10-25 ms host loop per
+        read of a 627-word state block (an event wait) instead of a 10-25 ms host loop per
         million rows.
 
-        The draw runs on its own stream.  When two consecutive calls asked for the same (B,
-        elites), the NEXT draw is queued speculatively from the state this one leaves; a later
-        call uses it only if ``np.random`` is still exactly in that state (nobody else drew) and
-        asks for the same shape, so the result is the one a fresh draw would give -- but it was
-        generated under the previous rollout, off the host's critical path."""
+        The draw runs on its own stream.  When consecutive calls ask for the same (B, elites),
+        the next ``draw_lookahead`` draws are queued ahead, each continuing the stream on the
+        device where the previous one stopped.  A later call consumes the head of that queue only
+        if ``np.random`` is still exactly in the state the previous call left (nobody else drew)
+        and the shape is the same; otherwise the queue is dropped and the draw starts from the
+        host state.  Either way the result is what a fresh draw gives -- but a queued one was
+        generated under earlier rollouts, off the host's critical path (small batches are
+        otherwise paced by the draw's launch-and-wait latency, ~0.3 ms per call)."""
         elite = self.elite_indices
         if elite is None:
             elite = list(np.arange(self.ensemble_size))
@@ -299,42 +319,47 @@ class B200PEModel(Component, nn.Module):
         main = torch.cuda.current_stream(dev)
         if self._draw_stream is None:
             self._draw_stream = torch.cuda.Stream(dev)
-            self._draw_state = [torch.zeros(627, dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._draw_state = torch.zeros(627, dtype=torch.int32).pin_memory()
         side = self._draw_stream
         shape = (B, el, str(dev))
-        spec, self._draw_spec = self._draw_spec, None
-        out, done, blk = None, 0, self._draw_state[0]
-        if spec is not None:
-            spec["event"].synchronize()            # nothing may still write its state block
-            if spec["shape"] == shape and spec["pos"] == pos and np.array_equal(spec["key"], key):
-                out, blk = spec["out"], spec["blk"]
-                ev = spec["event"]
-                host = blk.numpy().view(np.uint32)
-                if len(el) > 1:
-                    key, pos = host[:624].copy(), int(host[624])
-                done = int(host[625]) | (int(host[626]) << 32)
-                assert 0 < done <= B
+        q = self._draw_queue
+        left = self._draw_np_state
+        hit = bool(q) and q[0]["shape"] == shape and left is not None and left[1] == pos and \
+            np.array_equal(left[0], key)
+        if q and not hit:                          # drop the look-ahead; the state block must be idle
+            for d in q:
+                self._draw_result(d["event"], d["snap"], el)
+            q.clear()
+        out, done, ev = None, 0, None
+        if hit:
+            d = q.popleft()
+            out, ev = d["out"], d["event"]
+            key, pos, done = self._draw_result(ev, d["snap"], el)
+            assert 0 < done <= B
+            if done < B:                           # word budget ran out: the queued draws behind it are void
+                for d in q:
+                    self._draw_result(d["event"], d["snap"], el)
+                q.clear()
         if out is None:
             with torch.cuda.stream(side):
                 out = torch.empty(B, dtype=torch.uint8, device=dev)
         while done < B:      # one pass unless the word budget (mean + 12 sigma attempts) ran out
-            ev = self._draw_launch(blk, key, pos, el, B - done, out[done:])
-            ev.synchronize()
-            host = blk.numpy().view(np.uint32)
+            ev, snap = self._draw_launch((key, pos), el, B - done, out[done:])
+            k2, p2, produced = self._draw_result(ev, snap, el)
             if len(el) > 1:
-                key, pos = host[:624].copy(), int(host[624])
-            produced = int(host[625]) | (int(host[626]) << 32)
+                key, pos = k2, p2
             assert 0 < produced <= B - done
             done += produced
         main.wait_event(ev)
         out.record_stream(main)
         np.random.set_state((st[0], key, pos, st[3], st[4]))
-        if self.speculative_draw and shape == self._draw_last_shape and len(el) > 1:
-            other = self._draw_state[1] if blk is self._draw_state[0] else self._draw_state[0]
-            with torch.cuda.stream(side):
-                nxt = torch.empty(B, dtype=torch.uint8, device=dev)
-            self._draw_spec = {"shape": shape, "key": np.array(key, copy=True), "pos": pos, "out": nxt, "blk": other,
-                               "event": self._draw_launch(other, key, pos, el, B, nxt)}
+        self._draw_np_state = (np.array(key, copy=True), pos)
+        if shape == self._draw_last_shape and len(el) > 1:
+            while len(q) < self.draw_lookahead:    # every queued draw chains on the block in place
+                with torch.cuda.stream(side):
+                    nxt = torch.empty(B, dtype=torch.uint8, device=dev)
+                e2, s2 = self._draw_launch(None, el, B, nxt)
+                q.append({"shape": shape, "out": nxt, "event": e2, "snap": s2})
         self._draw_last_shape = shape
         return out
 

@@ -17,8 +17,8 @@ for B in (125_000, 250_000, 1_000_000):
             m.step_rows(o, a, buf[k & 1])
         torch.cuda.synchronize()
 
-    for spec in (False, True):
-        m.speculative_draw = spec
+    for spec in (0, 1, 2, 3):
+        m.draw_lookahead = spec
         loop(10)
         t = time.perf_counter(); loop(100); dt = (time.perf_counter() - t) / 100
         print("B=%7d spec=%d: %.3f ms per call (%.1f M rows/s)" % (B, spec, dt * 1e3, B / dt / 1e6), flush=True)
