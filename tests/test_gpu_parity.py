@@ -500,6 +500,37 @@ def test_full_size_properties(kernel):
     assert_close(r0, sel[:, 17:], what="zero-noise reward")
 
 
+def test_maximum_size_rollout_10m_rows():
+    """BASELINE.json's largest rollout batch (1e7 states, horizon 15 chained in place): rows are
+    independent, so every horizon step of a 50k-row slice taken alone must reproduce the same rows
+    of the full run bit for bit (catches 32-bit index overflow in the bucketing, the tile plan and
+    the pool-row addressing), and the pool rows must chain: obs of step h == next_obs of h-1."""
+    m, _ = make_pe_model(cases.MBPO, 11, kernel="tcgen05")
+    _kernel_or_skip(m, "tcgen05")
+    m.remember_loss(LOSS_VEC7)
+    B, H, O, A = 10_000_000, 15, 17, 6
+    lo, hi = B - 50_000, B                       # the slice with the largest addresses
+    g = torch.Generator(device="cuda").manual_seed(9)
+    o = torch.randn(B, O, device="cuda", generator=g)
+    pool = torch.empty(2 * B, m.row_stride(), device="cuda")
+    small = torch.empty(2, hi - lo, m.row_stride(), device="cuda")
+    os_ = o[lo:hi].clone()
+    for h in range(H):
+        a = torch.rand(B, A, device="cuda", generator=g) * 2 - 1
+        eps = torch.randn(B, O + 1, device="cuda", generator=g)
+        idx = torch.randint(0, 5, (B,), device="cuda", generator=g).to(torch.uint8)
+        idx = torch.tensor(m.elite_indices, device="cuda", dtype=torch.uint8)[idx.long()]
+        off = (h & 1) * B
+        no, r, d = m.step_rows(o, a, pool, row_offset=off, indices=idx, noise=eps)
+        rows = pool[off:off + B]
+        assert torch.equal(rows[:, :O], o) and torch.equal(rows[:, O:O + A], a)
+        sn, sr, sd = m.step_rows(os_, a[lo:hi], small[h & 1], indices=idx[lo:hi], noise=eps[lo:hi])
+        assert torch.equal(no[lo:hi], sn) and torch.equal(r[lo:hi], sr) and torch.equal(d[lo:hi], sd)
+        assert bool(torch.isfinite(no).all())
+        o, os_ = no, sn                          # views into the pool rows: the next step reads them in place
+    assert float(pool[:, 2 * O + A + 1].abs().sum()) == 0.0      # cheetah never terminates
+
+
 def test_device_pool_matches_reference_simple_pool():
     """B200DevicePool against the reference SimplePool run (tests/golden/pool.npz): ring inserts that
     wrap, sampled batches from the same NumPy stream (bit-exact: pure data movement), get_data
