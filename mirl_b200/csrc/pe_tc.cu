@@ -213,7 +213,16 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 const int* __restrict__ perm, const int* __restrict__ totals,
                 int64_t seg, int done_kind, float* __restrict__ next_obs,
                 float* __restrict__ reward, float* __restrict__ done, RowsOut rows, TcForward fwd, TcZSave zs,
-                int dbg) {
+                int dbg_arg) {
+    // Timing-experiment switches (MB_TC_DEBUG) exist only in builds with -DMB_TC_DEBUG_HOOKS: as
+    // a run-time argument they cost a select per activation in the epilogue (16 of ~150
+    // instructions per 16-column block).
+#ifdef MB_TC_DEBUG_HOOKS
+    const int dbg = dbg_arg;
+#else
+    constexpr int dbg = 0;
+    (void)dbg_arg;
+#endif
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
