@@ -139,16 +139,23 @@ k_tc_gemm(TgBatch gb, int nt_max) {
 
     // item coordinates (fixed for the whole kernel): A 128 x 8 items, B NT x 8 items (NT <= 128)
     constexpr int kItems = kUmmaM * (kTgKC / 8) / kTgThreads;         // 2
+    const int a_act = op.a_act, a_strided = op.a_trans, a_ones = op.a_ones_row, b_strided = op.b_trans ? 0 : 1;
+    // Two lane mappings.  Operand stored with the reduction index strided (element (g, r) at
+    // src[r*ld + g]): lanes on 32 consecutive rows g, so each scalar load of the warp is one 128 B
+    // line.  Reduction index contiguous: a warp covers 8 rows x 4 k-chunks -- the 4 chunks of a row
+    // are 128 contiguous bytes, so a 16 B load instruction touches 8 lines instead of 32, and the
+    // 8 lanes of a quarter warp write the 8 rows of one core matrix (128 contiguous bytes of
+    // shared memory, no bank conflict).
     TgItem ia[kItems], ib[kItems];
 #pragma unroll
     for (int q = 0; q < kItems; ++q) {
         const int it = (int)threadIdx.x + q * kTgThreads;
-        ia[q].row = it & (kUmmaM - 1);
-        ia[q].j = it / kUmmaM;
-        ib[q].row = it < NT * (kTgKC / 8) ? it % NT : -1;
-        ib[q].j = it / NT;
+        const int row8 = 8 * warp + (lane & 7), j8 = 4 * q + (lane >> 3);
+        if (a_strided) { ia[q].row = it & (kUmmaM - 1); ia[q].j = it / kUmmaM; }
+        else { ia[q].row = row8; ia[q].j = j8; }
+        if (b_strided) { ib[q].row = it < NT * (kTgKC / 8) ? it % NT : -1; ib[q].j = it / NT; }
+        else { ib[q].row = row8 < NT ? row8 : -1; ib[q].j = j8; }
     }
-    const int a_act = op.a_act, a_strided = op.a_trans, a_ones = op.a_ones_row, b_strided = op.b_trans ? 0 : 1;
     const int64_t lda = op.lda, ldb = op.ldb;
     const int Nn = op.N;
     auto stage = [&](int c, int s) {
