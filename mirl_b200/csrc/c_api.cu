@@ -49,6 +49,11 @@ int validate_model(const mb_pe_model* m, const char* who) {
     return MB_OK;
 }
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("MB_PDL"); return !(v && v[0] == '0'); }();
+    return on;
+}
+
 static int g_reserved_sms = 0;
 int reserved_sms() { return g_reserved_sms; }
 

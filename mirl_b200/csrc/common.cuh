@@ -29,6 +29,32 @@ void set_error(const char* fmt, ...);
 
 __host__ __device__ inline int64_t round_up4(int64_t x) { return (x + 3) & ~int64_t(3); }
 
+// ---- programmatic dependent launch (the latency-bound chains: train step, critic layers) -------
+// A kernel launched through launch_pdl may become resident while its predecessor in the stream is
+// still running (as soon as every CTA of the predecessor has called pdl_trigger or exited); it
+// runs its prologue (barrier init, TMEM allocation, descriptor copies) and then blocks in
+// pdl_wait until the predecessor has completed and its writes are visible.  Both instructions
+// are no-ops for a grid launched the ordinary way.  MB_PDL=0 launches everything the ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // errors surface in MB_CUDA_LAUNCH_CHECK
+}
+#endif
+
 // ---- packed parameter blob layout (include/mirl_b200.h, mb_mlp_desc) ----------------------
 __host__ __device__ inline int64_t w_offset(const mb_mlp_desc& d, int layer) {
     int64_t off = 0;

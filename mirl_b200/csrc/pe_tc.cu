@@ -160,6 +160,8 @@ size_t tc_pack_bytes(const mb_mlp_desc& d) {
 //      output column (n == N, hidden layers) is kSwishOne so that column of the next A operand is 1.
 //      blockIdx.z == L writes the member's [32 max_logstd | 32 min_logstd] block.
 __global__ void k_tc_pack(mb_mlp_desc d, TcShape s, const float* __restrict__ params, uint8_t* __restrict__ pack) {
+    pdl_trigger();
+    pdl_wait();
     const int e = blockIdx.y, l = blockIdx.z;
     uint8_t* mp = pack + (int64_t)e * s.member_bytes;
     if (l == s.L) {
@@ -262,6 +264,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcMaxStages + kTcMaxKs + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if constexpr (kZSave) pdl_trigger();
     __shared__ long long tl[4][40];          // debug timeline (MB_TC_DEBUG & 8), CTA 0 only
 #define TL(i, slot)                                                                       \
     do {                                                                                  \
@@ -308,6 +311,9 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // training forward (launched with programmatic dependent launch behind the weight re-pack):
+    // the set-up above ran under the predecessor's tail; its writes are needed from here on
+    if constexpr (kZSave) pdl_wait();
 
     if (warp >= kTcEpiWarp0 && warp < kTcEpiWarp0 + kTcEpiWarps) {
         // ================================ EPILOGUE WARPS ========================================
@@ -790,7 +796,7 @@ int launch_tc_pack(const PeDev& m, void* pack, cudaStream_t st) {
     TcShape s = tc_shape(m.mlp);
     if (!s.ok) { set_error("tcgen05 rollout kernel does not support this model shape"); return MB_EUNSUPPORTED; }
     dim3 grid(16, (unsigned)m.mlp.ensemble_size, (unsigned)s.L + 1);
-    k_tc_pack<<<grid, 256, 0, st>>>(m.mlp, s, m.params, reinterpret_cast<uint8_t*>(pack));
+    launch_pdl(k_tc_pack, grid, dim3(256), 0, st, m.mlp, s, m.params, reinterpret_cast<uint8_t*>(pack));
     MB_CUDA_LAUNCH_CHECK("k_tc_pack");
     return MB_OK;
 }
@@ -834,9 +840,15 @@ static int launch_tc_forward(const PeDev& m, const TcShape& s, const void* pack,
     sms -= reserved_sms();
     const int64_t ntiles = (int64_t)n_members * ((fwd.B + kTcTM - 1) / kTcTM);
     const int grid = ntiles < sms ? (int)ntiles : sms;
-    k_pe_rollout_tc<kZSave><<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, m.O, act,
-                                                            m.A, nullptr, nullptr, nullptr, 0, MB_DONE_CHEETAH, nullptr,
-                                                            nullptr, nullptr, RowsOut{}, fwd, zs, 0);
+    if constexpr (kZSave)
+        launch_pdl(k_pe_rollout_tc<true>, dim3(grid), dim3(kTcThreads), smem, st, m, s,
+                   reinterpret_cast<const uint8_t*>(pack), obs, (int64_t)m.O, act, (int64_t)m.A, (const float*)nullptr,
+                   (const int*)nullptr, (const int*)nullptr, (int64_t)0, (int)MB_DONE_CHEETAH, (float*)nullptr,
+                   (float*)nullptr, (float*)nullptr, RowsOut{}, fwd, zs, 0);
+    else
+        k_pe_rollout_tc<false><<<grid, kTcThreads, smem, st>>>(m, s, reinterpret_cast<const uint8_t*>(pack), obs, m.O,
+                                                               act, m.A, nullptr, nullptr, nullptr, 0, MB_DONE_CHEETAH,
+                                                               nullptr, nullptr, nullptr, RowsOut{}, fwd, zs, 0);
     MB_CUDA_LAUNCH_CHECK("k_pe_rollout_tc(forward)");
     return MB_OK;
 }

@@ -167,6 +167,8 @@ __global__ void k_train_prep(PeDev m, int e0, int ne, const float* __restrict__ 
                              const float* __restrict__ act, int64_t B, float* __restrict__ x0s,
                              float* __restrict__ grads, float* __restrict__ ensemble_loss,
                              float* __restrict__ loss_terms) {
+    pdl_trigger();
+    pdl_wait();
     const int O = m.O, A = m.A, IN = O + A, D = O + 1;
     const float* nrm = m.norm;
     const int64_t total = (int64_t)ne * B * IN;
@@ -198,6 +200,8 @@ k_train_loss(PeDev m, mb_train_cfg cfg, int e0, const float* __restrict__ out,
              float* __restrict__ grads, float* __restrict__ ensemble_loss, float* __restrict__ loss_terms) {
     __shared__ float red[8];
     __shared__ float gmx[64], gmn[64];
+    pdl_trigger();
+    pdl_wait();
     const int O = m.O, A = m.A, D = O + 1;
     const int e = e0 + blockIdx.y;
     const int64_t mrow = (int64_t)e * B;
@@ -443,6 +447,8 @@ struct AdamSegs { int n; int64_t off[2 * MB_MAX_LAYERS + 2]; int64_t len[2 * MB_
 // Advances the device-resident step count and derives Adam's two bias-correction scalars from it
 // ONCE (double-precision pow is slow on this part; every k_adam block used to redo it).
 __global__ void k_step_inc(int32_t* step_counter, float* scal, float lr, float beta1, float beta2) {
+    pdl_trigger();
+    pdl_wait();
     *step_counter += 1;
     const double t = (double)*step_counter;
     scal[0] = (float)((double)lr / (1.0 - pow((double)beta1, t)));
@@ -454,6 +460,8 @@ __global__ void k_adam(AdamSegs segs, float* __restrict__ p, float* __restrict__
                        float* __restrict__ m2, const float* __restrict__ g, float beta1,
                        float beta2, float eps, float step_size, float bc2_sqrt,
                        const float* __restrict__ scal) {
+    pdl_trigger();
+    pdl_wait();
     if (scal != nullptr) {                   // graph replay: scalars written by k_step_inc
         step_size = scal[0];
         bc2_sqrt = scal[1];
@@ -518,8 +526,8 @@ int launch_pe_train(const PeDev& m, void* tc_pack, const mb_train_cfg& cfg, floa
         // small batch: one launch per layer spreads the work over all SMs
         {
             const int64_t total = (int64_t)ne * B * d.sizes[0];
-            k_train_prep<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m, e0, ne, obs, act, B, w.x0, grads,
-                                                                       ensemble_loss, loss_terms);
+            launch_pdl(k_train_prep, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, m, e0, ne, obs, act, B,
+                       w.x0, grads, ensemble_loss, loss_terms);
             MB_CUDA_LAUNCH_CHECK("k_train_prep");
         }
         // One launch for the whole forward when the fused tile kernel covers the shape: the
@@ -561,8 +569,8 @@ int launch_pe_train(const PeDev& m, void* tc_pack, const mb_train_cfg& cfg, floa
             if (rc) return rc;
         }
         dim3 gl((unsigned)((B + kLossRows - 1) / kLossRows), (unsigned)ne);
-        k_train_loss<<<gl, 256, 0, s>>>(m, cfg, e0, gnext, delta, reward, done, B, gcur, grads, ensemble_loss,
-                                        loss_terms);
+        launch_pdl(k_train_loss, gl, dim3(256), 0, s, m, cfg, e0, (const float*)gnext, delta, reward, done, B, gcur,
+                   grads, ensemble_loss, loss_terms);
         MB_CUDA_LAUNCH_CHECK("k_train_loss");
     } else {
         // large batch: fused tile kernel keeps the activations on chip
@@ -677,11 +685,11 @@ int launch_pe_train(const PeDev& m, void* tc_pack, const mb_train_cfg& cfg, floa
         float* scal = nullptr;
         if (step_counter) {
             scal = w.grads + round_up4(param_count(d, true));          // inside the workspace's tail slack
-            k_step_inc<<<1, 1, 0, s>>>(step_counter, scal, cfg.lr, cfg.beta1, cfg.beta2);
+            launch_pdl(k_step_inc, dim3(1), dim3(1), 0, s, step_counter, scal, cfg.lr, cfg.beta1, cfg.beta2);
             MB_CUDA_LAUNCH_CHECK("k_step_inc");
         }
-        k_adam<<<ga, 256, 0, s>>>(segs, params, exp_avg, exp_avg_sq, grads, cfg.beta1, cfg.beta2, cfg.eps,
-                                  (float)(cfg.lr / bc1), (float)sqrt(bc2), scal);
+        launch_pdl(k_adam, ga, dim3(256), 0, s, segs, params, exp_avg, exp_avg_sq, (const float*)grads, cfg.beta1,
+                   cfg.beta2, cfg.eps, (float)(cfg.lr / bc1), (float)sqrt(bc2), (const float*)scal);
         MB_CUDA_LAUNCH_CHECK("k_adam");
     }
     (void)E;

@@ -97,6 +97,7 @@ k_tc_gemm(TgBatch gb, int nt_max) {
     // this CTA's descriptor -> shared memory once (indexing the kernel-parameter array with a
     // run-time index makes every later field access a slow indexed constant load)
     __shared__ TgOp sop;
+    pdl_trigger();
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&gb.op[blockIdx.z / gb.nmem]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sop);
@@ -165,6 +166,7 @@ k_tc_gemm(TgBatch gb, int nt_max) {
         tg_stage<kItems>(b_hi(s), b_lo(s), (uint32_t)NT * 16u, ib, Bm, ldb, b_strided, -1, n0, Nn, -1, r0, R);
     };
 
+    pdl_wait();            // everything above touched only shared / tensor memory
     stage(0, 0);
     fence_proxy_async();
     tc_fence_before();
@@ -342,7 +344,7 @@ int launch_tc_gemm(const TgBatch& b, cudaStream_t s) {
         configured = smem;
     }
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)(b.nops * b.nmem));
-    k_tc_gemm<<<grid, kTgThreads, smem, s>>>(b, nt_max);
+    launch_pdl(k_tc_gemm, grid, dim3(kTgThreads), smem, s, b, nt_max);
     MB_CUDA_LAUNCH_CHECK("k_tc_gemm");
     return MB_OK;
 }

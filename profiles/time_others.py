@@ -23,7 +23,7 @@ def timeit(fn, n=200, warm=20):
 
 
 m, _ = make_pe_model(cases.MBPO, 11)
-tr = mirl_b200.B200PEModelTrainer(FakeEnv(), m, tb_log_freq=-1, silent=True, use_cuda_graph="--nograph" not in sys.argv)
+tr = mirl_b200.B200PEModelTrainer(FakeEnv(), m, tb_log_freq=-1, silent=True, use_cuda_graph="--graph" in sys.argv)
 for B in (256, 1024, 4096):
     bt = {k: T(v, "cuda") for k, v in cases.train_batch(600, 7, B).items()}
     ms = timeit(lambda: tr.train_step_async(bt))

@@ -190,14 +190,17 @@ def test_gradients_match_reference_autograd():
             assert abs(got[1] - ref[1]) <= 1e-3 * ref[0] + 1e-9, (name, got, ref)     # projection
 
 
+@pytest.mark.parametrize("graph", [False, True])
 @pytest.mark.parametrize("tag,cfg,seed,B", [("small", cases.SMALL, 51, 64), ("mbpo", cases.MBPO, 11, 256)])
-def test_fused_train_steps_match_reference_adam(tag, cfg, seed, B):
+def test_fused_train_steps_match_reference_adam(tag, cfg, seed, B, graph):
+    """Ten fused steps against the reference's Adam run; stream launches (programmatic dependent
+    launch, host-side step count) and CUDA-graph replay (device-side step count)."""
     import mirl_b200
     from tests.helpers_gpu import FakeEnv
     g = golden("pe_train_%s.npz" % tag)
     m, _ = make_pe_model(cfg, seed)
     tr = mirl_b200.B200PEModelTrainer(FakeEnv(), m, lr=1e-3, tb_log_freq=-1, silent=True,
-                                      ignore_terminal_state=False)
+                                      ignore_terminal_state=False, use_cuda_graph=graph)
     for s in range(10):
         diag = tr.train_from_torch_batch(_batch(600 + s, cfg["E"], B))
         assert_close(np.array(diag["train_loss"]), g["loss"][s], what="loss step %d" % s)
