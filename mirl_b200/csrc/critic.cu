@@ -257,6 +257,8 @@ __global__ void k_redq_reduce(const float* __restrict__ q, int nmem, MemberList 
                               const float* __restrict__ reward, const float* __restrict__ terminal,
                               const float* __restrict__ log_prob, float alpha, float discount,
                               float* __restrict__ value) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= B) return;
     float acc = mode == MB_REDUCE_MIN ? INFINITY : mode == MB_REDUCE_MAX ? -INFINITY : 0.f;
@@ -283,6 +285,8 @@ k_tqc_sort(const float* __restrict__ raw /*[E][B][Q]*/, int E, int Q, int64_t B,
            const float* __restrict__ log_prob, float alpha, float discount, float* __restrict__ value,
            float* __restrict__ atoms) {
     extern __shared__ float pool[];                       // [8 warps][npad]
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * 8 + warp;
     if (r >= B) return;
@@ -394,8 +398,8 @@ int launch_critic_redq(const mb_mlp_desc& d, const float* params, const float* o
         float* q = nullptr;
         int rc = layered_forward(d, params, obs, act, O, A, B, ml.id, ml.n, (float*)ws, nullptr, &q, s);
         if (rc) return rc;
-        k_redq_reduce<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(q, ml.n, ml, B, row_members, n_sub, mode, td, reward,
-                                                                 terminal, log_prob, alpha, discount, value);
+        launch_pdl(k_redq_reduce, dim3((unsigned)((B + 255) / 256)), dim3(256), 0, s, (const float*)q, ml.n, ml, B,
+                   row_members, n_sub, mode, td, reward, terminal, log_prob, alpha, discount, value);
         MB_CUDA_LAUNCH_CHECK("k_redq_reduce");
         return MB_OK;
     }
@@ -425,9 +429,9 @@ int launch_critic_tqc(const mb_mlp_desc& d, const float* params, const float* ob
         const int NAl = d.ensemble_size * d.sizes[d.num_layers];
         int np2 = 32;
         while (np2 < NAl) np2 <<= 1;
-        k_tqc_sort<<<(unsigned)((B + 7) / 8), 256, (size_t)8 * np2 * sizeof(float), s>>>(
-            raw, d.ensemble_size, d.sizes[d.num_layers], B, n_drop, np2, td, reward, terminal, log_prob, alpha, discount,
-            value, atoms);
+        launch_pdl(k_tqc_sort, dim3((unsigned)((B + 7) / 8)), dim3(256), (size_t)8 * np2 * sizeof(float), s,
+                   (const float*)raw, d.ensemble_size, d.sizes[d.num_layers], B, n_drop, np2, td, reward, terminal,
+                   log_prob, alpha, discount, value, atoms);
         MB_CUDA_LAUNCH_CHECK("k_tqc_sort");
         return MB_OK;
     }

@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(256)
 k_layer_gemm(LayerArgs a, ConcatIn ci) {
     __shared__ __align__(16) float As[kLgK][kLgLD];
     __shared__ __align__(16) float Bs[kLgK][kLgLD];
+    pdl_trigger();
+    pdl_wait();
     const int z = blockIdx.z, e = a.member[z], slot = a.slot0 + z;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * kLgT, n0 = blockIdx.x * kLgT;
@@ -150,10 +152,10 @@ k_layer_gemm(LayerArgs a, ConcatIn ci) {
 
 inline int launch_layer(const LayerArgs& a, const ConcatIn* ci, cudaStream_t s) {
     dim3 grid((unsigned)((a.N + kLgT - 1) / kLgT), (unsigned)((a.B + kLgT - 1) / kLgT), (unsigned)a.nmem);
-    if (ci) k_layer_gemm<true><<<grid, 256, 0, s>>>(a, *ci);
+    if (ci) launch_pdl(k_layer_gemm<true>, grid, dim3(256), 0, s, a, *ci);
     else {
         ConcatIn none{};
-        k_layer_gemm<false><<<grid, 256, 0, s>>>(a, none);
+        launch_pdl(k_layer_gemm<false>, grid, dim3(256), 0, s, a, none);
     }
     MB_CUDA_LAUNCH_CHECK("k_layer_gemm");
     return MB_OK;
