@@ -69,13 +69,15 @@ __device__ __forceinline__ void tg_load8(const float* __restrict__ src, int64_t 
 // of the thread are issued before the first conversion.
 struct TgItem { int row, j; };
 template <int NI>
-__device__ __forceinline__ void tg_stage(uint32_t hi_plane, uint32_t lo_plane, uint32_t lbo, const TgItem (&it)[NI],
-                                         const float* __restrict__ src, int64_t ld, int strided, int act, int row0,
-                                         int rows_valid, int ones_row, int r0, int R) {
-    float v[NI][8];
+__device__ __forceinline__ void tg_fetch(float (&v)[NI][8], const TgItem (&it)[NI], const float* __restrict__ src,
+                                         int64_t ld, int strided, int row0, int rows_valid, int ones_row, int r0, int R) {
 #pragma unroll
     for (int q = 0; q < NI; ++q)
         if (it[q].row >= 0) tg_load8(src, ld, strided, row0 + it[q].row, rows_valid, ones_row, r0 + 8 * it[q].j, R, v[q]);
+}
+template <int NI>
+__device__ __forceinline__ void tg_convert(float (&v)[NI][8], uint32_t hi_plane, uint32_t lo_plane, uint32_t lbo,
+                                           const TgItem (&it)[NI], int act, int row0, int ones_row) {
 #pragma unroll
     for (int q = 0; q < NI; ++q) {
         if (it[q].row < 0) continue;
@@ -159,15 +161,22 @@ k_tc_gemm(TgBatch gb, int nt_max) {
     }
     const int64_t lda = op.lda, ldb = op.ldb;
     const int Nn = op.N;
-    auto stage = [&](int c, int s) {
+    // stage = fetch (global -> registers, both operands in flight together) + convert (registers ->
+    // bf16 hi/lo planes of ring slot s); `ready` runs between the two: the loads overlap whatever
+    // it waits for
+    auto stage = [&](int c, int s, auto&& ready) {
         const int r0 = c * kTgKC;
-        tg_stage<kItems>(a_hi(s), a_lo(s), kUmmaM * 16u, ia, A, lda, a_strided, a_act, m0, a_rows, a_ones, r0, R);
+        float va[kItems][8], vb[kItems][8];
+        tg_fetch<kItems>(va, ia, A, lda, a_strided, m0, a_rows, a_ones, r0, R);
         // "reduction index is the strided one" is b_trans == 0 for B'
-        tg_stage<kItems>(b_hi(s), b_lo(s), (uint32_t)NT * 16u, ib, Bm, ldb, b_strided, -1, n0, Nn, -1, r0, R);
+        tg_fetch<kItems>(vb, ib, Bm, ldb, b_strided, n0, Nn, -1, r0, R);
+        ready();
+        tg_convert<kItems>(va, a_hi(s), a_lo(s), kUmmaM * 16u, ia, a_act, m0, a_ones);
+        tg_convert<kItems>(vb, b_hi(s), b_lo(s), (uint32_t)NT * 16u, ib, -1, n0, -1);
     };
 
     pdl_wait();            // everything above touched only shared / tensor memory
-    stage(0, 0);
+    stage(0, 0, [] {});
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -197,11 +206,12 @@ k_tc_gemm(TgBatch gb, int nt_max) {
         }
         if (c + 1 < nch) {
             const int ns = s ^ 1;
-            if (c >= 1) {                       // the MMAs of chunk c-1 have finished reading stage ns
-                if (ns == 0) { mbar_wait_relaxed(bar0, ph0); ph0 ^= 1u; }
-                else { mbar_wait_relaxed(bar0 + 8, ph1); ph1 ^= 1u; }
-            }
-            stage(c + 1, ns);
+            stage(c + 1, ns, [&] {
+                if (c >= 1) {                   // the MMAs of chunk c-1 have finished reading stage ns
+                    if (ns == 0) { mbar_wait_relaxed(bar0, ph0); ph0 ^= 1u; }
+                    else { mbar_wait_relaxed(bar0 + 8, ph1); ph1 ^= 1u; }
+                }
+            });
             fence_proxy_async();
         }
         tc_fence_before();
