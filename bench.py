@@ -297,7 +297,6 @@ def main():
     # ---- end to end through the public API from pinned host buffers ------------------------------
     h_obs0 = obs0.cpu().pin_memory()
     h_acts = acts.cpu().pin_memory()
-    h_out = torch.empty(H, B, O + 2).pin_memory()
     np.random.seed(4321 + rank)
     torch.manual_seed(4321 + rank)
 
@@ -306,51 +305,68 @@ def main():
     # [next_obs | reward | done] goes back to pinned host memory.  PCIe is full duplex, so the
     # batch is rolled in row chunks: the H2D copies run ahead on one copy stream in the order the
     # rollouts consume them, the D2H of every (chunk, step) runs on another under the next rollout
-    # (two row buffers), and the link carries both directions at once.
+    # (two row buffers), and the link carries both directions at once.  Consecutive steps are
+    # pipelined MB_E2E_DEPTH deep (default 2: double-buffered device inputs and host outputs; the
+    # host takes ownership of step k's transitions before it issues step k+2; depth 1 = the
+    # caller waits for every step's transitions before issuing the next step).
     W = 2 * O + A + 2
     n_chunks = max(1, int(os.environ.get("MB_E2E_CHUNKS", "2")))
+    depth = max(1, min(2, int(os.environ.get("MB_E2E_DEPTH", "2"))))
     bounds = [B * c // n_chunks for c in range(n_chunks + 1)]
     Bc = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
     e2e_rows = torch.empty(2, Bc, W, device=dev)
-    d_obs0 = torch.empty(B, O, device=dev)
-    d_acts = torch.empty(H, B, A, device=dev)
+    h_out = [torch.empty(H, B, O + 2).pin_memory() for _ in range(depth)]
+    d_obs0 = [torch.empty(B, O, device=dev) for _ in range(depth)]
+    d_acts = [torch.empty(H, B, A, device=dev) for _ in range(depth)]
     in_stream, copy_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
-    in_ready = [[torch.cuda.Event() for _ in range(H)] for _ in range(n_chunks)]
+    in_ready = [[[torch.cuda.Event() for _ in range(H)] for _ in range(n_chunks)] for _ in range(depth)]
+    rolled = [torch.cuda.Event() for _ in range(depth)]        # the step's rollouts have read its device inputs
+    landed = [torch.cuda.Event() for _ in range(depth)]        # the step's transitions are in host memory
+    e2e_count = [0, 0]                                         # steps issued, row-buffer uses
 
     def e2e_step():
         main = torch.cuda.current_stream()
-        in_stream.wait_stream(main)                # the device inputs of the previous call are free
+        step_no = e2e_count[0]
+        p = step_no % depth
+        e2e_count[0] += 1
+        if step_no >= depth:
+            landed[p].synchronize()                # the caller owns the transitions of step_no - depth
+            in_stream.wait_event(rolled[p])        # ... and that step is done with this input set
         with torch.cuda.stream(in_stream):
             for c in range(n_chunks):
                 lo, hi = bounds[c], bounds[c + 1]
-                d_obs0[lo:hi].copy_(h_obs0[lo:hi], non_blocking=True)
+                d_obs0[p][lo:hi].copy_(h_obs0[lo:hi], non_blocking=True)
                 for h in range(H):
-                    d_acts[h, lo:hi].copy_(h_acts[h, lo:hi], non_blocking=True)
-                    in_ready[c][h].record(in_stream)
-        k = 0
+                    d_acts[p][h, lo:hi].copy_(h_acts[h, lo:hi], non_blocking=True)
+                    in_ready[p][c][h].record(in_stream)
         for c in range(n_chunks):
             lo, hi = bounds[c], bounds[c + 1]
-            o = d_obs0[lo:hi]
+            o = d_obs0[p][lo:hi]
             for h in range(H):
+                k = e2e_count[1]
+                e2e_count[1] += 1
                 buf = e2e_rows[k & 1, :hi - lo]
-                main.wait_event(in_ready[c][h])
+                main.wait_event(in_ready[p][c][h])
                 main.wait_event(copy_done[k & 1])  # its previous contents have left for the host
-                o, _, _ = model.step_rows(o, d_acts[h, lo:hi], buf)
+                o, _, _ = model.step_rows(o, d_acts[p][h, lo:hi], buf)
                 ev = torch.cuda.Event()
                 ev.record(main)
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(ev)
-                    h_out[h, lo:hi].copy_(buf[:, O + A:], non_blocking=True)
+                    h_out[p][h, lo:hi].copy_(buf[:, O + A:], non_blocking=True)
                     copy_done[k & 1].record(copy_stream)
-                k += 1
-        copy_stream.synchronize()                  # the caller owns the transitions now
+        rolled[p].record(main)
+        landed[p].record(copy_stream)
+        if depth == 1:
+            landed[p].synchronize()                # the caller owns the transitions now
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_ms = timed(e2e_step, e2e_steps, 3) / e2e_steps
     e2e = {"value": world * B * H / (e2e_ms * 1e-3), "unit": "transitions/s",
            "h2d_bytes_per_step": B * O * 4 + H * (B * A * 4 + n_chunks * 627 * 4),
-           "d2h_bytes_per_step": H * B * (O + 2) * 4, "ms_per_step": e2e_ms, "row_chunks": n_chunks}
+           "d2h_bytes_per_step": H * B * (O + 2) * 4, "ms_per_step": e2e_ms, "row_chunks": n_chunks,
+           "steps_in_flight": depth}
 
     # ---- roofline of the dominant kernel (events inside the C ABI around that kernel only) -------
     roof = None
