@@ -205,15 +205,19 @@ static bool critic_gemm_tc() {
 
 // Runs the stack for `nmem` members; returns the final layer's output [nmem][B][N_out] (in ws
 // unless `final_out` is given).
+// `layers` < num_layers stops after that many layers and returns the (activated) hidden rows
+// [nmem][B][sizes[layers]] -- the caller then folds the remaining narrow output layer into its
+// own reduction kernel instead of paying a GEMM launch for it.
 static int layered_forward(const mb_mlp_desc& d, const float* params, const float* obs, const float* act,
                            int O, int A, int64_t B, const int* members, int nmem, float* ws, float* final_out,
-                           float** result, cudaStream_t s) {
+                           float** result, cudaStream_t s, int layers = -1) {
+    if (layers < 0) layers = d.num_layers;
     int w = 0;
     for (int l = 0; l <= d.num_layers; ++l) w = d.sizes[l] > w ? d.sizes[l] : w;
     float* buf[2] = {ws, ws + (int64_t)d.ensemble_size * B * w};
     float* last = final_out ? final_out : ws + 2 * (int64_t)d.ensemble_size * B * w;
     ConcatIn ci{obs, act, nullptr, O, A, 0};
-    for (int l = 0; l < d.num_layers; ++l) {
+    for (int l = 0; l < layers; ++l) {
         LayerArgs a;
         a.B = (int)B; a.K = d.sizes[l]; a.N = d.sizes[l + 1];
         a.A = l == 0 ? nullptr : buf[(l - 1) & 1];
@@ -247,8 +251,43 @@ static int layered_forward(const mb_mlp_desc& d, const float* params, const floa
         int rc = launch_layer(a, l == 0 ? &ci : nullptr, s);
         if (rc) return rc;
     }
-    *result = last;
+    *result = layers == d.num_layers ? last : buf[(layers - 1) & 1];
     return MB_OK;
+}
+
+// The same reduction with the critics' single-output last layer folded in: one warp per row,
+// q_k = h[k][r][:] . W_last[e_k] + b_last[e_k] (ensemble_value.py:65-107 after the hidden stack).
+__global__ void __launch_bounds__(256)
+k_redq_reduce_dot(const float* __restrict__ h, int K, const float* __restrict__ Wl, const float* __restrict__ bl,
+                  int nmem, MemberList ml, int64_t B, const uint8_t* __restrict__ row_members, int n_sub, int mode,
+                  int td, const float* __restrict__ reward, const float* __restrict__ terminal,
+                  const float* __restrict__ log_prob, float alpha, float discount, float* __restrict__ value) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= B) return;
+    float acc = mode == MB_REDUCE_MIN ? INFINITY : mode == MB_REDUCE_MAX ? -INFINITY : 0.f;
+    for (int k = 0; k < nmem; ++k) {
+        bool use = true;
+        if (row_members) {
+            use = false;
+            for (int sidx = 0; sidx < n_sub; ++sidx) use = use || (row_members[(int64_t)sidx * B + r] == ml.id[k]);
+        }
+        if (!use) continue;                                   // uniform over the warp (same row)
+        const float* hr = h + ((int64_t)k * B + r) * K;
+        const float* w = Wl + (int64_t)ml.id[k] * K;
+        float v = 0.f;
+        for (int j = lane; j < K; j += 32) v = fmaf(hr[j], w[j], v);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        v += bl[ml.id[k]];
+        acc = mode == MB_REDUCE_MIN ? fminf(acc, v) : mode == MB_REDUCE_MAX ? fmaxf(acc, v) : acc + v;
+    }
+    if (lane) return;
+    if (mode == MB_REDUCE_MEAN) acc /= (float)n_sub;
+    if (td) acc = reward[r] + (1.f - terminal[r]) * discount * (acc - alpha * log_prob[r]);
+    value[r] = acc;
 }
 
 // value[b] = reduce over the evaluated members that count for row b (+ optional TD transform)
@@ -396,6 +435,16 @@ int launch_critic_redq(const mb_mlp_desc& d, const float* params, const float* o
     const int w = max_width(d);
     if (ws && B * ml.n <= kLayeredMaxRows) {
         float* q = nullptr;
+        const int L = d.num_layers;
+        if (L >= 2 && d.sizes[L] == 1) {       // Q critics: the 1-wide output layer rides in the reduction
+            int rc = layered_forward(d, params, obs, act, O, A, B, ml.id, ml.n, (float*)ws, nullptr, &q, s, L - 1);
+            if (rc) return rc;
+            launch_pdl(k_redq_reduce_dot, dim3((unsigned)((B + 7) / 8)), dim3(256), 0, s, (const float*)q, d.sizes[L - 1],
+                       params + w_offset(d, L - 1), params + b_offset(d, L - 1), ml.n, ml, B, row_members, n_sub, mode,
+                       td, reward, terminal, log_prob, alpha, discount, value);
+            MB_CUDA_LAUNCH_CHECK("k_redq_reduce_dot");
+            return MB_OK;
+        }
         int rc = layered_forward(d, params, obs, act, O, A, B, ml.id, ml.n, (float*)ws, nullptr, &q, s);
         if (rc) return rc;
         launch_pdl(k_redq_reduce, dim3((unsigned)((B + 255) / 256)), dim3(256), 0, s, (const float*)q, ml.n, ml, B,
