@@ -795,7 +795,7 @@ static int tc_ensure_smem(size_t smem) {
 int launch_tc_pack(const PeDev& m, void* pack, cudaStream_t st) {
     TcShape s = tc_shape(m.mlp);
     if (!s.ok) { set_error("tcgen05 rollout kernel does not support this model shape"); return MB_EUNSUPPORTED; }
-    dim3 grid(16, (unsigned)m.mlp.ensemble_size, (unsigned)s.L + 1);
+    dim3 grid(48, (unsigned)m.mlp.ensemble_size, (unsigned)s.L + 1);    // ~3 elements per thread: the pack sits on the train step's critical path
     launch_pdl(k_tc_pack, grid, dim3(256), 0, st, m.mlp, s, m.params, reinterpret_cast<uint8_t*>(pack));
     MB_CUDA_LAUNCH_CHECK("k_tc_pack");
     return MB_OK;
