@@ -270,6 +270,15 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
     do {                                                                                  \
         if ((dbg & 8) && blockIdx.x == 0 && (i) < 4 && lane == 0) tl[(i)][(slot)] = clock64(); \
     } while (0)
+#ifdef MB_TC_DEBUG_HOOKS
+    __shared__ long long tlb[8][6];          // per-block phases of one epilogue warp (MB_TC_DEBUG & 32): tile 1, layer 2
+#define TLB(cond, blk, ph)                                                                \
+    do {                                                                                  \
+        if ((dbg & 32) && blockIdx.x == 0 && (cond) && lane == 0) tlb[(blk) & 7][(ph)] = clock64(); \
+    } while (0)
+#else
+#define TLB(cond, blk, ph) do {} while (0)
+#endif
     __shared__ TileIndex tix;
     __shared__ int fwd_total[kMaxMembers];
     const bool direct = fwd.mode != 0;          // rows of every listed member in order, no bucket plan
@@ -401,7 +410,11 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                 // without a block of its own in that round, so the MMA warp polls one barrier per
                 // round instead of one per k-step.
                 auto do_block = [&](int ks, uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
+                    const bool tb = warp == kTcEpiWarp0 && i == 1 && l == 2;
+                    (void)tb;
+                    TLB(tb, ks / kTcClasses, 0);
                     tc_wait_ld();
+                    TLB(tb, ks / kTcClasses, 1);
                     if (ks + kTcClasses < s.nksh) tc_ld16(dcol + (ks + kTcClasses) * 16, nxt);
                     if (kZSave && zl != nullptr) {          // 16 pre-activations of this row (bias included)
                         if ((zw & 3) == 0) {
@@ -438,9 +451,12 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                         unpack2(sub2(a, hf), l0, l1);
                         lo[t] = cvt_bf16x2(l0, l1);
                     }
+                    TLB(tb, ks / kTcClasses, 2);
                     tc_st8(dcol + ks * 16, h);
                     tc_st8(dcol + ks * 16 + 8, lo);
+                    TLB(tb, ks / kTcClasses, 3);
                     tc_wait_st();
+                    TLB(tb, ks / kTcClasses, 4);
                     // The bias column of the next A operand (column H) is rewritten as EXACTLY 1
                     // instead of swish(kSwishOne * previous ones): that constant is only a bf16 hi+lo
                     // pair in the pack (2^-17 relative) and its error grew 1.28x per layer, 6e-5 at
@@ -455,6 +471,7 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_ready(ks / kTcRound));
+                    TLB(tb, ks / kTcClasses, 5);
                 };
                 if (c < s.nksh) tc_ld16(dcol + c * 16, r0);
                 int ks = c;
@@ -773,6 +790,15 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
                    tl[i][24] - t0, tl[i][25] - t0, tl[i][33] - t0, tl[i][34] - t0);
         }
     }
+#ifdef MB_TC_DEBUG_HOOKS
+    if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 0 && n_my > 1) {
+        const long long t0 = tlb[0][0];
+        printf("epilogue warp, tile 1 layer 2, per block: start wait_ld | compute | st issue | wait_st | fence+arrive (cycles)\n");
+        for (int b = 0; b < (s.nksh + kTcClasses - 1) / kTcClasses && b < 8; ++b)
+            printf("  block %d @%6lld: %5lld | %5lld | %5lld | %5lld | %5lld\n", b, tlb[b][0] - t0, tlb[b][1] - tlb[b][0],
+                   tlb[b][2] - tlb[b][1], tlb[b][3] - tlb[b][2], tlb[b][4] - tlb[b][3], tlb[b][5] - tlb[b][4]);
+    }
+#endif
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
