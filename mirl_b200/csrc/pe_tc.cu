@@ -43,9 +43,13 @@
 // [mean | clamped log-std] rows: the all-member forward behind predict_distribution and the MOPO
 // penalised step.
 //
-// MB_TC_DEBUG (timing experiments, numerics wrong for 1/2/4/16): 1 one MMA per k-step, 2 no weight
-// copies, 4 identity instead of swish (the arithmetic still runs), 8 print a clock64 timeline of
-// CTA 0's first tiles, 16 skip the input fence.
+// MB_TC_DEBUG (builds with -DMB_TC_DEBUG_HOOKS only -- as a run-time argument the switches cost a
+// select per activation; timing experiments, numerics wrong for 1/2/4/16): 1 one MMA per k-step,
+// 2 no weight copies, 4 identity instead of swish (the arithmetic still runs), 8 print a clock64
+// timeline of CTA 0's first tiles, 16 skip the input fence, 32 print the phases (load wait,
+// arithmetic, store, store wait, fence + arrive) of one epilogue warp's blocks.  The training
+// instantiation (kZSave) is launched with programmatic dependent launch: its set-up overlaps the
+// weight re-pack that precedes it.
 //
 // mbarrier discipline: a waiter must observe EVERY phase of a barrier it waits on (parity
 // aliasing otherwise), so each consumer group has its own barrier(s): d_full (epilogue warps, all
