@@ -202,7 +202,9 @@ int mb_pe_loss(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs,
  * m->tc_pack, when non-NULL (mb_pe_tc_pack_bytes bytes), is used as SCRATCH: the call re-packs the
  * current weights into it and runs the whole forward as one launch of the tcgen05 tile kernel
  * (pre-activations saved for the backward pass); with NULL the forward is one GEMM launch per
- * layer.  A rollout pack must be rebuilt after training either way (the weights changed). */
+ * layer.  A rollout pack must be rebuilt after training either way (the weights changed).
+ * Without step_counter the step runs as ONE persistent cooperative launch (see mb_pe_train_steps);
+ * MB_TRAIN_FUSED=0 selects the chain of per-layer launches instead. */
 size_t mb_pe_train_workspace_bytes(const mb_pe_model* m, int64_t B);
 int mb_pe_train_step(const mb_pe_model* m, const mb_train_cfg* cfg, float* params,
                      float* exp_avg, float* exp_avg_sq, int64_t step, int32_t* step_counter,
@@ -211,6 +213,25 @@ int mb_pe_train_step(const mb_pe_model* m, const mb_train_cfg* cfg, float* param
                      int member_begin, int member_end,
                      float* ensemble_loss, float* loss_terms,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* `nsteps` consecutive training steps in ONE persistent launch, with the bootstrap batches gathered on
+ * the device (PEModelTrainer.sufficiently_train's inner loop, pe_model_trainer.py:240,268-272):
+ *   dataset tensors obs/act/delta/reward/done are [N][.] rows; index [E][index_stride] (int64) is the
+ *   bootstrap table `ensemble_index` (pe_model_trainer.py:179); step t of the schedule
+ *   (t = first_step + s, s < nsteps) uses k = t mod ceil(train_length / batch_size),
+ *   rows index[e][k*batch_size .. min((k+1)*batch_size, train_length)) for member e -- the reference's
+ *   `for j in range(0, train_length, batch_size)` loop, ragged last batch included.
+ *   index == NULL: the tensors are one per-member batch [E][batch_size][.] (train_length = batch_size).
+ * adam_steps_done = Adam steps already applied to this optimiser state (bias correction continues from
+ * there).  ensemble_loss [nsteps][E] and loss_terms [nsteps][3] receive every step's values (zeroed by
+ * the call).  An empty member slice is a no-op.  Layer widths up to 256. */
+size_t mb_pe_train_steps_workspace_bytes(const mb_pe_model* m, int64_t batch_size);
+int mb_pe_train_steps(const mb_pe_model* m, const mb_train_cfg* cfg, float* params, float* exp_avg,
+                      float* exp_avg_sq, int64_t adam_steps_done, const float* obs, const float* act,
+                      const float* delta, const float* reward, const float* done, const int64_t* index,
+                      int64_t index_stride, int64_t train_length, int64_t batch_size, int64_t first_step,
+                      int nsteps, int member_begin, int member_end, float* ensemble_loss, float* loss_terms,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* gradients only (same maths as the training step, no Adam); grads is a packed blob.
  * Exposed for parity tests of loss.backward(). */

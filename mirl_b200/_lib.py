@@ -69,6 +69,9 @@ SIGNATURES = {
     "mb_pe_train_workspace_bytes": (c_size_t, [POINTER(PeModel), c_int64]),
     "mb_pe_train_step": (c_int, [POINTER(PeModel), POINTER(TrainCfg), P, P, P, c_int64, P, P, P, P,
                                  P, P, c_int64, c_int, c_int, P, P, P, c_size_t, P]),
+    "mb_pe_train_steps_workspace_bytes": (c_size_t, [POINTER(PeModel), c_int64]),
+    "mb_pe_train_steps": (c_int, [POINTER(PeModel), POINTER(TrainCfg), P, P, P, c_int64, P, P, P, P, P, P,
+                                  c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "mb_pe_loss_grads": (c_int, [POINTER(PeModel), POINTER(TrainCfg), P, P, P, P, P, c_int64, P,
                                  P, P, P, c_size_t, P]),
     "mb_critic_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
@@ -142,8 +145,10 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
-def stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None):
+    """The CUDA stream the launches go to: torch's current stream of ``device`` (the tensors'
+    device, not whatever device happens to be current)."""
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def f32(t, device):

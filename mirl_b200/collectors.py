@@ -51,9 +51,16 @@ class B200MBPOCollector(Component):
         self.resize_pool(cur_epoch)
         number_sample = states.shape[0]
         batch_size = self.batch_size or number_sample
+        rank, ws = mbdist.world()
+        sharded = self.shard and ws > 1
         with torch.no_grad():
+            # loop bounds come from the GLOBAL row count: every rank runs the same number of chunks
+            # (the loop body issues collectives when sharded) and takes its row slice of each chunk
             for i in range(0, number_sample, batch_size):
                 o = states[i:i + min(batch_size, number_sample - i)]
+                if sharded:
+                    r0, r1 = mbdist.row_partition(o.shape[0], ws)[rank]
+                    o = o[r0:r1]
                 stop = torch.zeros((o.shape[0], 1), device=o.device)
                 for j in range(depth):
                     a, _ = self.policy.action(o)
@@ -101,15 +108,25 @@ class B200MBPOCollector(Component):
         return n[0].item() == 0 or n[1].item() == n[0].item()
 
     def get_start_states(self):
-        """mbpo_collector.py:56-58; with ``shard`` every rank draws the same global batch (same
-        NumPy stream) and keeps its row slice."""
-        data = self.pool.random_batch_torch(int(self.number_sample), keys=["observations"])
-        states = data["observations"].to(self.model.device)
+        """mbpo_collector.py:56-58.  With ``shard`` rank 0 draws the global batch and broadcasts it:
+        the ranks' NumPy streams drift apart after the first call (each rank draws member indices
+        for its own row count), so "every rank draws the same batch" cannot rely on them."""
         rank, ws = mbdist.world()
+        dev = self.model.device
+        n = int(self.number_sample)
         if self.shard and ws > 1:
-            r0, r1 = mbdist.row_partition(states.shape[0], ws)[rank]
-            states = states[r0:r1]
-        return states
+            shape = [None]
+            if rank == 0:
+                states = self.pool.random_batch_torch(n, keys=["observations"])["observations"].to(dev).float()
+                states = states.contiguous()
+                shape = [tuple(states.shape)]
+            torch.distributed.broadcast_object_list(shape, 0)
+            if rank != 0:
+                states = torch.empty(shape[0], device=dev)
+            torch.distributed.broadcast(states, 0)
+            return states
+        data = self.pool.random_batch_torch(n, keys=["observations"])
+        return data["observations"].to(dev)
 
     def _get_live_ind(self, stop):
         return (stop < 0.5).flatten()
@@ -117,11 +134,12 @@ class B200MBPOCollector(Component):
     def _emit(self, samples):
         """D2H + pool insert (mbpo_collector.py:81-83); all-gather first when sharded."""
         if self.shard and mbdist.world()[1] > 1:
-            packed = torch.cat([samples[k].reshape(samples[k].shape[0], -1) for k in _KEYS], dim=1)
+            widths = {k: int(np.prod(samples[k].shape[1:])) for k in _KEYS}       # also right for 0 rows
+            packed = torch.cat([samples[k].reshape(samples[k].shape[0], widths[k]) for k in _KEYS], dim=1)
             packed = mbdist.all_gather_rows(packed.contiguous())
             out, c = {}, 0
             for k in _KEYS:
-                w = samples[k].reshape(samples[k].shape[0], -1).shape[1]
+                w = widths[k]
                 out[k] = packed[:, c:c + w]
                 c += w
             samples = out

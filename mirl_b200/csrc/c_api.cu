@@ -5,6 +5,9 @@
 #include <cstring>
 #include "pe_kernels.h"
 #include "simt_mlp.cuh"
+#include "train_fused.h"
+#include <math.h>
+#include <stdlib.h>
 
 namespace mb {
 
@@ -277,8 +280,86 @@ int mb_pe_loss(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs, 
                                   done, cfg->ignore_terminal_state, cfg->reward_coef, ensemble_loss, s);
 }
 
+// MB_TRAIN_FUSED=0 keeps the round-1 chain of per-layer launches (A/B timing, gradient-only mode)
+static bool fused_enabled() {
+    static const bool on = [] { const char* v = getenv("MB_TRAIN_FUSED"); return !(v && v[0] == '0'); }();
+    return on;
+}
+
 size_t mb_pe_train_workspace_bytes(const mb_pe_model* m, int64_t B) {
-    return train_workspace_bytes(m->mlp, B < 1 ? 1 : B);
+    const size_t chain = train_workspace_bytes(m->mlp, B < 1 ? 1 : B);
+    const size_t fused = fused_train_supported(m->mlp, 1) ? fused_train_workspace_bytes(m->mlp, B < 1 ? 1 : B) : 0;
+    return chain > fused ? chain : fused;
+}
+
+size_t mb_pe_train_steps_workspace_bytes(const mb_pe_model* m, int64_t batch_size) {
+    if (!m || !fused_train_supported(m->mlp, 1)) return 0;
+    return fused_train_workspace_bytes(m->mlp, batch_size < 1 ? 1 : batch_size);
+}
+
+// common argument block of the fused kernel for a probabilistic-ensemble model
+static void fused_pe_args(FusedArgs& a, const mb_pe_model* m, const mb_train_cfg* cfg, float* params,
+                          float* exp_avg, float* exp_avg_sq, int64_t steps_done, int e0, int e1) {
+    const mb_mlp_desc& d = m->mlp;
+    a.e0 = e0;
+    a.ne = e1 - e0;
+    a.O = m->obs_dim;
+    a.A = m->act_dim;
+    a.D = m->obs_dim + 1;
+    a.head_kind = FUSED_HEAD_NLL;
+    a.E_total = d.ensemble_size;
+    a.maxls_off = logstd_offset(d, 0);
+    a.minls_off = logstd_offset(d, 1);
+    a.norm = m->norm;
+    a.params = params;
+    a.exp_avg = exp_avg;
+    a.exp_avg_sq = exp_avg_sq;
+    a.target_params = nullptr;
+    a.tau = 0.f;
+    a.target = nullptr;
+    a.cfg = *cfg;
+    a.beta1_pow0 = pow((double)cfg->beta1, (double)steps_done);
+    a.beta2_pow0 = pow((double)cfg->beta2, (double)steps_done);
+    for (int l = 0; l < d.num_layers; ++l) a.ly[l].wd = cfg->weight_decay[l];
+}
+
+int mb_pe_train_steps(const mb_pe_model* m, const mb_train_cfg* cfg, float* params, float* exp_avg,
+                      float* exp_avg_sq, int64_t adam_steps_done, const float* obs, const float* act,
+                      const float* delta, const float* reward, const float* done, const int64_t* index,
+                      int64_t index_stride, int64_t train_length, int64_t batch_size, int64_t first_step,
+                      int nsteps, int member_begin, int member_end, float* ensemble_loss, float* loss_terms,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    const char* who = "mb_pe_train_steps";
+    int rc = validate_model(m, who);
+    if (rc) return rc;
+    MB_CHECK_ARG(cfg != nullptr, "%s: null cfg", who);
+    MB_CHECK_ARG(params && exp_avg && exp_avg_sq && params == m->params, "%s: params must be the model's blob", who);
+    MB_CHECK_ARG(nsteps >= 0 && nsteps <= (1 << 20), "%s: nsteps %d out of range", who, nsteps);
+    MB_CHECK_ARG(batch_size >= 1 && batch_size < (int64_t)1 << 20, "%s: batch_size out of range", who);
+    MB_CHECK_ARG(train_length >= 1 && first_step >= 0 && adam_steps_done >= 0, "%s: bad schedule", who);
+    MB_CHECK_ARG(index == nullptr || index_stride >= train_length, "%s: index_stride < train_length", who);
+    MB_CHECK_ARG(0 <= member_begin && member_begin <= member_end && member_end <= m->mlp.ensemble_size,
+                 "%s: member slice [%d,%d) invalid", who, member_begin, member_end);
+    MB_CHECK_ARG(obs && act && delta && reward && ensemble_loss && loss_terms, "%s: null tensor", who);
+    MB_CHECK_ARG(!cfg->ignore_terminal_state || done, "%s: ignore_terminal_state needs done", who);
+    if (nsteps == 0 || member_begin == member_end) return MB_OK;      // an empty member slice is a no-op
+    if (!fused_train_supported(m->mlp, member_end - member_begin)) {
+        set_error("%s: layer widths above 256 are not covered by the fused training kernel", who);
+        return MB_EUNSUPPORTED;
+    }
+    FusedArgs a{};
+    fused_pe_args(a, m, cfg, params, exp_avg, exp_avg_sq, adam_steps_done, member_begin, member_end);
+    a.obs = obs; a.actn = act; a.delta = delta; a.reward = reward; a.done = done;
+    a.index = index;
+    a.index_stride = index_stride;
+    a.per_member_rows = 1;
+    a.nsteps = nsteps;
+    a.first_step = first_step;
+    a.train_length = train_length;
+    a.batch_size = batch_size;
+    a.ensemble_loss = ensemble_loss;
+    a.loss_terms = loss_terms;
+    return launch_train_fused(m->mlp, a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 static int train_common(const char* who, const mb_pe_model* m, const mb_train_cfg* cfg, float* params,
@@ -298,6 +379,23 @@ static int train_common(const char* who, const mb_pe_model* m, const mb_train_cf
     if (workspace == nullptr || workspace_bytes < mb_pe_train_workspace_bytes(m, B)) {
         set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, mb_pe_train_workspace_bytes(m, B));
         return MB_EWORKSPACE;
+    }
+    if (params != nullptr && grads == nullptr && step_counter == nullptr && fused_enabled() &&
+        fused_train_supported(m->mlp, e1 - e0)) {
+        // ONE persistent launch: forward + NLL + backward + Adam (train_fused.cu)
+        FusedArgs a{};
+        fused_pe_args(a, m, cfg, params, exp_avg, exp_avg_sq, step - 1, e0, e1);
+        a.obs = obs; a.actn = act; a.delta = delta; a.reward = reward; a.done = done;
+        a.index = nullptr;
+        a.index_stride = 0;
+        a.per_member_rows = 1;
+        a.nsteps = 1;
+        a.first_step = 0;
+        a.train_length = B;
+        a.batch_size = B;
+        a.ensemble_loss = ensemble_loss;
+        a.loss_terms = loss_terms;
+        return launch_train_fused(m->mlp, a, workspace, workspace_bytes, (cudaStream_t)stream);
     }
     return launch_pe_train(to_dev(m), const_cast<void*>(m->tc_pack), *cfg, params, exp_avg, exp_avg_sq, step, step_counter, obs, act, delta, reward, done,
                            B, e0, e1, grads, ensemble_loss, loss_terms, workspace, (cudaStream_t)stream);

@@ -813,11 +813,14 @@ k_pe_rollout_tc(PeDev m, TcShape s, const uint8_t* __restrict__ pack, const floa
 // share the kernel, and lowering the attribute would make a later launch of a larger shape fail.
 template <bool kZSave>
 static int tc_ensure_smem(size_t smem) {
-    static size_t configured = 0;
-    if (configured < smem) {
+    static size_t configured[64] = {0};          // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = dev < 0 || dev >= 64 ? 0 : dev;
+    if (configured[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(k_pe_rollout_tc<kZSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("k_pe_rollout_tc smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
-        configured = smem;
+        configured[dev] = smem;
     }
     return MB_OK;
 }

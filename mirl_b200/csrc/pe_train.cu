@@ -184,8 +184,9 @@ __global__ void k_train_prep(PeDev m, int e0, int ne, const float* __restrict__ 
     }
     if (gid < ne) ensemble_loss[e0 + gid] = 0.f;
     if (gid < 3) loss_terms[gid] = 0.f;
-    if (gid < 2 * (int64_t)ne * D) {
-        const int which = (int)(gid / (ne * D)), k = (int)(gid % (ne * D));
+    // grid-stride: the grid is sized from ne*B*IN, which is smaller than 2*ne*D for B = 1 with a wide D
+    for (int64_t t = gid; t < 2 * (int64_t)ne * D; t += (int64_t)gridDim.x * blockDim.x) {
+        const int which = (int)(t / (ne * D)), k = (int)(t % (ne * D));
         grads[logstd_offset(m.mlp, which) + (int64_t)e0 * D + k] = 0.f;
     }
 }

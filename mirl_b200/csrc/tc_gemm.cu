@@ -347,11 +347,14 @@ int launch_tc_gemm(const TgBatch& b, cudaStream_t s) {
         gy = ty > gy ? ty : gy;
     }
     const size_t smem = 2 * (2 * (size_t)kTgAPlane + 2 * (size_t)nt_max * kTgKC * 2) + 1024;
-    static size_t configured = 0;
-    if (configured < smem) {
+    static size_t configured[64] = {0};          // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = dev < 0 || dev >= 64 ? 0 : dev;
+    if (configured[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("k_tc_gemm smem %zu: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
-        configured = smem;
+        configured[dev] = smem;
     }
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)(b.nops * b.nmem));
     launch_pdl(k_tc_gemm, grid, dim3(kTgThreads), smem, s, b, nt_max);

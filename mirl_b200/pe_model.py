@@ -386,6 +386,9 @@ class B200PEModel(Component, nn.Module):
         done = torch.empty(B, 1, device=dev)
         info = {}
         if B == 0:
+            if penalty_type is not None:                 # a rank whose rows have all terminated
+                info["penalty"] = torch.empty(0, 1, device=dev)
+                info["penalized_reward"] = torch.empty(0, 1, device=dev)
             return next_obs, reward, done, info
         kind = _lib.DONE_KIND[self.done_kind]
         if not return_distribution and penalty_type is None:

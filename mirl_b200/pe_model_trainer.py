@@ -1,13 +1,17 @@
 """B200PEModelTrainer -- drop-in for ``PEModelTrainer``
 (mirl/agents/mbpo/pe_model_trainer.py:18-306).
 
-``train_from_torch_batch`` is ONE call into the fused CUDA training step (forward + Gaussian
-NLL + log-std bound + L2 + backward + Adam, ``mb_pe_train_step``) instead of ~4 500 ATen ops
-(SURVEY.md 2.1).  ``sufficiently_train`` keeps the reference's control flow (bootstrap indices,
-periodic hold-out evaluation, per-member early stopping, best-snapshot restore, elite ranking)
-and its NumPy RNG consumption order, but keeps the dataset, the bootstrap index table and the
-per-member "best" snapshots in device memory instead of NumPy fancy-indexing + H2D every step
-(:268-270) and ``torch.save`` per improved member (:249,256).
+``train_from_torch_batch`` is ONE persistent kernel launch (forward + Gaussian NLL + log-std
+bound + L2 + backward + Adam, ``mb_pe_train_step`` -> ``train_fused.cu``) instead of ~4 500 ATen
+ops.  ``sufficiently_train`` keeps the reference's control flow (bootstrap
+indices, periodic hold-out evaluation, per-member early stopping, best-snapshot restore, elite
+ranking) and its NumPy RNG consumption order, but keeps the dataset, the bootstrap index table
+and the per-member "best" snapshots in device memory instead of NumPy fancy-indexing + H2D every
+step (:268-270) and ``torch.save`` per improved member (:249,256) -- and runs every block of
+``report_freq`` steps between two evaluations as ONE launch (``mb_pe_train_steps``: the kernel
+gathers each step's bootstrap batch from the index table itself).  With a ``B200ExtraFieldPool``
+``train_with_pool`` never touches host NumPy arrays (the permutation / bootstrap draws still
+come from the global NumPy generator, in the reference's order).
 
 Member-sharded training (``members=(e0, e1)``): members are independent (pe_model.py:95-96), so
 each rank trains its slice with no collective in the step; ``mirl_b200.dist.all_gather_members``
@@ -150,8 +154,12 @@ class B200PEModelTrainer(Component):
         else:
             if self._step_dev is None or self._step_dev.device != dev:
                 self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._scratch_pack()                     # allocated outside the capture
             key = (B, model.module.flat.data_ptr(), model._norm().data_ptr(), self.ignore_terminal_state,
-                   self.lr, self.members)
+                   self.lr, self.members, self.betas, self.eps, tuple(model.weight_decay),
+                   model.reward_coef, model.bound_reg_coef, self.exp_avg.data_ptr(),
+                   self.exp_avg_sq.data_ptr(), self._ws.data_ptr(), self._ensemble_loss.data_ptr(),
+                   self._pack.data_ptr() if self._pack is not None else 0)
             if self._graph is None or self._graph[0] != key:
                 static = {k: torch.empty_like(v) for k, v in t.items()}
                 self._step_dev.fill_(self.num_train_steps - 1)
@@ -169,6 +177,47 @@ class B200PEModelTrainer(Component):
             g.replay()
         model.module.mark_weights_changed()
         return self._ensemble_loss, self._loss_terms
+
+    def fused_steps_supported(self):
+        L = _lib.lib()
+        m = self.model._c_model(None)
+        return L.mb_pe_train_steps_workspace_bytes(ctypes.byref(m), 1) > 0
+
+    def train_steps_async(self, data, index, train_length, batch_size, first_step, nsteps):
+        """``nsteps`` consecutive training steps of the epoch schedule in ONE persistent launch
+        (pe_model_trainer.py:240,268-272 for steps ``first_step .. first_step + nsteps - 1``): ``data``
+        holds the device dataset tensors ``[N,.]``, ``index`` the bootstrap table ``[E,train_length]``
+        (int64, device).  Returns ``(ensemble_loss [nsteps,E], loss_terms [nsteps,3])`` device
+        tensors, no synchronisation."""
+        model, L = self.model, _lib.lib()
+        dev = model.device
+        self._state_to(dev)
+        e0, e1 = self.members
+        E = model.ensemble_size
+        el = torch.zeros(max(nsteps, 1), E, device=dev)
+        terms = torch.zeros(max(nsteps, 1), 3, device=dev)
+        if nsteps == 0 or e0 == e1:
+            return el, terms
+        with torch.cuda.device(dev):
+            m = model._c_model(None)
+            need = L.mb_pe_train_steps_workspace_bytes(ctypes.byref(m), batch_size)
+            if need == 0:
+                raise RuntimeError("the fused training kernel does not cover this model shape")
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                self._graph = None
+            cfg = model.train_cfg(self.ignore_terminal_state, self.lr, self.betas, self.eps)
+            assert index.dtype == torch.int64 and index.is_contiguous() and index.shape[0] == E
+            _lib.check(L.mb_pe_train_steps(
+                ctypes.byref(m), ctypes.byref(cfg), _lib.ptr(model.module.flat.data), _lib.ptr(self.exp_avg),
+                _lib.ptr(self.exp_avg_sq), self.num_train_steps, _lib.ptr(data["observations"]),
+                _lib.ptr(data["actions"]), _lib.ptr(data["deltas"]), _lib.ptr(data["rewards"]),
+                _lib.ptr(data["terminals"]), _lib.ptr(index), index.shape[1], train_length, batch_size,
+                first_step, nsteps, e0, e1, _lib.ptr(el), _lib.ptr(terms), _lib.ptr(self._ws),
+                self._ws.numel(), _lib.stream(dev)))
+        self.num_train_steps += nsteps
+        model.module.mark_weights_changed()
+        return el, terms
 
     def train_from_torch_batch(self, batch):
         """pe_model_trainer.py:85-106 (same diagnostics keys; synchronises like the reference)."""
@@ -213,7 +262,8 @@ class B200PEModelTrainer(Component):
     def train_with_pool(self, pool):
         """pe_model_trainer.py:138-170."""
         max_step = self.max_step_per_train
-        temp = pool.get_unprocessed_data("compute_delta", ["observations", "next_observations"])
+        getter = getattr(pool, "get_unprocessed_data_torch", pool.get_unprocessed_data)     # device pool
+        temp = getter("compute_delta", ["observations", "next_observations"])
         deltas = temp["next_observations"] - temp["observations"]
         pool.update_single_extra_field("deltas", deltas)
         pool.update_process_flag("compute_delta", len(deltas))
@@ -235,9 +285,21 @@ class B200PEModelTrainer(Component):
     def split_dataset(self, pool, valid_ratio, max_valid, resample):
         """pe_model_trainer.py:172-182 (permutation, then the bootstrap index table)."""
         E = self.model.ensemble_size
-        dataset = pool.get_data()
-        (self.train_dataset, self.eval_dataset,
-         self.train_length, self.eval_length) = split_dataset(dataset, valid_ratio, max_valid)
+        if hasattr(pool, "get_data_torch"):
+            # device-resident pool: same permutation draw (pools/utils.py:69), applied on the device
+            dataset = pool.get_data_torch()
+            n_sample = len(next(iter(dataset.values())))
+            valid_length = int(np.ceil(min(max_valid, valid_ratio * n_sample)))
+            train_length = n_sample - valid_length
+            indices = torch.from_numpy(np.random.permutation(n_sample)).to(self.model.device)
+            tr_i, va_i = indices[:train_length], indices[n_sample - valid_length:]
+            self.train_dataset = {k: v.index_select(0, tr_i) for k, v in dataset.items()}
+            self.eval_dataset = {k: v.index_select(0, va_i) for k, v in dataset.items()}
+            self.train_length, self.eval_length = train_length, valid_length
+        else:
+            dataset = pool.get_data()
+            (self.train_dataset, self.eval_dataset,
+             self.train_length, self.eval_length) = split_dataset(dataset, valid_ratio, max_valid)
         if resample:
             self.ensemble_index = np.random.randint(self.train_length, size=(E, self.train_length))
         else:
@@ -274,7 +336,19 @@ class B200PEModelTrainer(Component):
     def sufficiently_train(self, pool=None, max_step=2000, valid_ratio=0.2, max_valid=5000,
                            resample=True, batch_size=256, report_freq=100, max_not_improve=20,
                            load_best=True, silent=False, load_dataset_dir=None):
-        """pe_model_trainer.py:212-293."""
+        """pe_model_trainer.py:212-293.  Same schedule as the reference's ``while True: for j in
+        range(0, train_length, batch_size)`` loop -- step ``t`` trains on bootstrap columns
+        ``[k*batch_size, (k+1)*batch_size)`` with ``k = t mod ceil(train_length / batch_size)`` and the
+        hold-out evaluation runs whenever ``t % report_freq == 0`` -- but the steps between two
+        evaluations go out as ONE persistent launch.
+
+        Member-sharded (``members`` a strict slice, ``torch.distributed`` initialised): every rank
+        draws the same split / bootstrap table (same NumPy stream), trains its own members and stops
+        on its own members' counters (no collective inside the loop); afterwards the trained slices
+        are all-gathered so that the final evaluation, ``remember_loss`` and therefore
+        ``elite_indices`` are identical on every rank.  An empty slice (E=7 over 8 ranks) trains
+        nothing and still takes part in the exchange."""
+        from . import dist as mbdist
         model = self.model
         dev = model.device
         if pool is not None:
@@ -283,52 +357,61 @@ class B200PEModelTrainer(Component):
             assert load_dataset_dir is not None
             self.load_dataset(load_dataset_dir)
             self.set_mean_std()
-        train = {k: torch.as_tensor(np.asarray(v), device=dev).float()
-                 for k, v in self.train_dataset.items() if k in _FIELDS}
-        evald = {k: torch.as_tensor(np.asarray(v), device=dev).float()
-                 for k, v in self.eval_dataset.items() if k in _FIELDS}
-        index = torch.as_tensor(self.ensemble_index, device=dev)
+
+        def _dev(v):
+            return (v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))).to(dev).float().contiguous()
+        train = {k: _dev(v) for k, v in self.train_dataset.items() if k in _FIELDS}
+        evald = {k: _dev(v) for k, v in self.eval_dataset.items() if k in _FIELDS}
+        index = torch.as_tensor(self.ensemble_index).to(device=dev, dtype=torch.int64).contiguous()
         train_length = self.train_length
         e0, e1 = self.members
+        fused = self.fused_steps_supported() and not self.use_cuda_graph
         total_train_step = 0
         eval_stat, eval_loss, last = OrderedDict(), None, None
         continue_training = True
-        while True:
-            for j in range(0, train_length, batch_size):
-                if total_train_step % report_freq == 0:
-                    eval_stat, eval_loss = self.eval_with_dataset(evald)
-                    if total_train_step == 0:
-                        min_loss = eval_loss
-                        not_improve = []
-                        for i, _ in enumerate(eval_loss):
+        while e1 > e0:
+            if total_train_step % report_freq == 0:
+                eval_stat, eval_loss = self.eval_with_dataset(evald)
+                if total_train_step == 0:
+                    min_loss = eval_loss
+                    not_improve = []
+                    for i, _ in enumerate(eval_loss):
+                        self._snapshot_member(i)
+                        not_improve.append(0)
+                else:
+                    for i, l in enumerate(eval_loss):
+                        if l < min_loss[i]:
+                            min_loss[i] = l
+                            not_improve[i] = 0
                             self._snapshot_member(i)
-                            not_improve.append(0)
-                    else:
-                        for i, l in enumerate(eval_loss):
-                            if l < min_loss[i]:
-                                min_loss[i] = l
-                                not_improve[i] = 0
-                                self._snapshot_member(i)
-                            else:
-                                not_improve[i] += 1
-                    continue_training = False
-                    for i, n in enumerate(not_improve):
-                        eval_stat["mt/net_%d/not_improve" % i] = n
-                        if e0 <= i < e1 and (max_not_improve < 0 or n < max_not_improve):
-                            continue_training = True
-                if total_train_step >= max_step:
-                    continue_training = False
-                if not continue_training:
-                    break
-                ind = index[:, j:j + batch_size]
-                batch = {k: v[ind] for k, v in train.items()}
-                last = self.train_step_async(batch)
-                total_train_step += 1
+                        else:
+                            not_improve[i] += 1
+                continue_training = False
+                for i, n in enumerate(not_improve):
+                    eval_stat["mt/net_%d/not_improve" % i] = n
+                    if e0 <= i < e1 and (max_not_improve < 0 or n < max_not_improve):
+                        continue_training = True
+            if total_train_step >= max_step:
+                continue_training = False
             if not continue_training:
                 break
-        if load_best:
+            # steps until the next evaluation (or the step budget): one launch
+            n = min(report_freq - total_train_step % report_freq, int(max_step) - total_train_step)
+            if fused:
+                el, terms = self.train_steps_async(train, index, train_length, batch_size, total_train_step, n)
+                last = (el[n - 1], terms[n - 1])
+            else:
+                spe = (train_length + batch_size - 1) // batch_size
+                for t in range(total_train_step, total_train_step + n):
+                    j = (t % spe) * batch_size
+                    ind = index[:, j:j + batch_size]
+                    last = self.train_step_async({k: v[ind] for k, v in train.items()})
+            total_train_step += n
+        if load_best and e1 > e0 and self._best is not None:
             for i in range(e0, e1):
                 self._restore_member(i)
+        if (e0, e1) != (0, model.ensemble_size) and mbdist.world()[1] > 1:
+            mbdist.all_gather_members(model.module)          # every rank now holds every trained member
         eval_stat, eval_loss = self.eval_with_dataset(evald)
         model.remember_loss(eval_loss)
         if last is not None:

@@ -125,3 +125,70 @@ def pool_samples(seed, n, obs=OBS, act=ACT):
         "rewards": rs.standard_normal((n, 1)).astype(np.float32),
         "terminals": (rs.uniform(size=(n, 1)) < 0.1).astype(np.float32),
     }
+
+
+# ---- learnable synthetic dynamics (train-loop / ExtraFieldPool / collector fixtures) -------------
+def dyn_samples(seed, n, obs=OBS, act=ACT, env="cheetah"):
+    """Transitions of a fixed smooth synthetic system (so that model training has something to
+    learn and the early-stopping counters move): delta = 0.1 tanh(o A + a B) + noise."""
+    rs = np.random.RandomState(seed)
+    ms = np.random.RandomState(4242)
+    Aw = (0.6 * ms.standard_normal((obs, obs)) / np.sqrt(obs)).astype(np.float32)
+    Bw = (0.5 * ms.standard_normal((act, obs))).astype(np.float32)
+    rw = (ms.standard_normal(obs + act) / 3.0).astype(np.float32)
+    o, a = rollout_inputs(seed + 1, n, obs, act, env)
+    delta = (0.1 * np.tanh(o @ Aw + a @ Bw) + 0.02 * rs.standard_normal((n, obs))).astype(np.float32)
+    r = (np.tanh(np.concatenate([o, a], 1) @ rw) + 0.05 * rs.standard_normal(n)).astype(np.float32)
+    return {
+        "observations": o, "actions": a, "next_observations": (o + delta).astype(np.float32),
+        "rewards": r[:, None].astype(np.float32),
+        "terminals": (rs.uniform(size=(n, 1)) < 0.05).astype(np.float32),
+    }
+
+
+# PEModelTrainer.train_with_pool fixture (tests/golden/pe_trainloop_*.npz): two pool fills, two calls
+TRAINLOOP = {
+    "mbpo": dict(cfg=MBPO, seed=11, adds=[(7001, 1200), (7002, 500)], batch_size=256, report_freq=8,
+                 max_not_improve=2, init_model_train_step=48, max_step_per_train=40, max_valid=300, lr=1e-3,
+                 rng_seed=80),
+    # a large step size makes the hold-out loss non-monotonic: non-improvements, per-member early
+    # stopping and the restore of an EARLIER best snapshot are all exercised
+    "small": dict(cfg=SMALL, seed=51, adds=[(7101, 300), (7102, 200)], batch_size=32, report_freq=10,
+                  max_not_improve=2, init_model_train_step=300, max_step_per_train=60, max_valid=100,
+                  lr=0.1, rng_seed=76),
+}
+
+
+class TanhPolicy:
+    """Stand-in for ``GaussianPolicy.action`` in the collector fixtures: fixed weights,
+    ``a = tanh(obs M + 0.3 eps)`` with ``eps [B,A]`` drawn from the global torch generator -- the
+    same place in the RNG consumption order as the reference policy's draw (mbpo_collector.py:48,
+    gaussian.py:199-204).  ``noise_source(B, A)`` replays recorded draws instead."""
+
+    def __init__(self, seed, obs=OBS, act=ACT, noise_source=None):
+        import torch
+        self.M = torch.from_numpy((np.random.RandomState(seed).standard_normal((obs, act)) /
+                                   np.sqrt(obs)).astype(np.float32))
+        self.act = act
+        self.noise_source = noise_source
+        self.drawn = []
+
+    def action(self, obs, **kwargs):
+        import torch
+        B = obs.shape[0]
+        if self.noise_source is not None:
+            eps = self.noise_source(B, self.act).to(obs.device)
+        else:
+            eps = torch.randn(B, self.act, device=obs.device)
+            self.drawn.append(eps.cpu().numpy().copy())
+        return torch.tanh(obs @ self.M.to(obs.device) + 0.3 * eps), {}
+
+
+# MBPOCollector / MOPOCollector fixtures (tests/golden/collector_*.npz)
+COLLECT = {
+    "mbpo": dict(cfg=MBPO, mseed=11, env="hopper", pool_seed=8001, pool_n=1500, number_sample=600,
+                 batch_size=400, depth=5, save_n=2, loss=[0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4]),
+    "mopo": dict(cfg=MOPO, mseed=31, env="hopper", pool_seed=8002, pool_n=800, number_sample=300,
+                 batch_size=200, depth=3, save_n=2, penalty_coef=0.7, penalty_type="total_var",
+                 loss=[0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4, 0.05, 0.8, 0.6]),
+}

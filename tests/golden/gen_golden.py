@@ -171,7 +171,11 @@ def gen_train():
     from mirl.utils.logger import logger
     tmp = tempfile.mkdtemp()
     logger.set_snapshot_dir(tmp)
-    for tag, cfg, seed, B, steps in (("mbpo", cases.MBPO, 11, 256, 10), ("small", cases.SMALL, 51, 64, 10)):
+    only100 = os.environ.get("GOLDEN_TRAIN_ONLY100")
+    for tag, cfg, seed, B, steps in (("mbpo", cases.MBPO, 11, 256, 10), ("small", cases.SMALL, 51, 64, 10),
+                                     ("mbpo100", cases.MBPO, 11, 256, 100)):
+        if only100 and steps != 100:
+            continue
         m, _ = build_pe(cfg, seed)
         tr = PEModelTrainer(ref_shim.FakeEnv(), m, lr=1e-3, tb_log_freq=-1, silent=True,
                             ignore_terminal_state=False)
@@ -188,7 +192,7 @@ def gen_train():
                 out["m_proj_%d" % (s + 1)] = np.stack([proj(st[p]["exp_avg"], 3000 + i) for i, (_, p) in enumerate(nt)])
                 out["v_proj_%d" % (s + 1)] = np.stack([proj(st[p]["exp_avg_sq"], 4000 + i) for i, (_, p) in enumerate(nt)])
                 if tag == "small":
-                    for n, p in nt:
+                    for n, p in nt:  # full tensors only for the small config
                         out["param_%d/%s" % (s + 1, n)] = p.detach().numpy().copy()
         out["loss"] = np.array(out["loss"], dtype=np.float64)
         out["ensemble_loss"] = np.array(out["ensemble_loss"], dtype=np.float64)
@@ -289,6 +293,170 @@ def gen_pool():
     np.savez(os.path.join(HERE, "pool.npz"), **out)
 
 
+def gen_trainloop():
+    """PEModelTrainer.train_with_pool (pe_model_trainer.py:138-293) on a synthetic ExtraFieldPool:
+    two fills, two calls (init_model_train_step, then max_step_per_train).  Records the eval-loss
+    trajectory at every report point, the not_improve counters, the train-loss curve, the step
+    counts, the normaliser statistics the pool produced and the final ranking / parameters."""
+    from mirl.agents.mbpo.pe_model_trainer import PEModelTrainer
+    from mirl.pools.extra_field_pool import ExtraFieldPool
+    from mirl.utils.logger import logger
+    tmp = tempfile.mkdtemp()
+    logger.set_snapshot_dir(tmp)
+    for tag, c in cases.TRAINLOOP.items():
+        cfg = c["cfg"]
+        m, _ = build_pe(cfg, c["seed"])
+        env = ref_shim.FakeEnv()
+        pool = ExtraFieldPool(env, max_size=5000, compute_mean_std=True)
+        pool.add_extra_fields({"deltas": {"shape": (cases.OBS,), "type": np.float32}})
+        tr = PEModelTrainer(env, m, lr=c["lr"], tb_log_freq=-1, silent=True, ignore_terminal_state=False,
+                            batch_size=c["batch_size"], report_freq=c["report_freq"],
+                            max_not_improve=c["max_not_improve"], max_valid=c["max_valid"],
+                            init_model_train_step=c["init_model_train_step"],
+                            max_step_per_train=c["max_step_per_train"])
+        rec = {"eval": [], "train": []}
+        ev0, tr0 = tr.eval_with_dataset, tr.train_from_torch_batch
+
+        def ev(ds, _f=ev0):
+            st, el = _f(ds)
+            rec["eval"].append(np.array(el, dtype=np.float64))
+            return st, el
+
+        def trn(bt, _f=tr0):
+            d = _f(bt)
+            rec["train"].append(np.array([d["mt/net_%d/train_loss" % i] for i in range(cfg["E"])] +
+                                         [d["train_loss"]], dtype=np.float64))
+            return d
+        tr.eval_with_dataset, tr.train_from_torch_batch = ev, trn
+        out = {}
+        np.random.seed(c["rng_seed"]); torch.manual_seed(c["rng_seed"])
+        for call, (seed, n) in enumerate(c["adds"]):
+            pool.add_samples(cases.dyn_samples(seed, n))
+            rec["eval"], rec["train"] = [], []
+            stats = tr.train_with_pool(pool)
+            pre = "c%d_" % call
+            out[pre + "eval"] = np.stack(rec["eval"])
+            out[pre + "train"] = np.stack(rec["train"])
+            out[pre + "train_step"] = np.array(stats["train_step"])
+            out[pre + "min_loss"] = np.array(tr.min_loss, dtype=np.float64)
+            out[pre + "elite_indices"] = np.asarray(m.elite_indices, dtype=np.int64)
+            out[pre + "rank"] = np.asarray(m.rank, dtype=np.int64)
+            out[pre + "lengths"] = np.array([tr.train_length, tr.eval_length])
+            out[pre + "index_proj"] = proj(T(tr.ensemble_index.astype(np.float64)), 5)
+            for k, (mu, sd) in tr.mean_std_dict.items():
+                out[pre + "mean_" + k], out[pre + "std_" + k] = np.asarray(mu), np.asarray(sd)
+            nt = named_trainables(m)
+            out[pre + "param_proj"] = np.stack([proj(p, 2000 + i) for i, (_, p) in enumerate(nt)])
+            # how decisive every early-stopping comparison was (a fixture with near-ties would make
+            # the trajectory depend on rounding): min |l - min_loss| / |l| over all decisions
+            ev_arr = out[pre + "eval"][:-1]
+            best = ev_arr[0].copy(); margin = np.inf
+            for row in ev_arr[1:]:
+                margin = min(margin, np.min(np.abs(row - best) / np.abs(row)))
+                best = np.minimum(best, row)
+            out[pre + "decision_margin"] = np.array(margin)
+            print(tag, "call", call, "steps", stats["train_step"], "evals", len(rec["eval"]),
+                  "margin %.2e" % margin,
+                  "elites", m.elite_indices)
+        out["names"] = np.array([n for n, _ in named_trainables(m)])
+        np.savez(os.path.join(HERE, "pe_trainloop_%s.npz" % tag), **out)
+
+
+def _margin(no, env):
+    """Distance of every next_obs row to the nearest done threshold (hopper)."""
+    assert env == "hopper"
+    return np.minimum(np.abs(no[:, 0] - 0.7), np.abs(np.abs(no[:, 1]) - 0.2)).min()
+
+
+def gen_collect():
+    """MBPOCollector.imagine / MOPOCollector.imagine (mbpo_collector.py:34-97, mopo_collector.py:29-68)
+    into a SimplePool: pool contents row for row.  The policy is tests.golden.cases.TanhPolicy (the
+    reference GaussianPolicy is not on the path under test); its draws and the model's draws are
+    recorded in consumption order."""
+    from mirl.agents.mbpo.mbpo_collector import MBPOCollector
+    from mirl.agents.mbpo.mopo_collector import MOPOCollector
+    from mirl.pools.simple_pool import SimplePool
+    from mirl.utils.logger import logger
+    if hasattr(logger, "set_log_level"):
+        logger.set_log_level(logger.ERROR)
+    for tag, c in cases.COLLECT.items():
+        best = None
+        for rng_seed in range(100, 160):
+            m, _ = build_pe(c["cfg"], c["mseed"], c["env"])
+            m.remember_loss(c["loss"])
+            env = ref_shim.FakeEnv(c["env"])
+            pool = SimplePool(env, max_size=c["pool_n"] + 10)
+            pool.add_samples(cases.dyn_samples(c["pool_seed"], c["pool_n"], env=c["env"]))
+            imag = SimplePool(env, max_size=10)
+            pol = cases.TanhPolicy(c["mseed"] + 5)
+            kw = dict(depth_schedule=c["depth"], number_sample=c["number_sample"], save_n=c["save_n"],
+                      bathch_size=c["batch_size"])
+            if tag == "mopo":
+                col = MOPOCollector(m, pol, pool, imag, penalty_coef=c["penalty_coef"],
+                                    penalty_type=c["penalty_type"], **kw)
+            else:
+                col = MBPOCollector(m, pol, pool, imag, **kw)
+            noise = []
+            import mirl.agents.mbpo.pe_model as pem
+            real_randn_like = torch.randn_like
+
+            def rec_randn_like(t, *a, **k):
+                e = real_randn_like(t, *a, **k)
+                noise.append(e.numpy().copy())
+                return e
+            np.random.seed(rng_seed); torch.manual_seed(rng_seed)
+            torch.randn_like = rec_randn_like
+            try:
+                col.imagine(0)
+            finally:
+                torch.randn_like = real_randn_like
+            data = imag.get_data()
+            mg = _margin(data["next_observations"], c["env"])
+            if best is None or mg > best[0]:
+                best = (mg, rng_seed, data, noise, pol.drawn, imag.max_size, imag.get_size())
+            if mg > 1e-4:
+                break
+        mg, rng_seed, data, noise, pdraws, max_size, size = best
+        print(tag, "seed", rng_seed, "rows", size, "margin %.2e" % mg, "steps", len(noise),
+              "done ratio %.3f" % data["terminals"].mean())
+        out = {"rng_seed": np.array(rng_seed), "margin": np.array(mg), "size": np.array([size, max_size]),
+               "n_calls": np.array(len(noise)),
+               "model_noise": np.concatenate(noise, 0), "policy_noise": np.concatenate(pdraws, 0),
+               "call_rows": np.array([len(x) for x in noise])}
+        for k, v in data.items():
+            out["data_" + k] = v
+        np.savez(os.path.join(HERE, "collector_%s.npz" % tag), **out)
+
+
+def gen_extrapool():
+    """ExtraFieldPool (extra_field_pool.py:19-71, flag_pool.py, utils/mean_std.py:12-33): running
+    fp64 mean/std over three fills, the 'deltas' extra field, the compute_delta flag protocol of
+    train_with_pool (pe_model_trainer.py:140-144), get_data order after a wrap, random batches."""
+    from mirl.pools.extra_field_pool import ExtraFieldPool
+    env = ref_shim.FakeEnv()
+    pool = ExtraFieldPool(env, max_size=1000, compute_mean_std=True)
+    pool.add_extra_fields({"deltas": {"shape": (cases.OBS,), "type": np.float32}})
+    out = {}
+    np.random.seed(93)
+    for i, n in enumerate([400, 350, 500]):          # the third fill wraps
+        pool.add_samples(cases.dyn_samples(9300 + i, n))
+        tmp = pool.get_unprocessed_data("compute_delta", ["observations", "next_observations"])
+        deltas = tmp["next_observations"] - tmp["observations"]
+        out["unprocessed_%d" % i] = np.array(len(deltas))
+        pool.update_single_extra_field("deltas", deltas)
+        pool.update_process_flag("compute_delta", len(deltas))
+        ms = pool.get_mean_std()
+        for k, (mu, sd) in ms.items():
+            out["mean_%d_%s" % (i, k)], out["std_%d_%s" % (i, k)] = np.asarray(mu), np.asarray(sd)
+        b = pool.random_batch(32)
+        for k, v in b.items():
+            out["batch_%d_%s" % (i, k)] = v
+        out["size_%d" % i] = np.array([pool.get_size(), pool._stop])
+    for k, v in pool.get_data().items():
+        out["data_" + k] = proj(T(v), 9)
+    np.savez(os.path.join(HERE, "extra_pool.npz"), **out)
+
+
 def main():
     ref_shim.install()
     torch.set_num_threads(1)        # bitwise-stable reductions for the fixtures
@@ -297,6 +465,7 @@ def main():
         globals()["gen_" + only]()
     else:
         gen_forward(); gen_step(); gen_dist(); gen_loss(); gen_train(); gen_critics(); gen_keys(); gen_pool()
+        gen_trainloop(); gen_collect(); gen_extrapool()
     for f in sorted(os.listdir(HERE)):
         if f.endswith((".npz", ".json")):
             print("%8d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))

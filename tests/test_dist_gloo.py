@@ -121,3 +121,48 @@ def test_collector_matches_reference_loop_semantics():
     got = sum(len(r["observations"]) for r in im.rows)
     assert got == exp_rows
     assert set(im.rows[0].keys()) == {"observations", "actions", "next_observations", "rewards", "terminals"}
+
+
+def _collector_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mirl_b200.collectors import B200MBPOCollector
+        np.random.seed(100 + rank)                  # the ranks' NumPy streams are NOT in step
+        pool, im = _Pool(), _Pool()
+        # 65 rows in chunks of 32: chunks of 32, 32 and 1 rows -- the last chunk leaves rank 1 with no
+        # rows at all, and the per-rank row counts straddle the chunk size
+        c = B200MBPOCollector(_Model(), _Policy(), pool, im, depth_schedule=5, number_sample=65, bathch_size=32,
+                              shard=True)
+        c.imagine(0)
+        got = sum(len(r["observations"]) for r in im.rows)
+        first = np.concatenate([r["observations"] for r in im.rows])
+        q.put((rank, got, float(first.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_collector_same_pool_on_every_rank_world2():
+    """Row-sharded imagine(): loop bounds come from the global row count (every rank issues the same
+    collectives even when a chunk leaves it without rows), rank 0's start-state draw is broadcast, and
+    the all-gathered pool is the single-process pool on every rank."""
+    from mirl_b200.collectors import B200MBPOCollector
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_collector_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pool, im = _Pool(), _Pool()
+    c = B200MBPOCollector(_Model(), _Policy(), pool, im, depth_schedule=5, number_sample=65, bathch_size=32)
+    c.imagine(0)
+    want = sum(len(r["observations"]) for r in im.rows)
+    want_sum = float(np.concatenate([r["observations"] for r in im.rows]).sum())
+    for _, got, s in res:
+        assert got == want
+        assert abs(s - want_sum) < 1e-3 * abs(want_sum)

@@ -1,0 +1,391 @@
+"""Round-2 GPU parity tests (through the C ABI): the persistent fused training kernel, the training loop
+against the reference's ``train_with_pool`` fixture, the collectors against the reference collectors'
+pool contents, the device ``ExtraFieldPool``, tcgen05 at every ensemble size, and an oracle comparison
+at 1e5 rows."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pe_oracle as po
+from tests.golden import cases
+from tests.helpers_gpu import FakeEnv, done_guard_mismatches, make_pe_model
+from tests.util import RTOL, T, assert_close, golden, norm_rel, proj, to_torch
+
+pytestmark = pytest.mark.gpu
+LOSS_VEC7 = [0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4]
+
+
+def _batch(seed, E, B, device="cuda"):
+    return {k: T(v, device) for k, v in cases.train_batch(seed, E, B).items()}
+
+
+def _trainer(m, **kw):
+    import mirl_b200
+    kw.setdefault("lr", 1e-3)
+    return mirl_b200.B200PEModelTrainer(FakeEnv(), m, tb_log_freq=-1, silent=True, **kw)
+
+
+# ---- fused persistent training kernel ------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 5, 16, 100, 256, 257, 600])
+def test_fused_train_step_matches_oracle_ragged(B):
+    """One step of the persistent kernel (train_fused.cu) against the CPU oracle: loss, per-member
+    loss, parameters and both Adam moments -- batches that are not multiples of the 16-row block or
+    of the 64-row chunk, and more row blocks than CTAs per member (B = 600)."""
+    m, p = make_pe_model(cases.MBPO, 11)
+    tr = _trainer(m, ignore_terminal_state=(B % 2 == 1))
+    bt = _batch(900 + B, 7, B)
+    diag = tr.train_from_torch_batch(bt)
+    pt = to_torch(p)
+    opt = po.new_adam_state(pt)
+    loss, el = po.train_step(pt, opt, {k: v.cpu() for k, v in bt.items()},
+                             ignore_terminal_state=(B % 2 == 1))
+    assert_close(np.array(diag["train_loss"]), loss.numpy(), what="loss")
+    assert_close(np.array([diag["mt/net_%d/train_loss" % i] for i in range(7)]), el.numpy(), what="ensemble_loss")
+    sd = m.module.reference_state_dict("module.")
+    msd = m.module.reference_state_dict("module.", flat=tr.exp_avg)
+    pn = {}
+    for k, v in pt.items():                                   # oracle parameters after its own step
+        pn[k] = [t.numpy() for t in v] if isinstance(v, list) else (v.numpy() if torch.is_tensor(v) else v)
+    ref = cases.pe_state_dict(pn)
+    worst = 0.0
+    for k, v in sd.items():
+        # first Adam step is lr * g/(|g| + eps): sign-like, so tiny gradients may flip -- compare the
+        # update through the first moment (the gradient itself) instead of element-wise parameters
+        worst = max(worst, float(np.abs(v.cpu().numpy() - ref[k]).max()))
+    assert worst <= 2.0e-3 + 1e-9, worst                      # |update| <= lr per element, both sides
+    # exp_avg after one step = 0.1 * grad: norm-wise 1e-3 against the oracle's analytic gradients
+    g = po.model_loss_grads(to_torch(p), *[bt[k].cpu() for k in ("observations", "actions", "deltas", "rewards",
+                                                                 "terminals")],
+                            ignore_terminal_state=(B % 2 == 1))
+    for l in range(5):
+        for e in range(7):
+            got = msd["module.net.%d.weight_net%d" % (2 * l, e)].cpu().numpy() / 0.1
+            assert norm_rel(got, g["W"][l][e].numpy()) < 1e-3, ("dW", l, e)
+            gb = msd["module.net.%d.bias_net%d" % (2 * l, e)].cpu().numpy() / 0.1
+            assert norm_rel(gb, g["b"][l][e].numpy()) < 1e-3, ("db", l, e)
+    for e in range(7):
+        assert norm_rel(msd["module.maxlogstd_net%d" % e].cpu().numpy() / 0.1, g["max_logstd"][e].numpy()) < 1e-3
+        assert norm_rel(msd["module.minlogstd_net%d" % e].cpu().numpy() / 0.1, g["min_logstd"][e].numpy()) < 1e-3
+
+
+def test_fused_train_100_steps_match_reference_adam():
+    """A hundred fused steps against the reference's PEModelTrainer run (loss curve, parameter and
+    moment checksums at step 100)."""
+    g = golden("pe_train_mbpo100.npz")
+    m, _ = make_pe_model(cases.MBPO, 11)
+    tr = _trainer(m, ignore_terminal_state=False)
+    for s in range(100):
+        el, terms = tr.train_step_async(_batch(600 + s, 7, 256))
+        if s % 10 == 9 or s < 3:
+            assert_close(terms.sum().cpu().numpy(), g["loss"][s], what="loss step %d" % s)
+            assert_close(el.cpu().numpy(), g["ensemble_loss"][s], what="ensemble_loss step %d" % s)
+    sd = m.state_dict()
+    msd = m.module.reference_state_dict("module.", flat=tr.exp_avg)
+    vsd = m.module.reference_state_dict("module.", flat=tr.exp_avg_sq)
+    for i, name in enumerate(g["names"]):
+        name = str(name)
+        got, ref = proj(sd[name], 2000 + i), g["param_proj_100"][i]
+        tol = 1e-3 * 100 * 0.02 * np.sqrt(sd[name].numel()) + 1e-4 * ref[0]
+        assert abs(got[0] - ref[0]) <= tol, (name, got, ref)
+        gm, rm = proj(msd[name], 3000 + i), g["m_proj_100"][i]
+        assert abs(gm[0] - rm[0]) <= 5e-3 * rm[0] + 1e-9, ("exp_avg", name, gm, rm)
+        gv, rv = proj(vsd[name], 4000 + i), g["v_proj_100"][i]
+        assert abs(gv[0] - rv[0]) <= 5e-3 * rv[0] + 1e-12, ("exp_avg_sq", name, gv, rv)
+
+
+def test_multi_step_launch_equals_single_step_launches():
+    """mb_pe_train_steps (bootstrap batches gathered on the device from the index table, ragged last
+    batch, epoch wrap-around) is bit-identical to one launch per step on host-gathered batches."""
+    cfg = cases.MBPO
+    N, bs, nsteps = 700, 256, 7                     # 3 steps per epoch: 256, 256, 188
+    data = {k: T(v, "cuda") for k, v in cases.train_batch(77, 1, N, shared=True).items()}
+    rs = np.random.RandomState(5)
+    index = torch.from_numpy(rs.randint(N, size=(cfg["E"], N))).cuda()
+    ma, _ = make_pe_model(cfg, 11)
+    mb_, _ = make_pe_model(cfg, 11)
+    ta, tb = _trainer(ma), _trainer(mb_)
+    el, terms = ta.train_steps_async(data, index, N, bs, 0, nsteps)
+    spe = (N + bs - 1) // bs
+    for t in range(nsteps):
+        j = (t % spe) * bs
+        ind = index[:, j:j + bs]
+        e1, t1 = tb.train_step_async({k: v[ind] for k, v in data.items()})
+        assert torch.equal(e1, el[t]), ("ensemble_loss", t)
+        assert_close(t1, terms[t], 1e-5, "loss terms %d" % t)
+    torch.cuda.synchronize()
+    assert ta.num_train_steps == tb.num_train_steps == nsteps
+    assert torch.equal(ma.module.flat.data, mb_.module.flat.data)
+    assert torch.equal(ta.exp_avg, tb.exp_avg) and torch.equal(ta.exp_avg_sq, tb.exp_avg_sq)
+    # continuing from step 7 in a second launch == one launch of 10
+    mc, _ = make_pe_model(cfg, 11)
+    tc = _trainer(mc)
+    tc.train_steps_async(data, index, N, bs, 0, 10)
+    ta.train_steps_async(data, index, N, bs, 7, 3)
+    assert torch.equal(ma.module.flat.data, mc.module.flat.data)
+
+
+def test_member_sharded_step_equals_unsharded_bitwise():
+    """Member-sharded training (last matrix row): two slices trained by two trainers over the
+    same blob equal the unsharded step bit for bit (members are independent, pe_model.py:95-96)."""
+    m1, _ = make_pe_model(cases.MBPO, 11)
+    m2, _ = make_pe_model(cases.MBPO, 11)
+    full = _trainer(m1)
+    lo, hi = _trainer(m2, members=(0, 4)), _trainer(m2, members=(4, 7))
+    hi.exp_avg, hi.exp_avg_sq = lo.exp_avg, lo.exp_avg_sq           # one optimiser state, two slices
+    for s in range(3):
+        bt = _batch(600 + s, 7, 256)
+        e_full, _ = full.train_step_async(bt)
+        e_full = e_full.clone()
+        e_lo, _ = lo.train_step_async(bt)
+        e_lo = e_lo.clone()
+        e_hi, _ = hi.train_step_async(bt)
+        assert torch.equal(e_full[:4], e_lo[:4]) and torch.equal(e_full[4:], e_hi[4:])
+    assert torch.equal(m1.module.flat.data, m2.module.flat.data)
+    assert torch.equal(full.exp_avg, lo.exp_avg)
+    # an empty slice (E=7 over 8 ranks) is a no-op
+    none = _trainer(m2, members=(7, 7))
+    before = m2.module.flat.data.clone()
+    none.train_steps_async({k: v[0] for k, v in bt.items()}, torch.zeros(7, 256, dtype=torch.int64, device="cuda"),
+                           256, 256, 0, 2)
+    assert torch.equal(before, m2.module.flat.data)
+
+
+def test_train_b1_ant_sized_model_chain_path(monkeypatch):
+    """B = 1 with a wide D (AntTruncatedObs: O=27, A=8) -- the chain path's prep kernel must
+    zero all 2*E*D bound gradients even when its grid has fewer threads than that."""
+    import ctypes
+    from mirl_b200 import _lib
+    m, p = make_pe_model(cases.MBPO, 11, env="mb_ant", obs=27, act=8)
+    L = _lib.lib()
+    bt = {k: T(v, "cuda") for k, v in cases.train_batch(3, 7, 1, obs=27, act=8).items()}
+    cm = m._c_model(None)
+    ws = torch.empty(L.mb_pe_train_workspace_bytes(ctypes.byref(cm), 1), dtype=torch.uint8, device="cuda")
+    cfg = m.train_cfg(False)
+    pt = to_torch(p)
+    want = po.model_loss_grads(pt, *[bt[k].cpu() for k in ("observations", "actions", "deltas", "rewards", "terminals")])
+    for rep in range(2):                         # the second call would see the first call's leftovers
+        grads = torch.full_like(m.module.flat.data, 7.0)
+        el, terms = torch.zeros(7, device="cuda"), torch.zeros(3, device="cuda")
+        _lib.check(L.mb_pe_loss_grads(ctypes.byref(cm), ctypes.byref(cfg), _lib.ptr(bt["observations"]),
+                                      _lib.ptr(bt["actions"]), _lib.ptr(bt["deltas"]), _lib.ptr(bt["rewards"]),
+                                      _lib.ptr(bt["terminals"]), 1, _lib.ptr(grads), _lib.ptr(el), _lib.ptr(terms),
+                                      _lib.ptr(ws), ws.numel(), _lib.stream()))
+        gsd = m.module.reference_state_dict("module.", flat=grads)
+        for e in range(7):
+            assert norm_rel(gsd["module.maxlogstd_net%d" % e].cpu().numpy(), want["max_logstd"][e].numpy()) < 1e-3
+            assert norm_rel(gsd["module.minlogstd_net%d" % e].cpu().numpy(), want["min_logstd"][e].numpy()) < 1e-3
+
+
+# ---- the training loop against the reference's train_with_pool -----------------------------------
+@pytest.mark.parametrize("tag", ["small", "mbpo"])
+def test_train_with_pool_matches_reference_fixture(tag):
+    """B200PEModelTrainer.train_with_pool over a B200ExtraFieldPool against the UNMODIFIED reference
+    (tests/golden/gen_golden.py::gen_trainloop): normaliser statistics, split lengths, bootstrap table,
+    hold-out loss at every report point, per-step training loss, early-stopping step count, restored
+    best snapshots (parameter checksums) and the final elite ranking -- two consecutive calls."""
+    import mirl_b200
+    from mirl_b200.pools import B200ExtraFieldPool
+    c = cases.TRAINLOOP[tag]
+    cfg = c["cfg"]
+    g = golden("pe_trainloop_%s.npz" % tag)
+    m, _ = make_pe_model(cfg, c["seed"])
+    env = FakeEnv()
+    pool = B200ExtraFieldPool(env, max_size=5000, compute_mean_std=True)
+    pool.add_extra_fields({"deltas": {"shape": (cases.OBS,), "type": np.float32}})
+    tr = mirl_b200.B200PEModelTrainer(env, m, lr=c["lr"], tb_log_freq=-1, silent=True, ignore_terminal_state=False,
+                                      batch_size=c["batch_size"], report_freq=c["report_freq"],
+                                      max_not_improve=c["max_not_improve"], max_valid=c["max_valid"],
+                                      init_model_train_step=c["init_model_train_step"],
+                                      max_step_per_train=c["max_step_per_train"])
+    rec = {"eval": [], "train": []}
+    ev0, st0 = tr.eval_with_dataset, tr.train_steps_async
+
+    def ev(ds):
+        s, el = ev0(ds)
+        rec["eval"].append(np.array(el, dtype=np.float64))
+        return s, el
+
+    def st(*a, **k):
+        el, terms = st0(*a, **k)
+        rec["train"].append(torch.cat([el, terms.sum(1, keepdim=True)], 1).cpu().numpy().astype(np.float64))
+        return el, terms
+    tr.eval_with_dataset, tr.train_steps_async = ev, st
+    # lr = 0.1 on the small config is a deliberately rough ride (early stopping must trigger): rounding
+    # differences are amplified step by step, the DECISIONS (margin >= 2e-2 in the fixture) must not move
+    tol = 5e-2 if tag == "small" else 2e-3
+    np.random.seed(c["rng_seed"])
+    torch.manual_seed(c["rng_seed"])
+    for call, (seed, n) in enumerate(c["adds"]):
+        pool.add_samples(cases.dyn_samples(seed, n))
+        rec["eval"], rec["train"] = [], []
+        stats = tr.train_with_pool(pool)
+        pre = "c%d_" % call
+        assert float(g[pre + "decision_margin"]) > 1e-3          # no early-stopping decision is a near-tie
+        assert [tr.train_length, tr.eval_length] == list(g[pre + "lengths"])
+        assert np.allclose(proj(torch.as_tensor(tr.ensemble_index.astype(np.float64)), 5), g[pre + "index_proj"])
+        for k, (mu, sd) in tr.mean_std_dict.items():
+            assert np.allclose(mu, g[pre + "mean_" + k], rtol=1e-5, atol=1e-7), k
+            assert np.allclose(sd, g[pre + "std_" + k], rtol=1e-5, atol=1e-7), k
+        assert stats["train_step"] == int(g[pre + "train_step"])
+        got_eval = np.stack(rec["eval"])
+        assert got_eval.shape == g[pre + "eval"].shape
+        assert np.abs(got_eval - g[pre + "eval"]).max() <= tol * np.abs(g[pre + "eval"]).max(), \
+            np.abs(got_eval / g[pre + "eval"] - 1).max()
+        assert np.allclose(got_eval, g[pre + "eval"], rtol=tol * 4, atol=0)
+        got_train = np.concatenate(rec["train"])
+        assert got_train.shape == g[pre + "train"].shape
+        assert np.allclose(got_train, g[pre + "train"], rtol=tol * 4, atol=0)
+        assert list(m.elite_indices) == list(g[pre + "elite_indices"])
+        assert list(m.rank) == list(g[pre + "rank"])
+        assert np.allclose(np.array(tr.min_loss, dtype=np.float64), g[pre + "min_loss"], rtol=tol * 4)
+        sd = m.state_dict()
+        for i, name in enumerate(g["names"]):
+            got, ref = proj(sd[str(name)], 2000 + i), g[pre + "param_proj"][i]
+            assert abs(got[0] - ref[0]) <= (tol * 2) * ref[0] + 2e-3 * np.sqrt(sd[str(name)].numel()) * c["lr"] * 50, \
+                (str(name), got, ref)
+
+
+def test_extra_field_pool_matches_reference():
+    """B200ExtraFieldPool against the reference ExtraFieldPool: float64 running mean/std over three fills
+    (the third wraps the ring), the deltas field, the compute_delta flag protocol, sampled batches."""
+    from mirl_b200.pools import B200ExtraFieldPool
+    g = golden("extra_pool.npz")
+    pool = B200ExtraFieldPool(FakeEnv(), max_size=1000, compute_mean_std=True)
+    pool.add_extra_fields({"deltas": {"shape": (cases.OBS,), "type": np.float32}})
+    np.random.seed(93)
+    for i, n in enumerate([400, 350, 500]):
+        pool.add_samples(cases.dyn_samples(9300 + i, n))
+        tmp = pool.get_unprocessed_data_torch("compute_delta", ["observations", "next_observations"])
+        deltas = tmp["next_observations"] - tmp["observations"]
+        assert len(deltas) == int(g["unprocessed_%d" % i])
+        with pytest.raises(RuntimeError):
+            pool.random_batch(4)                               # deltas not aligned yet
+        pool.update_single_extra_field("deltas", deltas)
+        pool.update_process_flag("compute_delta", len(deltas))
+        for k, (mu, sd) in pool.get_mean_std().items():
+            assert np.allclose(mu, g["mean_%d_%s" % (i, k)], rtol=1e-5, atol=1e-6), (i, k)
+            assert np.allclose(sd, g["std_%d_%s" % (i, k)], rtol=1e-5, atol=1e-6), (i, k)
+        b = pool.random_batch(32)
+        for k, v in b.items():
+            assert np.array_equal(v, g["batch_%d_%s" % (i, k)]), (i, k)
+        assert [pool.get_size(), pool._stop] == list(g["size_%d" % i])
+    for k, v in pool.get_data().items():
+        assert np.allclose(proj(torch.from_numpy(v), 9), g["data_" + k]), k
+
+
+# ---- collectors against the reference collectors --------------------------------------------------
+class _ReplayModel:
+    """Feeds the recorded torch.randn draws of the reference run to the model (the CUDA generator is a
+    different stream); member indices still come from the global NumPy generator, like the reference."""
+
+    def __init__(self, model, noise):
+        self._m, self._noise, self._pos = model, noise, 0
+
+    def __getattr__(self, k):
+        return getattr(self._m, k)
+
+    def _take(self, n):
+        out = T(self._noise[self._pos:self._pos + n], "cuda")
+        self._pos += n
+        return out
+
+    def step(self, o, a, **kw):
+        return self._m.step(o, a, noise=self._take(o.shape[0]), **kw)
+
+    def step_rows(self, o, a, dest, **kw):
+        return self._m.step_rows(o, a, dest, noise=self._take(o.shape[0]), **kw)
+
+
+class _Replay:
+    def __init__(self, arr):
+        self.arr, self.pos = arr, 0
+
+    def __call__(self, B, A):
+        out = T(self.arr[self.pos:self.pos + B], "cuda")
+        self.pos += B
+        return out
+
+
+@pytest.mark.parametrize("tag,imagined", [("mbpo", "device"), ("mbpo", "host"), ("mopo", "host")])
+def test_collector_matches_reference_pool_contents(tag, imagined):
+    """B200MBPOCollector / B200MOPOCollector.imagine against the pool the reference collector filled
+    (hopper, two chunks, depth 5 / 3, rows terminate and are compacted away): same NumPy seed, recorded
+    torch draws -> same start states, same member indices, and the pool contents match row for row."""
+    import mirl_b200
+    from mirl_b200.collectors import B200MBPOCollector, B200MOPOCollector
+    c = cases.COLLECT[tag]
+    g = golden("collector_%s.npz" % tag)
+    env = FakeEnv(c["env"])
+    m, _ = make_pe_model(c["cfg"], c["mseed"], c["env"])
+    m.remember_loss(c["loss"])
+    pool = mirl_b200.B200DevicePool(env, max_size=c["pool_n"] + 10)
+    pool.add_samples(cases.dyn_samples(c["pool_seed"], c["pool_n"], env=c["env"]))
+    imag = mirl_b200.B200DevicePool(env, max_size=10, row_stride=m.row_stride())
+    pol = cases.TanhPolicy(c["mseed"] + 5, noise_source=_Replay(g["policy_noise"]))
+    model = _ReplayModel(m, g["model_noise"])
+    kw = dict(depth_schedule=c["depth"], number_sample=c["number_sample"], save_n=c["save_n"],
+              bathch_size=c["batch_size"])
+    if tag == "mopo":
+        col = B200MOPOCollector(model, pol, pool, imag, penalty_coef=c["penalty_coef"],
+                                penalty_type=c["penalty_type"], **kw)
+    else:
+        col = B200MBPOCollector(model, pol, pool, imag, **kw)
+    if imagined == "host":
+        col._fused_step = lambda o, a: None                  # reference-shaped path: step + add_samples
+    np.random.seed(int(g["rng_seed"]))
+    torch.manual_seed(int(g["rng_seed"]))
+    col.imagine(0)
+    assert [imag.get_size(), imag.max_size] == list(g["size"])
+    assert model._pos == len(g["model_noise"]) and pol.noise_source.pos == len(g["policy_noise"])
+    data = imag.get_data()
+    assert np.array_equal(data["terminals"], g["data_terminals"])
+    for k in ("observations", "actions", "next_observations", "rewards"):
+        assert_close(data[k], g["data_" + k], what=k)
+    assert 0.05 < data["terminals"].mean() < 0.95
+
+
+# ---- tensor-core kernel at every ensemble size; oracle comparison at 1e5 rows ----------------------
+@pytest.mark.parametrize("E,elites", [(2, 2), (5, 3), (10, 7), (20, 15)])
+def test_tcgen05_ensemble_sizes_match_oracle(E, elites):
+    cfg = dict(E=E, elites=elites, hidden=[200, 200, 200, 200], act="swish")
+    m, p = make_pe_model(cfg, 60 + E, "walker2d", kernel="tcgen05")
+    if not m._tc_supported():
+        pytest.skip("tcgen05 kernel does not cover this shape")
+    loss = list(np.random.RandomState(E).uniform(size=E))
+    m.remember_loss(loss)
+    B = 777
+    o, a = cases.rollout_inputs(70 + E, B, env="walker2d")
+    eps = np.random.RandomState(71).standard_normal((B, 18)).astype(np.float32)
+    idx = np.random.RandomState(72).choice(m.elite_indices, B)
+    no, r, d, _ = m.step(T(o, "cuda"), T(a, "cuda"), indices=idx, noise=T(eps, "cuda"))
+    rno, rr, rd = po.rollout_step(to_torch(p), T(o), T(a), torch.from_numpy(idx), T(eps), "walker2d")
+    assert_close(no, rno, what="next_obs")
+    assert_close(r, rr, what="reward")
+    out, _ = done_guard_mismatches("walker2d", rno.numpy(), rd.numpy(), d.cpu().numpy())
+    assert out == 0
+    mean, ls = m.predict_distribution(T(o[:300], "cuda"), T(a[:300], "cuda"))
+    rmean, rls = po.ensemble_distribution(to_torch(p), T(o[:300]), T(a[:300]))
+    assert_close(mean, rmean, what="mean")
+    assert_close(ls, rls, what="logstd")
+
+
+@pytest.mark.parametrize("kernel", ["tcgen05", "simt"])
+def test_rollout_100k_rows_matches_oracle(kernel):
+    """The bench's own shape (7 members / 5 elites, 4x200, obs 17 / act 6) at 1e5 rows against the CPU
+    oracle, device-side member draw included."""
+    B = 100_000
+    m, p = make_pe_model(cases.MBPO, 11, "hopper", kernel=kernel)
+    m.remember_loss(LOSS_VEC7)
+    o, a = cases.rollout_inputs(5, B, env="hopper")
+    eps = np.random.RandomState(6).standard_normal((B, 18)).astype(np.float32)
+    np.random.seed(9)
+    want_idx = np.random.choice(m.elite_indices, B)
+    np.random.seed(9)
+    no, r, d, _ = m.step(T(o, "cuda"), T(a, "cuda"), noise=T(eps, "cuda"))        # draws on the device
+    assert m._drew_on_device
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    rno, rr, rd = po.rollout_step(to_torch(p), T(o), T(a), torch.from_numpy(want_idx), T(eps), "hopper")
+    assert_close(no, rno, what="next_obs")
+    assert_close(r, rr, what="reward")
+    out, inside = done_guard_mismatches("hopper", rno.numpy(), rd.numpy(), d.cpu().numpy())
+    assert out == 0 and inside <= 20
