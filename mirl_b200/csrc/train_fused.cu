@@ -41,19 +41,25 @@
 #ifdef MB_FUSED_TIMELINE
 #define TL_ON (blockIdx.x == 0 && threadIdx.x == 0 && step == 2)
 #define TL_SET(i) do { if (TL_ON) a.dbg[i] = clock64(); } while (0)
+// per-CTA wall-clock stamps (globaltimer is synchronised across SMs, clock64 is not): member 0, step 2
+#define TL_ALL(base) do { if (threadIdx.x == 0 && step == 2 && blockIdx.x < a.G) { long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[(base) + blockIdx.x] = t_; } } while (0)
 #else
 #define TL_SET(i)
+#define TL_ALL(base)
 #endif
 
 namespace mb {
 
 namespace {
 
-constexpr int kT = 256;          // threads per CTA
-constexpr int kWarps = 8;
+constexpr int kWarps = 8;        // MMA warps; lane 0 of the last one also issues the bulk copies of the ring
+constexpr int kT = kWarps * 32;
+constexpr int kThreads = kT;
+constexpr int kIssuer = kWarps - 1;
 constexpr int kRows = 16;        // batch rows per block (one MMA M tile)
-constexpr int kChunk = 64;       // weight rows / batch rows per streamed chunk
-constexpr int kMaxNT = 4;        // n-tiles (8 columns) per warp: widths up to 256
+constexpr int kChunk = 64;       // batch rows per streamed chunk of phase B (and the ring's stage size)
+constexpr int kWChunk = 8 * kWarps;  // weight rows per streamed chunk of phase A: one dX output tile per warp (= 64)
 constexpr int kMaxStrips = 4;    // 16-row weight strips per phase-B job
 
 // ---- PTX helpers -----------------------------------------------------------------------------------
@@ -118,11 +124,11 @@ __device__ __forceinline__ void member_wait(const unsigned* cnt, unsigned target
         while (ld_acquire(cnt) < target) {
             if (++spins > (1u << 26)) __trap();          // never hang the box: a lost CTA is a bug
         }
-        // the bulk copies this thread issues next read, through the async proxy, global data that
-        // other CTAs wrote with ordinary stores
-        asm volatile("fence.proxy.async;" ::: "memory");
     }
     __syncthreads();
+    // the bulk copies issued next read, through the async proxy, global data that other CTAs wrote with
+    // ordinary stores
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 // activation and its derivative from one sigmoid: swish h = z s, h' = s (1 + z (1 - s)) = s + h (1 - s)
@@ -140,11 +146,11 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 }
 
 // bf16 offset of pack element (row k, column 0) of one member's layer pack; `half` 0 = hi, 1 = lo.
-// Layout: 64-row chunks, each [hi rows x Ns][lo rows x Ns] contiguous -> a chunk is ONE bulk copy.
+// Layout: kWChunk-row chunks, each [hi rows x Ns][lo rows x Ns] contiguous -> a chunk is ONE bulk copy.
 __device__ __forceinline__ int pack_row_off(int k, int half, int Kp, int Ns) {
-    const int c = k >> 6;
-    const int rows = min(kChunk, Kp - c * kChunk);
-    return c * (kChunk * Ns * 2) + half * rows * Ns + (k & 63) * Ns;
+    const int c = k / kWChunk;
+    const int rows = min(kWChunk, Kp - c * kWChunk);
+    return c * (kWChunk * Ns * 2) + half * rows * Ns + (k - c * kWChunk) * Ns;
 }
 
 struct StepScalars { float step_size, bc2_sqrt; };
@@ -152,9 +158,73 @@ struct StepScalars { float step_size, bc2_sqrt; };
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------
+// Global layouts of the phase-A -> phase-B hand-over (bf16 elements):
+//   g_l : [E][Bp/64][hi|lo][64][Ns]   a 64-row chunk of both halves is ONE bulk copy into the ring
+//   h_l : [hi|lo][Kp/16 strips][E][Bp][16]   a job's strip x 64 rows is one 2 KB bulk copy; the two 16-byte
+//         units of a row are swapped for rows with bit 2 set, which makes the transposed ldmatrix reads of
+//         the 32-byte-stride tile bank-conflict free
+__device__ __forceinline__ int64_t g_elem_off(const FusedLayer& ly, int e, int Bp, int b, int half) {
+    return ly.g_off + ((((int64_t)e * (Bp >> 6) + (b >> 6)) * 2 + half) * kChunk + (b & 63)) * ly.Ns;
+}
+__device__ __forceinline__ int64_t h_elem_off(const FusedLayer& ly, int E, int e, int Bp, int b, int strip, int half) {
+    return ly.h_off + ((((int64_t)half * (ly.Kp >> 4) + strip) * E + e) * Bp + b) * 16;
+}
+
+
+// ---- branch-free inner loops (the guarded generic loops below them keep every k-step behind a branch,
+// which stops ptxas from overlapping a k-step's fragment loads with the previous k-step's MMAs) -----------
+// forward: a full 64-row chunk (4 k-steps), NTW n-tiles per warp (tiles warp, warp+8, ...)
+template <int NTW>
+__device__ __forceinline__ void fwd_chunk4(float (&acc)[4][4], const __nv_bfloat16* Ah, const __nv_bfloat16* Al,
+                                           const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int a_off, int b_off, int Ns,
+                                           int warp) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        uint32_t ah[4], al[4];
+        ldsm_x4(ah, smem_u32(Ah + a_off + kk * 16));
+        ldsm_x4(al, smem_u32(Al + a_off + kk * 16));
+        uint32_t bh[NTW][2], bl[NTW][2];
+#pragma unroll
+        for (int i = 0; i < NTW; ++i) {
+            const int off = kk * 16 * Ns + b_off + (warp + kWarps * i) * 8;
+            ldsm_x2_t(bh[i], smem_u32(Wh + off));
+            ldsm_x2_t(bl[i], smem_u32(Wl + off));
+        }
+#pragma unroll
+        for (int i = 0; i < NTW; ++i) mma3(acc[i], ah, al, bh[i], bl[i]);
+    }
+}
+// phase B: a full 64-row chunk (4 groups of 16 batch rows), NS strips x NTW n-tiles per warp
+template <int NS, int NTW>
+__device__ __forceinline__ void dw_chunk4(float (&acc)[kMaxStrips][4][4], const __nv_bfloat16* Gh, const __nv_bfloat16* Gl,
+                                          const __nv_bfloat16* Hh, const __nv_bfloat16* Hl, int g_off, int Ns, int warp,
+                                          int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        uint32_t bh[NTW][2], bl[NTW][2];
+#pragma unroll
+        for (int i = 0; i < NTW; ++i) {
+            const int off = kk * 16 * Ns + g_off + (warp + kWarps * i) * 8;
+            ldsm_x2_t(bh[i], smem_u32(Gh + off));
+            ldsm_x2_t(bl[i], smem_u32(Gl + off));
+        }
+        const int hb = kk * 16 + (lane & 7) + 8 * (lane >> 4);
+        const int h_off = hb * 16 + ((((lane >> 3) & 1) ^ ((hb >> 2) & 1)) << 3);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            uint32_t ah[4], al[4];
+            ldsm_x4_t(ah, smem_u32(Hh + s * (kChunk * 16) + h_off));
+            ldsm_x4_t(al, smem_u32(Hl + s * (kChunk * 16) + h_off));
+#pragma unroll
+            for (int i = 0; i < NTW; ++i) mma3(acc[s][i], ah, al, bh[i], bl[i]);
+        }
+    }
+}
+
 // KS = compile-time bound of the dX reduction length in k-steps (its operand fragments live in registers)
-template <int KS>
-__global__ void __launch_bounds__(kT, 1)
+// NT = n-tiles (8 columns) per consumer warp: widths up to 8 * kWarps * NT
+template <int KS, int NT>
+__global__ void __launch_bounds__(kThreads, 1)
 k_train_fused(const __grid_constant__ FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -176,18 +246,41 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
     auto act_ptr = [&](int s) { return s ? act1 : act0; };
     __shared__ StepScalars s_sc;
     __shared__ float s_part[kWarps];
-    __shared__ __align__(8) uint64_t s_full[2];       // "chunk landed" barriers of the two stages
-    const uint32_t full0 = smem_u32(&s_full[0]);
-    uint32_t par0 = 0, par1 = 0;                      // phase parity of each stage's barrier
+    __shared__ int64_t s_rowidx[kRows];
+    __shared__ float s_tgt[kRows][64 + 1];            // head targets of the block (normalised delta | reward) and the loss mask
+    __shared__ float s_bound[2][64];                  // max / min log-std of this member
+    __shared__ __align__(8) uint64_t s_bar[4];        // full[2] ("chunk landed"), empty[2] ("chunk consumed")
+    const uint32_t full0 = smem_u32(&s_bar[0]), empty0 = smem_u32(&s_bar[2]);
     if (tid == 0) {
         mbar_init(full0, 1);
         mbar_init(full0 + 8, 1);
+        mbar_init(empty0, kWarps);
+        mbar_init(empty0 + 8, kWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto wait_stage = [&](int s) {
-        if (s) { mbar_wait(full0 + 8, par1); par1 ^= 1; } else { mbar_wait(full0, par0); par0 ^= 1; }
+    // Ring protocol.  Use number u (0, 1, 2, ... over the whole kernel) occupies stage u & 1.  The issuer
+    // (lane 0 of warp kIssuer, which has the fewest tiles) waits for the stage's previous use to be released
+    // by all 8 warps and issues the bulk copy of use u + 1 before it consumes use u; a warp waits for the
+    // copy to land, computes, and releases.  No CTA-wide barrier per chunk.
+    uint32_t use = 0, use_p = 0;                      // uses consumed (every thread) / issued (issuer warp)
+    auto producer_acquire = [&]() -> int {            // -> stage
+        const int s = use_p & 1;
+        if (use_p >= 2) mbar_wait(empty0 + 8 * s, ((use_p >> 1) & 1) ^ 1);
+        ++use_p;
+        return s;
     };
+    auto consumer_wait = [&]() -> int {
+        const int s = use & 1;
+        mbar_wait(full0 + 8 * s, (use >> 1) & 1);
+        ++use;
+        return s;
+    };
+    auto consumer_release = [&](int s) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    };
+    auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kT) : "memory"); };
 
     __nv_bfloat16* const pack = a.pack;
     __nv_bfloat16* const hbuf = a.hbuf;
@@ -206,7 +299,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
         __nv_bfloat16* pm = pack + ly.pack_off + (int64_t)e * 2 * ly.Kp * ly.Ns;
         const int k0 = jb.strip0 * 16, k1 = min(k0 + jb.nstrips * 16, ly.Kp);
         const int npair = ly.Ns >> 1;
-        for (int t = tid; t < (k1 - k0) * npair; t += kT) {
+        for (int t = tid; t < (k1 - k0) * npair; t += kThreads) {
             const int k = k0 + t / npair, n = (t % npair) * 2;
             float v0 = 0.f, v1 = 0.f;
             if (k <= ly.K) {
@@ -224,8 +317,9 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
     member_arrive(bar);
     member_wait(bar, bar_target);
 
-    // Adam bias corrections: beta^t carried as running products in double by thread 0
-    double b1t = a.beta1_pow0, b2t = a.beta2_pow0;
+    const int npass = 2 * L - 1;
+    auto pass_layer = [&](int p) { return p < L ? p : 2 * L - 1 - p; };
+    double b1t = a.beta1_pow0, b2t = a.beta2_pow0;    // beta^t as running products (thread 0)
 
     for (int step = 0; step < a.nsteps; ++step) {
         // batch of this step inside the epoch schedule (pe_model_trainer.py:240,268)
@@ -237,37 +331,41 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
         const float invB = 1.f / (float)B;
         float* const eloss = a.ensemble_loss + (int64_t)step * a.E;
         float* const lterms = a.loss_terms + (int64_t)step * 3;
+        const int nchunksB = (nblk * kRows + kChunk - 1) / kChunk;
 
-        // ================================ phase A ================================================
+        // ================================ phase A (consumer warps) =================================
         TL_SET(0);
+        TL_ALL(200);
         for (int blk = slot; blk < nblk; blk += G) {
             const int row0 = blk * kRows;
-            // ---- chunk stream over all layer passes of this block: forward 0..L-1, then dX L-1..1.
-            // One elected thread issues ONE bulk copy per chunk (the pack keeps a chunk's hi and lo
-            // halves adjacent); the copy of chunk i+1 is in flight while chunk i is consumed.
-            int is_pass = 0, is_chunk = 0;            // next chunk to ISSUE (thread 0 only uses these)
-            const int npass = 2 * L - 1;
-            auto pass_layer = [&](int p) { return p < L ? p : 2 * L - 1 - p; };
-            auto issue_next = [&](int stage) {
-                if (tid != 0 || is_pass >= npass) return;
-                const FusedLayer& ly = a.ly[pass_layer(is_pass)];
-                const int r0 = is_chunk * kChunk;
-                const int rows = min(kChunk, ly.Kp - r0);
-                const __nv_bfloat16* src = pack + ly.pack_off + (int64_t)e * 2 * ly.Kp * ly.Ns + (int64_t)is_chunk * (kChunk * ly.Ns * 2);
-#ifdef MB_EXP_NOCOPY
-                const uint32_t bytes = 16;
-#else
-                const uint32_t bytes = (uint32_t)rows * ly.Ns * 4;
-#endif
-                const uint32_t fb = full0 + 8 * stage;
-                mbar_expect_tx(fb, bytes);
-                // (one copy per chunk: splitting it into four concurrent pieces measured 20 % slower)
-                bulk_g2s(smem_u32(stage_ptr(stage)), src, bytes, fb);
-                if (++is_chunk * kChunk >= ly.Kp) { is_chunk = 0; ++is_pass; }
+            // chunk stream over all layer passes of this block (forward 0..L-1, then dX L-1..1): ONE bulk copy
+            // per chunk (the pack keeps a chunk's hi and lo halves adjacent), issued one chunk ahead
+            int ip = 0, ic = 0;                           // next (pass, chunk) to issue
+            auto issue_w = [&]() {
+                if (warp != kIssuer || ip >= npass) return;
+                const FusedLayer& ly = a.ly[pass_layer(ip)];
+                const int st = producer_acquire();
+                fence_proxy_async();
+                if (lane == 0) {
+                    const int rows = min(kWChunk, ly.Kp - ic * kWChunk);
+                    const uint32_t bytes = (uint32_t)rows * ly.Ns * 4;
+                    const uint32_t fb = full0 + 8 * st;
+                    mbar_expect_tx(fb, bytes);
+                    bulk_g2s(smem_u32(stage_ptr(st)),
+                             pack + ly.pack_off + (int64_t)e * 2 * ly.Kp * ly.Ns + (int64_t)ic * (kWChunk * ly.Ns * 2), bytes, fb);
+                }
+                if (++ic * kWChunk >= ly.Kp) { ic = 0; ++ip; }
             };
-            issue_next(0);
-
-            // ---- stage the normalised inputs [obs | act | 1 | 0...] as bf16 hi/lo (layer 0 operand)
+            issue_w();
+            // ---- row indices of the block, then the normalised inputs [obs | act | 1 | 0...] as bf16 hi/lo
+            if (tid < kRows) {
+                const int b = row0 + tid;
+                int64_t r = -1;
+                if (b < B) r = a.index ? a.index[(int64_t)e * a.index_stride + j0 + b]
+                                       : (a.per_member_rows ? (int64_t)e * a.batch_size + b : (int64_t)b);
+                s_rowidx[tid] = r;
+            }
+            consumer_sync();
             {
                 const FusedLayer& l0 = a.ly[0];
                 const int As = l0.As, IN = l0.K, O = a.O;
@@ -275,11 +373,9 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 __nv_bfloat16* al = ah + kRows * a.as_max;
                 for (int t = tid; t < kRows * (As / 2); t += kT) {
                     const int i = t / (As / 2), j = (t % (As / 2)) * 2;
-                    const int b = row0 + i;
+                    const int64_t r = s_rowidx[i];
                     float v[2] = {0.f, 0.f};
-                    if (b < B) {
-                        const int64_t r = a.index ? a.index[(int64_t)e * a.index_stride + j0 + b]
-                                                  : (a.per_member_rows ? (int64_t)e * a.batch_size + b : (int64_t)b);
+                    if (r >= 0) {
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const int c = j + q;
@@ -299,12 +395,38 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     split2(v[0], v[1], hi, lo);
                     *reinterpret_cast<uint32_t*>(ah + i * As + j) = hi;
                     *reinterpret_cast<uint32_t*>(al + i * As + j) = lo;
+                    // h_0 for phase B (strip-major, swizzled 16-byte units): 4 bytes per thread
+                    if (j < l0.Kp) {
+                        const int b = row0 + i, unit = ((j >> 3) & 1) ^ ((b >> 2) & 1);
+                        const int64_t o = h_elem_off(l0, a.E, e, a.Bp, b, j >> 4, 0) + unit * 8 + (j & 7);
+                        *reinterpret_cast<uint32_t*>(hbuf + o) = hi;
+                        *reinterpret_cast<uint32_t*>(hbuf + o + (int64_t)(l0.Kp >> 4) * a.E * a.Bp * 16) = lo;
+                    }
                 }
             }
-            __syncthreads();
+            // head operands of this block: fetched now, consumed five layers later (their latency hides
+            // behind the forward pass instead of sitting in front of the loss)
+            if (a.head_kind == FUSED_HEAD_NLL) {
+                const int D = a.D, O = a.O;
+                const float* dmean = a.norm + 2 * O + 2 * a.A;
+                const float* dstd = dmean + O;
+                for (int t = tid; t < kRows * (D + 1); t += kT) {
+                    const int i = t / (D + 1), j = t - i * (D + 1);
+                    const int64_t r = s_rowidx[i];
+                    float v = 0.f;
+                    if (r >= 0) {
+                        if (j < O) v = (a.delta[r * O + j] - dmean[j]) / (dstd[j] + kNormEps);
+                        else if (j == O) v = a.reward[r];
+                        else v = a.cfg.ignore_terminal_state ? 1.f - a.done[r] : 1.f;
+                    }
+                    s_tgt[i][j < D ? j : 64] = v;
+                }
+                if (tid < 2 * 64 && (tid & 63) < D)
+                    s_bound[tid >> 6][tid & 63] = __ldcg(a.params + ((tid >> 6) ? a.minls_off : a.maxls_off) + (int64_t)e * D + (tid & 63));
+            }
+            consumer_sync();
 
             int cur = 0;                                  // act[cur] = input operand of the running pass
-            int cs_stage = 0;                             // stage holding the chunk to CONSUME
             for (int pass = 0; pass < npass; ++pass) {
                 TL_SET(8 + pass);
                 const bool fwd = pass < L;
@@ -315,34 +437,31 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 const int astride = fwd ? ly.As : Ns;
                 const __nv_bfloat16* Ah = act_ptr(cur);
                 const __nv_bfloat16* Al = Ah + kRows * a.as_max;
-                // copy this pass's A operand to global for phase B (h_l for forward, g_l for dX):
-                // coalesced 16-byte pieces of the 16 rows
-                {
-                    __nv_bfloat16* gh = (fwd ? hbuf + ly.h_off : gbuf + ly.g_off) + ((int64_t)e * a.Bp + row0) * astride;
-                    __nv_bfloat16* gl = gh + (int64_t)a.E * a.Bp * astride;
-                    const int pieces = kRows * astride / 8;
-                    for (int p = tid; p < pieces; p += kT) {
-                        *reinterpret_cast<uint4*>(gh + p * 8) = *reinterpret_cast<const uint4*>(Ah + p * 8);
-                        *reinterpret_cast<uint4*>(gl + p * 8) = *reinterpret_cast<const uint4*>(Al + p * 8);
-                    }
-                }
-                TL_SET(60 + pass * 6 + 0);
-                const int nchunks = (ly.Kp + kChunk - 1) / kChunk;
-                float acc[kMaxNT][4];
-#pragma unroll
-                for (int i = 0; i < kMaxNT; ++i)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+                const int nchunks = (ly.Kp + kWChunk - 1) / kWChunk;
                 const int nt_total = fwd ? ly.nt_out : ly.nt_in;   // output n-tiles of this pass
                 const int out_w = fwd ? ly.N : ly.K;               // real output columns
                 // destination operand buffer of this pass
                 __nv_bfloat16* Dh = act_ptr(cur ^ 1);
                 __nv_bfloat16* Dl = Dh + kRows * a.as_max;
                 const bool last_fwd = fwd && l == L - 1;
-                // stride of the produced operand: forward -> next layer's input stride; dX -> Ns of layer l-1
-                const int dstride = fwd ? (last_fwd ? 0 : a.ly[l + 1].As) : a.ly[l - 1].Ns;
-                const float* zin = zbuf + (fwd ? l : l - 1) * kRows * a.z_stride;
+                // the produced operand: forward -> h_{l+1} (stride As of layer l+1); dX -> g_{l-1} (stride Ns of l-1)
+                const FusedLayer& lo_ = a.ly[fwd ? (last_fwd ? l : l + 1) : l - 1];
+                const int dstride = fwd ? lo_.As : lo_.Ns;
+                float* const zrow = zbuf + (fwd ? l : l - 1) * kRows * a.z_stride;
+                // global destination of this thread's two fragment rows (phase B's layouts), hoisted out of the tiles
+                const int64_t h_strip_stride = (int64_t)a.E * a.Bp * 16, h_half = (int64_t)(lo_.Kp >> 4) * h_strip_stride;
+                int64_t grow[2];
+                int gsw[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int b = row0 + (lane >> 2) + 8 * h;
+                    gsw[h] = (b >> 2) & 1;
+                    grow[h] = fwd ? h_elem_off(lo_, a.E, e, a.Bp, b, 0, 0) + 2 * (lane & 3)
+                                  : g_elem_off(lo_, e, a.Bp, b, 0) + 2 * (lane & 3);
+                }
 
+                // The epilogue of a tile writes the produced operand to shared memory (next pass) AND to
+                // global memory in phase B's layout -- no separate copy pass.
                 auto epilogue_tile = [&](int tile, const float (&c)[4]) {
                     // accumulator fragment: rows lane/4 and lane/4+8, columns n0 + 2*(lane%4), +1
                     const int n = tile * 8 + 2 * (lane & 3);
@@ -350,75 +469,93 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     for (int h = 0; h < 2; ++h) {
                         const int i = (lane >> 2) + 8 * h;
                         float v0 = c[2 * h], v1 = c[2 * h + 1];
+                        if (last_fwd) {
+                            if (n < out_w) headbuf[i * a.head_stride + n] = v0;
+                            if (n + 1 < out_w) headbuf[i * a.head_stride + n + 1] = v1;
+                            continue;
+                        }
+                        uint32_t hi, lo;
                         if (fwd) {
-                            if (last_fwd) {
-                                if (n < out_w) headbuf[i * a.head_stride + n] = v0;
-                                if (n + 1 < out_w) headbuf[i * a.head_stride + n + 1] = v1;
-                                continue;
-                            }
                             // the backward pass needs act'(z), not z: keep that (one sigmoid serves both)
-                            float* zr = const_cast<float*>(zin) + i * a.z_stride + n;
                             float d0 = 0.f, d1 = 0.f;
                             if (n < out_w) v0 = act_both(v0, act_kind, d0); else v0 = (n == out_w) ? 1.f : 0.f;
                             if (n + 1 < out_w) v1 = act_both(v1, act_kind, d1); else v1 = (n + 1 == out_w) ? 1.f : 0.f;
-                            *reinterpret_cast<float2*>(zr) = make_float2(d0, d1);
+                            *reinterpret_cast<float2*>(zrow + i * a.z_stride + n) = make_float2(d0, d1);
+                            split2(v0, v1, hi, lo);
+                            const int64_t o = grow[h] + (tile >> 1) * h_strip_stride + (((tile & 1) ^ gsw[h]) << 3);
+                            *reinterpret_cast<uint32_t*>(hbuf + o) = hi;
+                            *reinterpret_cast<uint32_t*>(hbuf + o + h_half) = lo;
                         } else {
-                            const float2 d = *reinterpret_cast<const float2*>(zin + i * a.z_stride + n);
+                            const float2 d = *reinterpret_cast<const float2*>(zrow + i * a.z_stride + n);
                             v0 = n < out_w ? v0 * d.x : 0.f;
                             v1 = n + 1 < out_w ? v1 * d.y : 0.f;
+                            split2(v0, v1, hi, lo);
+                            const int64_t o = grow[h] + tile * 8;
+                            *reinterpret_cast<uint32_t*>(gbuf + o) = hi;
+                            *reinterpret_cast<uint32_t*>(gbuf + o + (int64_t)kChunk * lo_.Ns) = lo;
                         }
-                        uint32_t hi, lo;
-                        split2(v0, v1, hi, lo);
                         *reinterpret_cast<uint32_t*>(Dh + i * dstride + n) = hi;
                         *reinterpret_cast<uint32_t*>(Dl + i * dstride + n) = lo;
                     }
                 };
 
-                // zero the destination's padding columns beyond the tiles the epilogue writes
+                // padding columns of the produced operand beyond the tiles the epilogue writes (shared
+                // memory and global): zeros, except the bias "1" when column N falls there
                 if (!last_fwd) {
                     const int c0 = nt_total * 8;
                     const int wpad = dstride - c0;
                     for (int t = tid; t < kRows * wpad; t += kT) {
                         const int i = t & (kRows - 1), c = c0 + (t >> 4);
-                        // forward: column N may fall beyond the last tile (N multiple of 8): it is the bias 1
                         const float v = (fwd && c == out_w) ? 1.f : 0.f;
-                        Dh[i * dstride + c] = __float2bfloat16(v);
-                        Dl[i * dstride + c] = __float2bfloat16(0.f);
-                    }
-                }
-
-                TL_SET(60 + pass * 6 + 1);
-                // per-lane ldmatrix offsets (elements) that do not depend on the chunk
-                const int a_lane_off = ((lane & 7) + 8 * ((lane >> 3) & 1)) * astride + 8 * (lane >> 4);
-                // dX: every chunk needs the whole g_l operand (the reduction runs over its columns): the
-                // fragments of all k-steps are loaded ONCE per pass and stay in registers -- re-reading
-                // them per chunk made the pass shared-memory-bandwidth bound (8 warps x 4 chunks x 13 KB)
-                uint32_t gfh[KS][4], gfl[KS][4];
-                if (!fwd) {
-#pragma unroll
-                    for (int kk = 0; kk < KS; ++kk) {
-                        if (kk < ly.ksteps_out) {
-                            ldsm_x4(gfh[kk], smem_u32(Ah + a_lane_off + kk * 16));
-                            ldsm_x4(gfl[kk], smem_u32(Al + a_lane_off + kk * 16));
+                        const __nv_bfloat16 vb = __float2bfloat16(v), zb = __float2bfloat16(0.f);
+                        Dh[i * dstride + c] = vb;
+                        Dl[i * dstride + c] = zb;
+                        const int b = row0 + i;
+                        if (fwd) {
+                            if (c < lo_.Kp) {
+                                const int unit = ((c >> 3) & 1) ^ ((b >> 2) & 1);
+                                const int64_t o = h_elem_off(lo_, a.E, e, a.Bp, b, c >> 4, 0) + unit * 8 + (c & 7);
+                                hbuf[o] = vb;
+                                hbuf[o + (int64_t)(lo_.Kp >> 4) * a.E * a.Bp * 16] = zb;
+                            }
+                        } else {
+                            const int64_t o = g_elem_off(lo_, e, a.Bp, b, 0) + c;
+                            gbuf[o] = zb;
+                            gbuf[o + (int64_t)kChunk * lo_.Ns] = zb;
                         }
                     }
                 }
-                for (int c = 0; c < nchunks; ++c) {
-                    issue_next(cs_stage ^ 1);
-                    wait_stage(cs_stage);
-                    if (c == 0) TL_SET(60 + pass * 6 + 2);
-                    const int rows = min(kChunk, ly.Kp - c * kChunk);
-                    const __nv_bfloat16* Wh = stage_ptr(cs_stage);
-                    const __nv_bfloat16* Wl = Wh + rows * Ns;
-#ifdef MB_EXP_NOMMA
-                    if (false) {} else if (a.nsteps < 0)
-#endif
-                    if (fwd) {
-                        // reduction over the chunk's rows; warp owns n-tiles warp, warp+8, ...
-                        const int b_lane_off = (lane & 15) * Ns;
+                TL_SET(60 + pass * 6 + 1);
+                // per-lane ldmatrix offsets (elements) that do not depend on the chunk
+                const int a_lane_off = ((lane & 7) + 8 * ((lane >> 3) & 1)) * astride + 8 * (lane >> 4);
+                if (fwd) {
+                    float acc[NT][4];
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+                    const int b_lane_off = (lane & 15) * Ns;
+                    for (int c = 0; c < nchunks; ++c) {
+                        issue_w();
+                        const int st = consumer_wait();
+                        if (c == 0) TL_SET(60 + pass * 6 + 2);
+                        const int rows = min(kWChunk, ly.Kp - c * kWChunk);
+                        const __nv_bfloat16* Wh = stage_ptr(st);
+                        const __nv_bfloat16* Wl = Wh + rows * Ns;
                         const int nk = rows / 16;
-                        // fully unrolled (guarded) so that the k-steps' fragment loads are scheduled ahead of
-                        // the previous k-step's MMAs
+                        // reduction over the chunk's rows; warp owns n-tiles warp, warp+8, ...
+                        const int ntw = nt_total > warp ? (nt_total - warp + kWarps - 1) / kWarps : 0;
+                        bool fast = false;
+                        if constexpr (NT == 4) {
+                            if (nk == 4 && ntw == 4) {
+                                fwd_chunk4<4>(acc, Ah, Al, Wh, Wl, a_lane_off + c * kWChunk, b_lane_off, Ns, warp);
+                                fast = true;
+                            } else if (nk == 4 && ntw == 3) {
+                                fwd_chunk4<3>(acc, Ah, Al, Wh, Wl, a_lane_off + c * kWChunk, b_lane_off, Ns, warp);
+                                fast = true;
+                            }
+                        }
+                        if (!fast)
 #pragma unroll
                         for (int kk = 0; kk < kChunk / 16; ++kk) {
                             if (kk >= nk) break;
@@ -426,9 +563,9 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                             uint32_t ah[4], al[4];
                             ldsm_x4(ah, smem_u32(Ah + a_lane_off + kcol));
                             ldsm_x4(al, smem_u32(Al + a_lane_off + kcol));
-                            uint32_t bh[kMaxNT][2], bl[kMaxNT][2];
+                            uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
-                            for (int i = 0; i < kMaxNT; ++i) {
+                            for (int i = 0; i < NT; ++i) {
                                 const int tile = warp + kWarps * i;
                                 if (tile < nt_total) {
                                     const int off = kk * 16 * Ns + b_lane_off + tile * 8;
@@ -437,16 +574,40 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                                 }
                             }
 #pragma unroll
-                            for (int i = 0; i < kMaxNT; ++i) {
+                            for (int i = 0; i < NT; ++i) {
                                 const int tile = warp + kWarps * i;
                                 if (tile < nt_total) mma3(acc[i], ah, al, bh[i], bl[i]);
                             }
                         }
-                    } else {
+                        consumer_release(st);
+                    }
+                    TL_SET(60 + pass * 6 + 3);
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) {
+                        const int tile = warp + kWarps * i;
+                        if (tile < nt_total) epilogue_tile(tile, acc[i]);
+                    }
+                } else {
+                    // dX: every chunk needs the whole g_l operand (the reduction runs over its columns).  The hi
+                    // fragments of all k-steps are loaded ONCE per pass and stay in registers (re-reading both
+                    // halves per chunk made the pass shared-memory-bandwidth bound: 8 warps x 4 chunks x 13 KB);
+                    // the lo halves are re-read -- keeping them too costs 52 more registers and spills
+                    uint32_t gfh[KS][4];
+#pragma unroll
+                    for (int kk = 0; kk < KS; ++kk) {
+                        if (kk < ly.ksteps_out) ldsm_x4(gfh[kk], smem_u32(Ah + a_lane_off + kk * 16));
+                    }
+                    for (int c = 0; c < nchunks; ++c) {
+                        issue_w();
+                        const int st = consumer_wait();
+                        if (c == 0) TL_SET(60 + pass * 6 + 2);
+                        const int rows = min(kWChunk, ly.Kp - c * kWChunk);
+                        const __nv_bfloat16* Wh = stage_ptr(st);
+                        const __nv_bfloat16* Wl = Wh + rows * Ns;
                         // chunk rows = output columns k; warp owns output tile 8c + warp; full reduction over n.
                         // six independent accumulator chains (3 terms x even/odd k-step): one tile per warp
                         // would otherwise be a 39-deep dependent MMA chain
-                        const int tile = c * (kChunk / 8) + warp;
+                        const int tile = c * (kWChunk / 8) + warp;
                         if (tile < nt_total) {
                             float c6[6][4];
 #pragma unroll
@@ -454,42 +615,52 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) c6[i][q] = 0.f;
                             const int b_lane_off = (warp * 8 + (lane & 7)) * Ns + 8 * ((lane >> 3) & 1);
+                            if (ly.ksteps_out == KS) {
 #pragma unroll
-                            for (int kk = 0; kk < KS; ++kk) {
-                                if (kk < ly.ksteps_out) {
-                                    uint32_t bh[2], bl[2];
+                                for (int kk = 0; kk < KS; ++kk) {
+                                    uint32_t bh[2], bl[2], gl4[4];
+                                    ldsm_x4(gl4, smem_u32(Al + a_lane_off + kk * 16));
                                     ldsm_x2(bh, smem_u32(Wh + b_lane_off + kk * 16));
                                     ldsm_x2(bl, smem_u32(Wl + b_lane_off + kk * 16));
                                     const int o = (kk & 1) * 3;
-                                    mma16816(c6[o + 0], gfl[kk], bh);
+                                    mma16816(c6[o + 0], gl4, bh);
                                     mma16816(c6[o + 1], gfh[kk], bl);
                                     mma16816(c6[o + 2], gfh[kk], bh);
                                 }
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < KS; ++kk) {
+                                    if (kk < ly.ksteps_out) {
+                                        uint32_t bh[2], bl[2], gl4[4];
+                                        ldsm_x4(gl4, smem_u32(Al + a_lane_off + kk * 16));
+                                        ldsm_x2(bh, smem_u32(Wh + b_lane_off + kk * 16));
+                                        ldsm_x2(bl, smem_u32(Wl + b_lane_off + kk * 16));
+                                        const int o = (kk & 1) * 3;
+                                        mma16816(c6[o + 0], gl4, bh);
+                                        mma16816(c6[o + 1], gfh[kk], bl);
+                                        mma16816(c6[o + 2], gfh[kk], bh);
+                                    }
+                                }
                             }
+                            consumer_release(st);              // the stage is free before the epilogue maths
                             float cacc[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
                                 cacc[q] = ((c6[0][q] + c6[3][q]) + (c6[1][q] + c6[4][q])) + (c6[2][q] + c6[5][q]);
                             epilogue_tile(tile, cacc);
+                        } else {
+                            consumer_release(st);
                         }
                     }
-                    __syncthreads();                       // stage may be refilled by the next issue
-                    cs_stage ^= 1;
-                }
-                TL_SET(60 + pass * 6 + 3);
-                if (fwd) {
-#pragma unroll
-                    for (int i = 0; i < kMaxNT; ++i) {
-                        const int tile = warp + kWarps * i;
-                        if (tile < nt_total) epilogue_tile(tile, acc[i]);
-                    }
+                    TL_SET(60 + pass * 6 + 3);
                 }
                 TL_SET(60 + pass * 6 + 4);
-                __syncthreads();
+                consumer_sync();
                 TL_SET(60 + pass * 6 + 5);
 
                 if (last_fwd) {
-                    // ---- loss head: writes g_L (bf16 hi/lo, stride Ns) into the destination buffer
+                    // ---- loss head: writes g_{L-1} (bf16 hi/lo, stride Ns) into the destination buffer and
+                    // to global memory
                     const int D = a.D, O = a.O;
                     const int gs = ly.Ns;
                     float part = 0.f;
@@ -500,28 +671,20 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                         Dh[t] = __float2bfloat16(0.f);
                         Dl[t] = __float2bfloat16(0.f);
                     }
-                    __syncthreads();
+                    consumer_sync();
                     if (a.head_kind == FUSED_HEAD_NLL) {
-                        const float* mxp = a.params + a.maxls_off + (int64_t)e * D;
-                        const float* mnp = a.params + a.minls_off + (int64_t)e * D;
-                        const float* dmean = a.norm + 2 * O + 2 * a.A;
-                        const float* dstd = dmean + O;
                         for (int t = tid; t < kRows * D; t += kT) {
                             const int i = t / D, j = t - i * D;
-                            const int b = row0 + i;
-                            if (b >= B) continue;
-                            const int64_t r = a.index ? a.index[(int64_t)e * a.index_stride + j0 + b]
-                                                      : (a.per_member_rows ? (int64_t)e * a.batch_size + b : (int64_t)b);
+                            if (s_rowidx[i] < 0) continue;
                             const float mu = headbuf[i * a.head_stride + j], raw = headbuf[i * a.head_stride + D + j];
-                            const float mx = __ldcg(mxp + j), mn = __ldcg(mnp + j);   // updated by another SM every step
+                            const float mx = s_bound[0][j], mn = s_bound[1][j];
                             const float aa = mx - raw;
                             const float ls1 = mx - softplusf_(aa);
                             const float cc = ls1 - mn;
                             const float ls = mn + softplusf_(cc);
-                            float tgt, coef;
-                            if (j < O) { tgt = (a.delta[r * O + j] - dmean[j]) / (dstd[j] + kNormEps); coef = 1.f; }
-                            else { tgt = a.reward[r]; coef = a.cfg.reward_coef; }
-                            const float mask = a.cfg.ignore_terminal_state ? 1.f - a.done[r] : 1.f;
+                            const float tgt = s_tgt[i][j];
+                            const float coef = j < O ? 1.f : a.cfg.reward_coef;
+                            const float mask = s_tgt[i][64];
                             const float inv_var = expf(-2.f * ls);
                             const float diff = tgt - mu;
                             const float w = mask * coef * invB;
@@ -555,7 +718,17 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     }
                     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
                     if (lane == 0) s_part[warp] = part;
-                    __syncthreads();
+                    consumer_sync();
+                    // g_{L-1} to global (phase B), 16-byte pieces
+                    {
+                        const int ppr = gs / 8;
+                        for (int p = tid; p < kRows * ppr; p += kT) {
+                            const int i = p / ppr, q = p - i * ppr;
+                            const int64_t o = g_elem_off(ly, e, a.Bp, row0 + i, 0) + q * 8;
+                            *reinterpret_cast<uint4*>(gbuf + o) = *reinterpret_cast<const uint4*>(Dh + i * gs + q * 8);
+                            *reinterpret_cast<uint4*>(gbuf + o + (int64_t)kChunk * gs) = *reinterpret_cast<const uint4*>(Dl + i * gs + q * 8);
+                        }
+                    }
                     float* slot_out = a.block_part + ((int64_t)e * a.nblk_max + blk) * kFusedPartStride;
                     if (tid == 0) {
                         float s = 0.f;
@@ -568,40 +741,27 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                         for (int i = 0; i < kRows; ++i) s += redbuf[(which * kRows + i) * 64 + j];
                         slot_out[4 + which * 64 + j] = s;
                     }
-                    __syncthreads();
+                    consumer_sync();
                 }
                 cur ^= 1;
             }
-            // the last dX pass produced g_0 in act[cur]: phase B needs it too
-            {
-                const FusedLayer& l0 = a.ly[0];
-                const int astride = l0.Ns;
-                const __nv_bfloat16* Ah = act_ptr(cur);
-                const __nv_bfloat16* Al = Ah + kRows * a.as_max;
-                __nv_bfloat16* gh = gbuf + l0.g_off + ((int64_t)e * a.Bp + row0) * astride;
-                __nv_bfloat16* gl = gh + (int64_t)a.E * a.Bp * astride;
-                const int pieces = kRows * astride / 8;
-                for (int p = tid; p < pieces; p += kT) {
-                    *reinterpret_cast<uint4*>(gh + p * 8) = *reinterpret_cast<const uint4*>(Ah + p * 8);
-                    *reinterpret_cast<uint4*>(gl + p * 8) = *reinterpret_cast<const uint4*>(Al + p * 8);
-                }
-            }
-            __syncthreads();
         }
         TL_SET(1);
+        TL_ALL(230);
         bar_target += G;
         member_arrive(bar);
         member_wait(bar, bar_target);
         TL_SET(2);
+        TL_ALL(290);
 
-        // ================================ phase B ================================================
+        // ================================ phase B (consumer warps) =================================
         if (tid == 0) {
             b1t *= (double)a.cfg.beta1;
             b2t *= (double)a.cfg.beta2;
             s_sc.step_size = (float)((double)a.cfg.lr / (1.0 - b1t));
             s_sc.bc2_sqrt = (float)sqrt(1.0 - b2t);
         }
-        __syncthreads();
+        consumer_sync();
         const float step_size = s_sc.step_size, inv_bc2 = 1.f / s_sc.bc2_sqrt;
         const float beta1 = a.cfg.beta1, beta2 = a.cfg.beta2, eps = a.cfg.eps;
         // torch.optim.Adam, single-tensor rule (pe_model_trainer.py:47-51): returns the new parameter
@@ -617,62 +777,73 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
             const FusedJob jb = a.jobs[slot][j];
             const int l = jb.layer;
             const FusedLayer& ly = a.ly[l];
-            const int Ns = ly.Ns, As = ly.As, ns = jb.nstrips;
-            const int HT = 16 * ns + 8;                       // h tile stride (odd multiple of 8: conflict-free)
-            const __nv_bfloat16* gh_src = gbuf + ly.g_off + (int64_t)e * a.Bp * Ns;
-            const __nv_bfloat16* gl_src = gh_src + (int64_t)a.E * a.Bp * Ns;
-            const __nv_bfloat16* hh_src = hbuf + ly.h_off + (int64_t)e * a.Bp * As + jb.strip0 * 16;
-            const __nv_bfloat16* hl_src = hh_src + (int64_t)a.E * a.Bp * As;
-            // g chunk: two bulk copies (hi, lo rows are contiguous); h tile: a few cp.async per thread
-            auto issue_b = [&](int c, int stage) {
-                const int rows = min(kChunk, nblk * kRows - c * kChunk);
-                if (tid == 0) {
-                    const uint32_t bytes = (uint32_t)rows * Ns * 2;
-                    const uint32_t fb = full0 + 8 * stage;
-                    const int64_t goff = (int64_t)c * kChunk * Ns;
-                    mbar_expect_tx(fb, 2 * bytes);
-                    bulk_g2s(smem_u32(stage_ptr(stage)), gh_src + goff, bytes, fb);
-                    bulk_g2s(smem_u32(stage_ptr(stage) + kChunk * Ns), gl_src + goff, bytes, fb);
-                }
-                __nv_bfloat16* th = act_ptr(stage);
-                __nv_bfloat16* tl = th + kChunk * HT;
-                const int ppr = 2 * ns;                        // 16-byte pieces per row
-                for (int p = tid; p < rows * ppr; p += kT) {
-                    const int r = p / ppr, q = p - r * ppr;
-                    const int64_t so = ((int64_t)c * kChunk + r) * As + q * 8;
-                    cp_async16(th + r * HT + q * 8, hh_src + so);
-                    cp_async16(tl + r * HT + q * 8, hl_src + so);
-                }
-                cp_async_commit();
-            };
-            float acc[kMaxStrips][kMaxNT][4];
+            const int Ns = ly.Ns, ns = jb.nstrips;
+            float acc[kMaxStrips][NT][4];
 #pragma unroll
             for (int s = 0; s < kMaxStrips; ++s)
 #pragma unroll
-                for (int i = 0; i < kMaxNT; ++i)
+                for (int i = 0; i < NT; ++i)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[s][i][q] = 0.f;
-            const int nchunks = (nblk * kRows + kChunk - 1) / kChunk;
             const int nt_total = ly.nt_out;
-            issue_b(0, 0);
-            for (int c = 0; c < nchunks; ++c) {
-                const int stage = c & 1;
-                if (c + 1 < nchunks) { issue_b(c + 1, stage ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-                wait_stage(stage);
-                __syncthreads();                              // everybody's cp.async pieces of the h tile
-                const __nv_bfloat16* Gh = stage_ptr(stage);
+            // g chunk: one bulk copy (both halves); h tiles [half][strip][64][16]: one 2 KB copy per strip and half
+            auto issue_b = [&](int c) {
+                if (warp != kIssuer) return;
+                const int st = producer_acquire();
+                fence_proxy_async();        // the ring doubles as epilogue scratch (generic-proxy writes)
+                const uint32_t fb = full0 + 8 * st;
+                const uint32_t gbytes = (uint32_t)kChunk * Ns * 4;
+                if (lane == 0) {
+                    mbar_expect_tx(fb, gbytes + (uint32_t)ns * 2 * (kChunk * 16 * 2));
+                    bulk_g2s(smem_u32(stage_ptr(st)), gbuf + g_elem_off(ly, e, a.Bp, c * kChunk, 0), gbytes, fb);
+                }
+                __syncwarp();
+                if (lane < 2 * ns) {
+                    const int half = lane / ns, sl = lane - half * ns;
+                    bulk_g2s(smem_u32(act_ptr(st) + (half * ns + sl) * (kChunk * 16)),
+                             hbuf + h_elem_off(ly, a.E, e, a.Bp, c * kChunk, jb.strip0 + sl, half), kChunk * 16 * 2, fb);
+                }
+            };
+            const int g_lane_off = (lane & 15) * Ns;
+            issue_b(0);
+            for (int c = 0; c < nchunksB; ++c) {
+                if (c + 1 < nchunksB) issue_b(c + 1);
+                const int st = consumer_wait();
+                const __nv_bfloat16* Gh = stage_ptr(st);
                 const __nv_bfloat16* Gl = Gh + kChunk * Ns;
-                const __nv_bfloat16* Hh = act_ptr(stage);
-                const __nv_bfloat16* Hl = Hh + kChunk * HT;
+                const __nv_bfloat16* Hh = act_ptr(st);        // [hi|lo][strip][64 rows][16], swizzled units
+                const __nv_bfloat16* Hl = Hh + ns * (kChunk * 16);
                 const int groups = min(kChunk / 16, nblk - c * (kChunk / 16));
-                const int g_lane_off = (lane & 15) * Ns;
-                const int h_lane_off = ((lane & 7) + 8 * (lane >> 4)) * HT + 8 * ((lane >> 3) & 1);
+                const int ntw = nt_total > warp ? (nt_total - warp + kWarps - 1) / kWarps : 0;
+                bool fast = false;
+                if constexpr (NT == 4) {
+                    if (groups == 4 && (ntw >= 3 || ntw <= 1)) {
+                        fast = true;
+                        if (ntw == 4) {
+                            if (ns == 4) dw_chunk4<4, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 3) dw_chunk4<3, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 2) dw_chunk4<2, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else dw_chunk4<1, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                        } else if (ntw == 3) {
+                            if (ns == 4) dw_chunk4<4, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 3) dw_chunk4<3, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 2) dw_chunk4<2, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else dw_chunk4<1, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                        } else if (ntw == 1) {                  // narrow layers (the 36-wide head): one tile per warp
+                            if (ns == 4) dw_chunk4<4, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 3) dw_chunk4<3, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 2) dw_chunk4<2, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else dw_chunk4<1, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                        }                                       // ntw == 0: nothing to do for this warp
+                    }
+                }
+                if (!fast)
 #pragma unroll
                 for (int kk = 0; kk < kChunk / 16; ++kk) {
                     if (kk >= groups) break;
-                    uint32_t bh[kMaxNT][2], bl[kMaxNT][2];
+                    uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
-                    for (int i = 0; i < kMaxNT; ++i) {
+                    for (int i = 0; i < NT; ++i) {
                         const int tile = warp + kWarps * i;
                         if (tile < nt_total) {
                             const int off = kk * 16 * Ns + g_lane_off + tile * 8;
@@ -680,24 +851,27 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                             ldsm_x2_t(bl[i], smem_u32(Gl + off));
                         }
                     }
+                    // A fragment (transposed load): matrix mi -> k half (mi & 1), row block (mi >> 1)
+                    const int hb = kk * 16 + (lane & 7) + 8 * (lane >> 4);
+                    const int h_off = hb * 16 + ((((lane >> 3) & 1) ^ ((hb >> 2) & 1)) << 3);
 #pragma unroll
                     for (int s = 0; s < kMaxStrips; ++s) {
                         if (s < ns) {
                             uint32_t ah[4], al[4];
-                            const int off = kk * 16 * HT + h_lane_off + s * 16;
-                            ldsm_x4_t(ah, smem_u32(Hh + off));
-                            ldsm_x4_t(al, smem_u32(Hl + off));
+                            ldsm_x4_t(ah, smem_u32(Hh + s * (kChunk * 16) + h_off));
+                            ldsm_x4_t(al, smem_u32(Hl + s * (kChunk * 16) + h_off));
 #pragma unroll
-                            for (int i = 0; i < kMaxNT; ++i) {
+                            for (int i = 0; i < NT; ++i) {
                                 const int tile = warp + kWarps * i;
                                 if (tile < nt_total) mma3(acc[s][i], ah, al, bh[i], bl[i]);
                             }
                         }
                     }
                 }
-                __syncthreads();
+                consumer_release(st);
             }
             TL_SET(40 + j);
+            consumer_sync();                                  // every warp is done reading the ring
             // ---- epilogue: the accumulators go through shared memory (the chunk ring is idle now) so that
             // weight decay + Adam + the pack refresh run as a row-contiguous, 16-byte-vectorised sweep over
             // parameters, moments and pack (fragment-order accesses were 32-byte scattered: the sweep was
@@ -707,7 +881,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
             for (int s = 0; s < kMaxStrips; ++s) {
                 if (s >= ns) continue;
 #pragma unroll
-                for (int i = 0; i < kMaxNT; ++i) {
+                for (int i = 0; i < NT; ++i) {
                     const int tile = warp + kWarps * i;
                     if (tile >= nt_total) continue;
                     const int n = tile * 8 + 2 * (lane & 3);
@@ -718,7 +892,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     }
                 }
             }
-            __syncthreads();
+            consumer_sync();
             {
                 float* Wp = a.params + ly.w_off + (int64_t)e * ly.K * ly.N;
                 float* W1 = a.exp_avg + ly.w_off + (int64_t)e * ly.K * ly.N;
@@ -730,38 +904,66 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 const int N = ly.N;
                 const int krows = min(16 * ns, ly.K + 1 - jb.strip0 * 16);      // rows k <= K of this job
                 const bool vec4 = (N & 3) == 0;
-                for (int r = warp; r < krows; r += kWarps) {                    // one weight row per warp
-                    const int k = jb.strip0 * 16 + r;
-                    const bool isw = k < ly.K;
-                    float* rp = isw ? Wp + (int64_t)k * N : Bq;
-                    float* r1 = isw ? W1 + (int64_t)k * N : B1;
-                    float* r2 = isw ? W2 + (int64_t)k * N : B2;
-                    const float wd = isw ? ly.wd : 0.f;
-                    __nv_bfloat16* ph = pm + pack_row_off(k, 0, ly.Kp, Ns);
-                    __nv_bfloat16* pl = pm + pack_row_off(k, 1, ly.Kp, Ns);
-                    const float* dr = dW + r * Ns;
-                    if (vec4) {
-                        for (int n = lane * 4; n < N; n += 128) {
-                            const float4 w = *reinterpret_cast<const float4*>(rp + n);
-                            float4 m1 = *reinterpret_cast<const float4*>(r1 + n);
-                            float4 m2 = *reinterpret_cast<const float4*>(r2 + n);
-                            const float4 g = *reinterpret_cast<const float4*>(dr + n);
-                            l2_part += 0.5f * wd * ((w.x * w.x + w.y * w.y) + (w.z * w.z + w.w * w.w));
+                if (vec4) {
+                    // Flat sweep, four float4 per thread and batch: the twelve loads of a batch are issued before
+                    // the first store (a row-by-row loop is one memory round trip per iteration -- the compiler
+                    // may not move loads above stores that could alias -- and the sweep was latency bound).
+                    // Parameters and both moments share one blob layout, so one offset addresses all three.
+                    const int n4 = N >> 2, total = krows * n4;
+                    const int64_t wbase = ly.w_off + (int64_t)e * ly.K * N, bbase = ly.b_off + (int64_t)e * N;
+                    for (int f0 = tid; f0 < total; f0 += 4 * kT) {
+                        float4 w[4], m1[4], m2[4];
+                        int64_t off[4];
+                        int rr[4], nn[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int f = f0 + u * kT;
+                            rr[u] = -1;
+                            if (f < total) {
+                                const int r = f / n4, n = (f - r * n4) * 4;
+                                const int k = jb.strip0 * 16 + r;
+                                rr[u] = r;
+                                nn[u] = n;
+                                off[u] = k < ly.K ? wbase + (int64_t)k * N + n : bbase + n;
+                                w[u] = *reinterpret_cast<const float4*>(a.params + off[u]);
+                                m1[u] = *reinterpret_cast<const float4*>(a.exp_avg + off[u]);
+                                m2[u] = *reinterpret_cast<const float4*>(a.exp_avg_sq + off[u]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (rr[u] < 0) continue;
+                            const int k = jb.strip0 * 16 + rr[u], n = nn[u];
+                            const float wd = k < ly.K ? ly.wd : 0.f;
+                            const float4 g = *reinterpret_cast<const float4*>(dW + rr[u] * Ns + n);
+                            const float4 wv = w[u];
+                            l2_part += 0.5f * wd * ((wv.x * wv.x + wv.y * wv.y) + (wv.z * wv.z + wv.w * wv.w));
                             float4 nw;
-                            nw.x = adam(w.x, m1.x, m2.x, fmaf(wd, w.x, g.x));
-                            nw.y = adam(w.y, m1.y, m2.y, fmaf(wd, w.y, g.y));
-                            nw.z = adam(w.z, m1.z, m2.z, fmaf(wd, w.z, g.z));
-                            nw.w = adam(w.w, m1.w, m2.w, fmaf(wd, w.w, g.w));
-                            *reinterpret_cast<float4*>(rp + n) = nw;
-                            *reinterpret_cast<float4*>(r1 + n) = m1;
-                            *reinterpret_cast<float4*>(r2 + n) = m2;
+                            nw.x = adam(wv.x, m1[u].x, m2[u].x, fmaf(wd, wv.x, g.x));
+                            nw.y = adam(wv.y, m1[u].y, m2[u].y, fmaf(wd, wv.y, g.y));
+                            nw.z = adam(wv.z, m1[u].z, m2[u].z, fmaf(wd, wv.z, g.z));
+                            nw.w = adam(wv.w, m1[u].w, m2[u].w, fmaf(wd, wv.w, g.w));
+                            *reinterpret_cast<float4*>(a.params + off[u]) = nw;
+                            *reinterpret_cast<float4*>(a.exp_avg + off[u]) = m1[u];
+                            *reinterpret_cast<float4*>(a.exp_avg_sq + off[u]) = m2[u];
                             uint2 hi, lo;
                             split2(nw.x, nw.y, hi.x, lo.x);
                             split2(nw.z, nw.w, hi.y, lo.y);
-                            *reinterpret_cast<uint2*>(ph + n) = hi;
-                            *reinterpret_cast<uint2*>(pl + n) = lo;
+                            *reinterpret_cast<uint2*>(pm + pack_row_off(k, 0, ly.Kp, Ns) + n) = hi;
+                            *reinterpret_cast<uint2*>(pm + pack_row_off(k, 1, ly.Kp, Ns) + n) = lo;
                         }
-                    } else {
+                    }
+                } else {
+                    for (int r = warp; r < krows; r += kWarps) {                // one weight row per warp
+                        const int k = jb.strip0 * 16 + r;
+                        const bool isw = k < ly.K;
+                        float* rp = isw ? Wp + (int64_t)k * N : Bq;
+                        float* r1 = isw ? W1 + (int64_t)k * N : B1;
+                        float* r2 = isw ? W2 + (int64_t)k * N : B2;
+                        const float wd = isw ? ly.wd : 0.f;
+                        __nv_bfloat16* ph = pm + pack_row_off(k, 0, ly.Kp, Ns);
+                        __nv_bfloat16* pl = pm + pack_row_off(k, 1, ly.Kp, Ns);
+                        const float* dr = dW + r * Ns;
                         for (int n = lane; n < N; n += 32) {
                             const float w = rp[n];
                             float m1 = r1[n], m2 = r2[n];
@@ -777,13 +979,13 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     }
                 }
             }
-            __syncthreads();                                  // the next job's first chunk overwrites the ring
+            consumer_sync();                                  // scratch no longer needed: the next job may refill the ring
         }
         // L2 term of the loss (mlp.py:170-178), from the pre-update weights
         for (int o = 16; o; o >>= 1) l2_part += __shfl_xor_sync(0xffffffffu, l2_part, o);
         if (lane == 0 && l2_part != 0.f) atomicAdd(lterms + 1, l2_part);
         // per-member loss and log-std bounds (pe_model.py:62-69,105-108): the row blocks' partials are
-        // summed in block order; Adam on 2 x D scalars per member + the bound term of the loss
+        // summed in a fixed order; Adam on 2 x D scalars per member + the bound term of the loss
         if (slot == G - 1 && warp < 3) {
             const float* parts = a.block_part + (int64_t)e * a.nblk_max * kFusedPartStride;
             if (warp == 0) {
@@ -818,7 +1020,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
         }
         // soft target update fused behind Adam (torch_modules/utils.py:151-155): target <- (1-tau) target + tau p
         if (a.target_params != nullptr) {
-            __syncthreads();
+            consumer_sync();
             for (int j = 0; j < njobs; ++j) {
                 const FusedJob jb = a.jobs[slot][j];
                 const FusedLayer& ly = a.ly[jb.layer];
@@ -832,6 +1034,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
             }
         }
         TL_SET(3);
+        TL_ALL(260);
         bar_target += G;
         member_arrive(bar);
         member_wait(bar, bar_target);
@@ -848,7 +1051,7 @@ static int stride_rule(int n) {           // >= roundup16(n), congruent 8 mod 16
 bool fused_train_supported(const mb_mlp_desc& d, int ne) {
     if (ne < 1 || ne > 148) return false;
     for (int l = 0; l <= d.num_layers; ++l)
-        if (d.sizes[l] > 8 * kWarps * kMaxNT) return false;          // widths up to 256
+        if (d.sizes[l] > 8 * kWarps * 4) return false;               // widths up to 256
     return true;
 }
 
@@ -883,9 +1086,9 @@ int fused_plan(const mb_mlp_desc& d, int ne, int64_t batch_size, int nsm, FusedA
         ly.pack_off = pack_elems;
         pack_elems += (int64_t)E * 2 * ly.Kp * ly.Ns;
         ly.h_off = h_elems;
-        h_elems += (int64_t)2 * E * a.Bp * ly.As;
+        h_elems += (int64_t)2 * E * a.Bp * ly.Kp;            // [hi|lo][Kp/16][E][Bp][16]
         ly.g_off = g_elems;
-        g_elems += (int64_t)2 * E * a.Bp * ly.Ns;
+        g_elems += (int64_t)2 * E * a.Bp * ly.Ns;            // [E][Bp/64][hi|lo][64][Ns]
         ns_max = ly.Ns > ns_max ? ly.Ns : ns_max;
         as_max = ly.As > as_max ? ly.As : as_max;
         as_max = ly.Ns > as_max ? ly.Ns : as_max;            // act buffers also hold g operands
@@ -897,7 +1100,7 @@ int fused_plan(const mb_mlp_desc& d, int ne, int64_t batch_size, int nsm, FusedA
     a.stage_bytes = kChunk * ns_max * 2 * 2;
     // act buffers: phase A [hi|lo] x 16 x as_max; phase B h tiles [hi|lo] x 64 x (16*kMaxStrips+8)
     int act_b = 2 * kRows * as_max * 2;
-    const int htile_b = 2 * kChunk * (16 * kMaxStrips + 8) * 2;
+    const int htile_b = 2 * kMaxStrips * kChunk * 16 * 2;        // [hi|lo][strip][64][16]
     a.act_bytes = act_b > htile_b ? act_b : htile_b;
     a.z_bytes = (L > 1 ? (L - 1) : 1) * kRows * a.z_stride * 4;
     a.head_bytes = (kRows * a.head_stride * 4 + 15) / 16 * 16;
@@ -998,7 +1201,7 @@ int launch_train_fused(const mb_mlp_desc& d, FusedArgs& a, void* ws, size_t ws_b
     int ks = 0;
     for (int l = 1; l < a.L; ++l) ks = a.ly[l].ksteps_out > ks ? a.ly[l].ksteps_out : ks;
     const int inst = ks <= 13 ? 0 : 1;
-    const void* kern = inst == 0 ? (const void*)k_train_fused<13> : (const void*)k_train_fused<16>;
+    const void* kern = inst == 0 ? (const void*)k_train_fused<13, 4> : (const void*)k_train_fused<16, 4>;
     static int configured[2][64] = {{0}};
     if (dev < 64 && configured[inst][dev] < (int)sz.smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sz.smem);
@@ -1009,7 +1212,7 @@ int launch_train_fused(const mb_mlp_desc& d, FusedArgs& a, void* ws, size_t ws_b
         configured[inst][dev] = (int)sz.smem;
     }
     void* args[] = {(void*)&a};
-    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)(a.ne * a.G)), dim3(kT), args, sz.smem, s);
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)(a.ne * a.G)), dim3(kThreads), args, sz.smem, s);
     if (e != cudaSuccess) {
         set_error("k_train_fused launch (%d CTAs, %zu B smem): %s", a.ne * a.G, sz.smem, cudaGetErrorString(e));
         return MB_ECUDA;

@@ -82,6 +82,8 @@ if __name__ == "__main__":
         check(cases.SMALL, 51, 64)
         check(cases.MBPO, 11, 256)
         check(cases.MBPO, 11, 37)
+        check(cases.MBPO, 11, 1)
+        check(cases.MBPO, 11, 600)
     if "time" in what:
         timing()
         timing(members=(0, 1))
@@ -107,6 +109,10 @@ def timeline():
     print("  phase A end %d | barrier1 passed %d | phase B end %d | barrier2 passed %d" % tuple(d[1:5] - t0))
     print("  pass starts:", list(d[8:17] - t0))
     print("  job epilogue starts %s" % (list(d[40:44] - t0)))
+    g0 = d[200:221].min()
+    print("  wall clock (ns from the first CTA's step start), member 0, per slot:")
+    for name, o in (("phase A start", 200), ("phase A end  ", 230), ("phase B start", 290), ("phase B end  ", 260)):
+        print("    %s" % name, " ".join("%6d" % v for v in (d[o:o + 21] - g0)))
     print("  per pass: start | after global copy | after pad zero | first chunk landed | chunks done | epilogue done | synced")
     for p in range(9):
         print("   pass %d:" % p, d[8 + p] - t0, list(d[60 + 6 * p:66 + 6 * p] - t0))

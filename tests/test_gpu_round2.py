@@ -35,6 +35,11 @@ def test_fused_train_step_matches_oracle_ragged(B):
     tr = _trainer(m, ignore_terminal_state=(B % 2 == 1))
     bt = _batch(900 + B, 7, B)
     diag = tr.train_from_torch_batch(bt)
+    # (to_torch shares memory with the numpy parameters and the oracle's step updates in place: take the
+    # analytic gradients of the ORIGINAL parameters first)
+    g = po.model_loss_grads(to_torch(p), *[bt[k].cpu() for k in ("observations", "actions", "deltas", "rewards",
+                                                                 "terminals")],
+                            ignore_terminal_state=(B % 2 == 1))
     pt = to_torch(p)
     opt = po.new_adam_state(pt)
     loss, el = po.train_step(pt, opt, {k: v.cpu() for k, v in bt.items()},
@@ -54,9 +59,6 @@ def test_fused_train_step_matches_oracle_ragged(B):
         worst = max(worst, float(np.abs(v.cpu().numpy() - ref[k]).max()))
     assert worst <= 2.0e-3 + 1e-9, worst                      # |update| <= lr per element, both sides
     # exp_avg after one step = 0.1 * grad: norm-wise 1e-3 against the oracle's analytic gradients
-    g = po.model_loss_grads(to_torch(p), *[bt[k].cpu() for k in ("observations", "actions", "deltas", "rewards",
-                                                                 "terminals")],
-                            ignore_terminal_state=(B % 2 == 1))
     for l in range(5):
         for e in range(7):
             got = msd["module.net.%d.weight_net%d" % (2 * l, e)].cpu().numpy() / 0.1
