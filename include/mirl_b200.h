@@ -274,6 +274,20 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
                          float* value, float* atoms, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- critic update: DDPGAgent.compute_qf_loss (ddpg_agent.py:138-149: F.mse_loss of the [E][B][out]
+ * ensemble prediction against the expanded target, optional clip_error) + qf_optimizer.step (torch.optim.Adam,
+ * ddpg_agent.py:82-86) + the soft target update ptu.soft_update_from_to (torch_modules/utils.py:151-155), as ONE
+ * persistent launch (the kernel of mb_pe_train_steps with an MSE head): forward, loss, backward, Adam and
+ * target <- (1 - tau) target + tau params.  obs/act [B][.] are shared by the members; q_target [B][out].
+ * target_params (same blob layout) may be NULL (no target update this step, sac_agent.py:165-166).
+ * ensemble_loss[E] = each member's share of the loss; loss_terms[0] = the loss.  Layer widths up to 256. */
+size_t mb_critic_train_workspace_bytes(const mb_mlp_desc* d, int64_t B);
+int mb_critic_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, float* exp_avg_sq,
+                         int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                         const float* obs, const float* act, int obs_dim, int act_dim, const float* q_target,
+                         int64_t B, float clip_error, float* target_params, float tau, float* ensemble_loss,
+                         float* loss_terms, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- tcgen05 operand pack: bf16 hi/lo split of every member's weights in the UMMA
  * shared-memory layout the rollout kernel streams (rebuild after the weights change). */
 size_t mb_pe_tc_pack_bytes(const mb_pe_model* m);

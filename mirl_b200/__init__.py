@@ -12,6 +12,8 @@ B200MOPOCollector     MOPOCollector                                mirl/agents/m
 B200EnsembleQValue    EnsembleQValue                               mirl/values/ensemble_value.py
 B200TQCQValue         TQCQValue                                    mirl/values/distributional_value.py
 B200DevicePool        SimplePool (imagined-data pool, in HBM)      mirl/pools/simple_pool.py
+B200ExtraFieldPool    ExtraFieldPool (real-data pool, in HBM)      mirl/pools/extra_field_pool.py
+B200CriticTrainer     critic half of SACAgent.train_from_torch_batch  mirl/agents/sac_agent.py:160-166
 ====================  ===========================================  ============================
 
 All computation goes through ``libmirl_b200.so`` (``include/mirl_b200.h``); there is no PyTorch
@@ -19,9 +21,9 @@ or CPU fallback -- calls raise if the library is missing or the tensors are not 
 """
 from .pe_model import B200PEModel                      # noqa: F401
 from .pe_model_trainer import B200PEModelTrainer       # noqa: F401
-from .values import B200EnsembleQValue, B200TQCQValue  # noqa: F401
+from .values import B200CriticTrainer, B200EnsembleQValue, B200TQCQValue  # noqa: F401
 from .collectors import B200MBPOCollector, B200MOPOCollector  # noqa: F401
-from .pools import B200DevicePool                      # noqa: F401
+from .pools import B200DevicePool, B200ExtraFieldPool  # noqa: F401
 
-__all__ = ["B200PEModel", "B200PEModelTrainer", "B200EnsembleQValue", "B200TQCQValue",
-           "B200MBPOCollector", "B200MOPOCollector", "B200DevicePool"]
+__all__ = ["B200PEModel", "B200PEModelTrainer", "B200EnsembleQValue", "B200TQCQValue", "B200CriticTrainer",
+           "B200MBPOCollector", "B200MOPOCollector", "B200DevicePool", "B200ExtraFieldPool"]

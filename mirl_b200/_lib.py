@@ -74,6 +74,9 @@ SIGNATURES = {
                                   c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "mb_pe_loss_grads": (c_int, [POINTER(PeModel), POINTER(TrainCfg), P, P, P, P, P, c_int64, P,
                                  P, P, P, c_size_t, P]),
+    "mb_critic_train_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
+    "mb_critic_train_step": (c_int, [POINTER(MlpDesc), P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P,
+                                     c_int, c_int, P, c_int64, c_float, P, c_float, P, P, P, c_size_t, P]),
     "mb_critic_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
     "mb_critic_forward": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64, P, P, c_size_t, P]),
     "mb_critic_redq_target": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64,

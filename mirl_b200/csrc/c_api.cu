@@ -424,6 +424,64 @@ int mb_pe_loss_grads(const mb_pe_model* m, const mb_train_cfg* cfg, const float*
                         workspace_bytes, stream);
 }
 
+/* ---- critic update: DDPGAgent.compute_qf_loss + qf_optimizer.step + soft target update ------------------ */
+size_t mb_critic_train_workspace_bytes(const mb_mlp_desc* d, int64_t B) {
+    if (!d || !fused_train_supported(*d, 1)) return 0;
+    return fused_train_workspace_bytes(*d, B < 1 ? 1 : B);
+}
+
+int mb_critic_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, float* exp_avg_sq,
+                         int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                         const float* obs, const float* act, int obs_dim, int act_dim, const float* q_target,
+                         int64_t B, float clip_error, float* target_params, float tau, float* ensemble_loss,
+                         float* loss_terms, void* workspace, size_t workspace_bytes, void* stream) {
+    const char* who = "mb_critic_train_step";
+    int rc = validate_desc(d, who);
+    if (rc) return rc;
+    MB_CHECK_ARG(obs_dim >= 1 && act_dim >= 0 && d->sizes[0] == obs_dim + act_dim, "%s: mlp input %d != obs+act %d", who,
+                 d->sizes[0], obs_dim + act_dim);
+    MB_CHECK_ARG(B >= 1 && B < (int64_t)1 << 20, "%s: B out of range", who);
+    MB_CHECK_ARG(params && exp_avg && exp_avg_sq && obs && act && q_target && ensemble_loss && loss_terms,
+                 "%s: null tensor", who);
+    MB_CHECK_ARG(adam_steps_done >= 0, "%s: adam_steps_done < 0", who);
+    if (!fused_train_supported(*d, d->ensemble_size)) {
+        set_error("%s: layer widths above 256 (or more members than SMs) are not covered by the fused kernel", who);
+        return MB_EUNSUPPORTED;
+    }
+    FusedArgs a{};
+    a.e0 = 0;
+    a.ne = d->ensemble_size;
+    a.O = obs_dim;
+    a.A = act_dim;
+    a.D = 0;
+    a.head_kind = FUSED_HEAD_MSE;
+    a.E_total = d->ensemble_size;
+    a.norm = nullptr;
+    a.params = params;
+    a.exp_avg = exp_avg;
+    a.exp_avg_sq = exp_avg_sq;
+    a.target_params = target_params;
+    a.tau = tau;
+    a.target = q_target;
+    a.clip_error = clip_error;
+    a.cfg = mb_train_cfg{};
+    a.cfg.lr = lr; a.cfg.beta1 = beta1; a.cfg.beta2 = beta2; a.cfg.eps = eps;
+    a.beta1_pow0 = pow((double)beta1, (double)adam_steps_done);
+    a.beta2_pow0 = pow((double)beta2, (double)adam_steps_done);
+    for (int l = 0; l < d->num_layers; ++l) a.ly[l].wd = 0.f;
+    a.obs = obs; a.actn = act; a.delta = nullptr; a.reward = nullptr; a.done = nullptr;
+    a.index = nullptr;
+    a.index_stride = 0;
+    a.per_member_rows = 0;                 // one batch shared by all members (ensemble_value.py:59-63,75-77)
+    a.nsteps = 1;
+    a.first_step = 0;
+    a.train_length = B;
+    a.batch_size = B;
+    a.ensemble_loss = ensemble_loss;
+    a.loss_terms = loss_terms;
+    return launch_train_fused(*d, a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 static int check_critic(const char* who, const mb_mlp_desc* d, const float* params, const float* obs,
                         const float* act, int O, int A, int64_t B) {
     int rc = validate_desc(d, who);

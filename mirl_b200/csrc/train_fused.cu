@@ -708,7 +708,8 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                             const int b = row0 + i;
                             if (b >= B) continue;
                             const float q = headbuf[i * a.head_stride + j];
-                            const float diff = q - a.target[(int64_t)b * N + j];
+                            float diff = q - a.target[(int64_t)b * N + j];
+                            if (a.clip_error > 0.f) diff = fminf(fmaxf(diff, -a.clip_error), a.clip_error);
                             part += diff * diff * wgt;
                             const float g = 2.f * diff * wgt;
                             const __nv_bfloat16 gh = __float2bfloat16(g);

@@ -44,6 +44,7 @@ struct FusedArgs {
     int64_t maxls_off, minls_off;
     const float* obs; const float* actn; const float* delta; const float* reward; const float* done;
     const float* target;           // MSE head: [B][N] shared by the members
+    float clip_error;              // MSE head: > 0 clamps (target - q) to +-clip_error (ddpg_agent.py:142-146)
     const int64_t* index;          // bootstrap index table [E][index_stride] or nullptr
     const float* norm;             // normaliser statistics or nullptr
     float* params; float* exp_avg; float* exp_avg_sq;

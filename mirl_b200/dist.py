@@ -180,3 +180,112 @@ class PeerPools:
             self.local = None
             self._lib.check(L.mb_peer_pool_free(self._own))
             self._own = None
+
+
+class ShardedPool:
+    """Rank-sharded model pool ("keep the pool sharded ... with local sampling").
+
+    ``PeerPools`` replicates every generated transition into all N pools, which costs every GPU
+    (N-1) x 176 B of NVLink ingress per transition and caps the aggregate rollout rate at one GPU's ingress
+    bandwidth whatever N is (measured: 3.98 G transitions/s at N = 8).  Here each rank keeps ONLY the rows
+    it generated (its shard is still an IPC-exported buffer every peer maps), so a rollout step moves
+    nothing over NVLink, and the exchange happens at SAMPLING time instead: a batch is drawn as global row
+    indices -- the same on every rank, from a generator the ranks seed identically -- and the rows another
+    rank owns are read through the mapping by the gather kernel itself (a 256-row SAC batch is 45 KB).
+
+    The global index space is the one a replicated pool filled by an all-gather would have: rows are
+    appended in BLOCKS (one per rollout step); inside a block rank 0's rows come first, then rank 1's, ...
+    (``all_gather_rows`` order).  So a seeded ``random_batch_rows`` returns exactly the rows the replicated pool
+    returns (tests/test_gpu_multi.py).  Append-only; ``reset()`` empties it (MBPO refills the imagined pool
+    every ``imagine_freq`` loops)."""
+
+    def __init__(self, rows_per_rank, width, device=None, group=None, seed=0):
+        import numpy as np
+        self._np = np
+        self.peers = PeerPools(rows_per_rank, width, device=device, group=group)
+        self.rank, self.world = self.peers.rank, self.peers.world
+        self.device, self.width, self.capacity = self.peers.device, int(width), int(rows_per_rank)
+        self.group = group
+        self.local = self.peers.local
+        # peer shards as tensors on THIS device (loads go over NVLink)
+        self.views = [self.local if r == self.rank else
+                      torch.as_tensor(_RawCudaArray(self.peers.ptrs[r], (self.capacity, self.width)), device=self.device)
+                      for r in range(self.world)]
+        self.rng = np.random.RandomState(seed)        # identical on every rank: the ranks' global streams drift
+        self.reset()
+
+    def reset(self):
+        self.used = 0                                 # local rows in use
+        self._starts = [0]                            # global start of every block (+ total at the end)
+        self._counts = []                             # per block: rows per rank
+        self._local0 = []                             # per block: first local row on every rank
+
+    def __len__(self):
+        return self._starts[-1]
+
+    def reserve(self, n_local, counts=None):
+        """Claim ``n_local`` rows of this rank's shard for a block whose rows the caller writes in place
+        (``step_rows(..., dest=pool.local, row_offset=...)``).  ``counts`` = rows of every rank in this block
+        when they are known (fixed-size rollouts); otherwise they are all-gathered (8 bytes per rank).
+        Every rank must call this for every block.  Returns the local row offset."""
+        np = self._np
+        if counts is None:
+            if self.world > 1:
+                c = torch.tensor([n_local], device=self.device, dtype=torch.int64)
+                out = torch.empty(self.world, device=self.device, dtype=torch.int64)
+                dist.all_gather_into_tensor(out, c, group=self.group)
+                counts = out.tolist()
+            else:
+                counts = [n_local]
+        assert counts[self.rank] == n_local
+        if self.used + n_local > self.capacity:
+            raise RuntimeError("ShardedPool: shard full (%d + %d > %d rows)" % (self.used, n_local, self.capacity))
+        prev = self._local0[-1] + np.asarray(self._counts[-1]) if self._counts else np.zeros(self.world, dtype=np.int64)
+        self._local0.append(np.asarray(prev, dtype=np.int64))
+        self._counts.append(np.asarray(counts, dtype=np.int64))
+        self._starts.append(self._starts[-1] + int(sum(counts)))
+        start = self.used
+        self.used += n_local
+        return start
+
+    def locate(self, gidx):
+        """Global row indices -> (owner rank, local row) arrays."""
+        np = self._np
+        gidx = np.asarray(gidx, dtype=np.int64)
+        starts = np.asarray(self._starts, dtype=np.int64)
+        blk = np.searchsorted(starts, gidx, side="right") - 1
+        off = gidx - starts[blk]
+        counts = np.stack(self._counts)[blk]                         # [n, world]
+        cum = np.cumsum(counts, axis=1)
+        owner = (off[:, None] >= cum).sum(1)
+        before = np.where(owner > 0, cum[np.arange(len(gidx)), np.maximum(owner - 1, 0)], 0)
+        local = np.stack(self._local0)[blk, owner] + (off - before)
+        return owner, local
+
+    def fence(self):
+        """Every rank's rollout kernels issued so far have finished writing their shards (needed before
+        a rank samples rows another rank generated): one stream-ordered 4-byte all-reduce."""
+        self.peers.fence()
+
+    def random_batch_index(self, batch_size):
+        return self.rng.randint(0, len(self), batch_size)           # pools/utils.py:38 on the shared generator
+
+    def rows(self, gidx):
+        """Gather rows by global index: local rows from HBM, the others through the peer mappings."""
+        owner, local = self.locate(gidx)
+        out = torch.empty(len(owner), self.width, device=self.device)
+        for r in range(self.world):
+            sel = self._np.nonzero(owner == r)[0]
+            if len(sel) == 0:
+                continue
+            li = torch.from_numpy(local[sel]).to(self.device)
+            out[torch.from_numpy(sel).to(self.device)] = self.views[r].index_select(0, li)
+        return out
+
+    def random_batch_rows(self, batch_size):
+        return self.rows(self.random_batch_index(batch_size))
+
+    def close(self):
+        self.views = None
+        self.local = None
+        self.peers.close()

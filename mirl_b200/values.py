@@ -6,11 +6,15 @@ random-subset target) and ``B200TQCQValue`` mirrors ``TQCQValue``
 (``np.random.choice`` for the member subset) are made exactly like the reference, in the same
 order, so a seeded run consumes the global NumPy stream identically.
 
-These classes are forward-only: they serve the TARGET network (``qf_target``), which the agents
-evaluate under ``torch.no_grad()`` (sac_agent.py:73-86, tqc_agent.py:41-57).  ``parameters()``
-yields per-member views in the reference's parameter order, so
-``ptu.soft_update_from_to(qf, qf_target, tau)`` (torch_modules/utils.py:151-155) works with a
-reference ``qf`` as the source.
+``value()`` is forward-only (the target network ``qf_target`` is evaluated under
+``torch.no_grad()``, sac_agent.py:73-86, tqc_agent.py:41-57).  ``parameters()`` yields per-member
+views in the reference's parameter order, so ``ptu.soft_update_from_to(qf, qf_target, tau)``
+(torch_modules/utils.py:151-155) works with a reference ``qf`` as the source.
+
+``B200CriticTrainer`` is the critic half of ``SACAgent.train_from_torch_batch`` (sac_agent.py:160-166) for
+a ``B200EnsembleQValue`` pair: ``compute_qf_loss`` (ddpg_agent.py:138-149) + ``qf_optimizer.step()`` +
+``_update_target`` (ddpg_agent.py:121-125) as ONE persistent kernel launch --
+REDQ runs 20 of these per environment step.
 """
 import ctypes
 
@@ -243,3 +247,76 @@ class B200TQCQValue(_CriticBase):
         n_drop, n_atom = self._n_drop(number_drop, percentage_drop)
         td = dict(rewards=rewards, terminals=terminals, log_prob=log_prob, alpha=alpha, discount=discount)
         return self._atoms(obs2, act2, n_drop, n_atom, td)[1]
+
+
+class B200CriticTrainer(object):
+    """Fused critic update for REDQ / SAC ensembles: forward over all E critics, ``F.mse_loss`` against
+    the expanded target (optional ``clip_error``), backward, ``torch.optim.Adam`` and the soft target
+    update, in one launch (``mb_critic_train_step``; the reference issues ~300 ATen calls plus a Python loop
+    over 6*E parameter tensors, torch_modules/utils.py:151-155).
+
+    ``qf`` and ``qf_target`` are ``B200EnsembleQValue`` of the same shape; ``qf_lr``, ``soft_target_tau``,
+    ``target_update_freq`` and ``clip_error`` are the ``DDPGAgent`` arguments (ddpg_agent.py:44-60)."""
+
+    def __init__(self, qf, qf_target=None, qf_lr=3e-4, soft_target_tau=5e-3, target_update_freq=1,
+                 clip_error=None, optimizer_class="Adam", optimizer_kwargs={}):
+        if optimizer_class not in ("Adam", torch.optim.Adam):
+            raise NotImplementedError("the fused critic update implements torch.optim.Adam only")
+        extra = set(optimizer_kwargs) - {"betas", "eps"}
+        if extra:
+            raise NotImplementedError("Adam options %s" % sorted(extra))
+        self.qf, self.qf_target = qf, qf_target
+        if qf_target is not None:
+            assert tuple(qf.module.flat.shape) == tuple(qf_target.module.flat.shape)
+        self.qf_lr = qf_lr
+        self.betas = tuple(optimizer_kwargs.get("betas", (0.9, 0.999)))
+        self.eps = optimizer_kwargs.get("eps", 1e-8)
+        self.soft_target_tau = soft_target_tau
+        self.target_update_freq = target_update_freq
+        self.clip_error = clip_error
+        self.exp_avg = torch.zeros_like(qf.module.flat.data)
+        self.exp_avg_sq = torch.zeros_like(qf.module.flat.data)
+        self.num_train_steps = 0
+        self._ws = None
+
+    def supported(self):
+        return _lib.lib().mb_critic_train_workspace_bytes(ctypes.byref(self.qf.module.desc), 1) > 0
+
+    def update_async(self, obs, actions, q_target):
+        """One critic update; returns device tensors ``(qf_loss [], ensemble_loss [E])`` without
+        synchronising.  ``q_target`` is ``[B, out]`` (``compute_q_target``'s result, detached)."""
+        qf, L = self.qf, _lib.lib()
+        dev = qf.device
+        mod = qf.module
+        obs, actions, q_target = (_lib.f32(t, dev) for t in (obs, actions, q_target))
+        B = obs.shape[0]
+        assert obs.dim() == 2 and q_target.shape == (B, mod.output_size)
+        if self.exp_avg.device != dev:
+            self.exp_avg, self.exp_avg_sq = self.exp_avg.to(dev), self.exp_avg_sq.to(dev)
+        need = L.mb_critic_train_workspace_bytes(ctypes.byref(mod.desc), B)
+        if need == 0:
+            raise NotImplementedError("the fused critic update covers layer widths up to 256")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        el = torch.zeros(mod.ensemble_size, device=dev)
+        terms = torch.zeros(3, device=dev)
+        tgt = None
+        if self.qf_target is not None and self.num_train_steps % self.target_update_freq == 0:
+            tgt = self.qf_target.module.flat.data
+        with torch.cuda.device(dev):
+            _lib.check(L.mb_critic_train_step(
+                ctypes.byref(mod.desc), _lib.ptr(mod.flat.data), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                self.num_train_steps, float(self.qf_lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                _lib.ptr(obs), _lib.ptr(actions), qf.observation_shape[0], qf.action_shape[0], _lib.ptr(q_target), B,
+                float(self.clip_error or 0.0), _lib.ptr(tgt), float(self.soft_target_tau), _lib.ptr(el), _lib.ptr(terms),
+                _lib.ptr(self._ws), self._ws.numel(), _lib.stream(dev)))
+        self.num_train_steps += 1
+        mod.mark_weights_changed()
+        if tgt is not None:
+            self.qf_target.module.mark_weights_changed()
+        return terms[0], el
+
+    def update(self, obs, actions, q_target):
+        """-> ``{'qf/loss': float}`` (ddpg_agent.py:155), synchronising like the reference."""
+        loss, _ = self.update_async(obs, actions, q_target)
+        return {"qf/loss": float(loss.item())}

@@ -78,3 +78,40 @@ def tqc_atoms(W, b, obs, act, number_drop=None, percentage_drop=None, activation
         atoms, _ = torch.sort(atoms, dim=-1)
         atoms = atoms[..., :-number_drop]
     return torch.mean(atoms, dim=-1, keepdim=True), atoms
+
+
+def critic_update(W, b, opt, target_W, target_b, obs, act, q_target, lr=3e-4, tau=5e-3, clip_error=None,
+                  activation="relu"):
+    """Critic half of SACAgent.train_from_torch_batch (mirl/agents/sac_agent.py:160-166):
+    DDPGAgent.compute_qf_loss (ddpg_agent.py:138-149: F.mse_loss of the [E,B,out] ensemble prediction against
+    the expanded target, optional clip_error), hand-written backward, torch.optim.Adam (ddpg_agent.py:82-86)
+    and ptu.soft_update_from_to (torch_modules/utils.py:151-155).  Mutates W, b, opt and the target lists;
+    ``opt = {"step": 0, "m": [...], "v": [...]}`` over ``W + b``.  Returns the loss."""
+    from oracle.pe_oracle import adam_update
+    assert activation == "relu"
+    L = len(W)
+    x = torch.cat([obs, act], -1).unsqueeze(0).expand(W[0].shape[0], -1, -1)
+    hs, zs = [x], []
+    for l in range(L):
+        z = hs[-1].matmul(W[l]) + b[l]
+        zs.append(z)
+        if l < L - 1:
+            hs.append(torch.relu(z))
+    q = zs[-1]
+    diff = q - q_target.unsqueeze(0)
+    if clip_error is not None and clip_error > 0:
+        diff = torch.clamp(diff, -clip_error, clip_error)
+    loss = (diff * diff).mean()
+    g = 2.0 * diff / diff.numel()
+    gW, gb = [None] * L, [None] * L
+    for l in range(L - 1, -1, -1):
+        gW[l] = hs[l].transpose(1, 2).matmul(g)
+        gb[l] = g.sum(1, keepdim=True)
+        if l > 0:
+            g = g.matmul(W[l].transpose(1, 2)) * (zs[l - 1] > 0).float()
+    opt["step"] += 1
+    for t, gr, m, v in zip(list(W) + list(b), gW + gb, opt["m"], opt["v"]):
+        adam_update(t, gr, m, v, opt["step"], lr=lr)
+    for tp, p in zip(list(target_W) + list(target_b), list(W) + list(b)):
+        tp.copy_(tp * (1.0 - tau) + p * tau)
+    return loss

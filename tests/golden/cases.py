@@ -192,3 +192,9 @@ COLLECT = {
                  batch_size=200, depth=3, save_n=2, penalty_coef=0.7, penalty_type="total_var",
                  loss=[0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4, 0.05, 0.8, 0.6]),
 }
+
+
+def critic_q_target(x):
+    """Synthetic TD target ``[B,1]`` for the critic-update fixture (the real one comes from
+    SACAgent.compute_q_target, which has its own fixture)."""
+    return (3.0 * x["rewards"] + x["log_prob"]).astype(np.float32)

@@ -457,6 +457,51 @@ def gen_extrapool():
     np.savez(os.path.join(HERE, "extra_pool.npz"), **out)
 
 
+def gen_critic_update():
+    """Critic half of SACAgent.train_from_torch_batch (sac_agent.py:160-166): DDPGAgent.compute_qf_loss
+    (ddpg_agent.py:138-149) called on the reference class, torch.optim.Adam(qf.parameters(), lr=3e-4)
+    (ddpg_agent.py:82-86) and ptu.soft_update_from_to(qf, qf_target, 5e-3) -- ten REDQ-shaped updates
+    (10 critics, 2x256 relu, batch 256) plus one with clip_error."""
+    import types
+    import mirl.torch_modules.utils as ptu
+    from mirl.agents.ddpg_agent import DDPGAgent
+    from mirl.values.ensemble_value import EnsembleQValue
+    env = ref_shim.FakeEnv()
+    c = cases.REDQ
+    sizes = [23] + c["hidden"] + [c["out"]]
+
+    def build(seed):
+        q = EnsembleQValue(env, ensemble_size=c["E"], hidden_layers=list(c["hidden"]), activation=c["act"])
+        W, b = cases.mlp_params(seed, c["E"], sizes)
+        q.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(W, b).items()})
+        return q
+    for tag, clip in (("plain", None), ("clip", 0.5)):
+        qf, qt = build(71), build(171)
+        opt = torch.optim.Adam(qf.parameters(), lr=3e-4)
+        stub = types.SimpleNamespace(qf=qf, clip_error=clip, _log_q_info=lambda *a: {})
+        out = {"loss": []}
+        steps = 10 if clip is None else 3
+        for s_ in range(steps):
+            x = cases.critic_inputs(720 + s_, 256)
+            q_target = T(cases.critic_q_target(x))
+            loss, _ = DDPGAgent.compute_qf_loss(stub, T(x["obs"]), T(x["act"]), q_target)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            ptu.soft_update_from_to(qf, qt, 5e-3)
+            out["loss"].append(float(loss))
+            if s_ + 1 in (1, steps):
+                names = [n for n, _ in qf.named_parameters()]
+                out["param_proj_%d" % (s_ + 1)] = np.stack([proj(p, 5000 + i) for i, p in enumerate(qf.parameters())])
+                out["target_proj_%d" % (s_ + 1)] = np.stack([proj(p, 6000 + i) for i, p in enumerate(qt.parameters())])
+                out["m_proj_%d" % (s_ + 1)] = np.stack([proj(opt.state[p]["exp_avg"], 7000 + i)
+                                                         for i, p in enumerate(qf.parameters())])
+        out["loss"] = np.array(out["loss"], dtype=np.float64)
+        out["names"] = np.array(names)
+        np.savez(os.path.join(HERE, "critic_update_%s.npz" % tag), **out)
+        print(tag, out["loss"])
+
+
 def main():
     ref_shim.install()
     torch.set_num_threads(1)        # bitwise-stable reductions for the fixtures
@@ -465,7 +510,7 @@ def main():
         globals()["gen_" + only]()
     else:
         gen_forward(); gen_step(); gen_dist(); gen_loss(); gen_train(); gen_critics(); gen_keys(); gen_pool()
-        gen_trainloop(); gen_collect(); gen_extrapool()
+        gen_trainloop(); gen_collect(); gen_extrapool(); gen_critic_update()
     for f in sorted(os.listdir(HERE)):
         if f.endswith((".npz", ".json")):
             print("%8d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))

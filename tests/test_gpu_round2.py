@@ -391,3 +391,35 @@ def test_rollout_100k_rows_matches_oracle(kernel):
     assert_close(r, rr, what="reward")
     out, inside = done_guard_mismatches("hopper", rno.numpy(), rd.numpy(), d.cpu().numpy())
     assert out == 0 and inside <= 20
+
+
+# ---- N3: fused critic update ------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,clip,steps", [("plain", None, 10), ("clip", 0.5, 3)])
+def test_fused_critic_update_matches_reference(tag, clip, steps):
+    """B200CriticTrainer against the reference's DDPGAgent.compute_qf_loss + torch.optim.Adam +
+    soft_update_from_to run (REDQ shape: 10 critics, 2x256 relu, batch 256): loss curve, parameters, first
+    moments and the soft-updated target network."""
+    import mirl_b200
+    from tests.helpers_gpu import make_critic
+    g = golden("critic_update_%s.npz" % tag)
+    qf, _ = make_critic("redq", 71)
+    qt, _ = make_critic("redq", 171)
+    tr = mirl_b200.B200CriticTrainer(qf, qt, qf_lr=3e-4, soft_target_tau=5e-3, clip_error=clip)
+    assert tr.supported()
+    for s_ in range(steps):
+        x = cases.critic_inputs(720 + s_, 256)
+        info = tr.update(T(x["obs"], "cuda"), T(x["act"], "cuda"), T(cases.critic_q_target(x), "cuda"))
+        assert abs(info["qf/loss"] - g["loss"][s_]) <= 1e-3 * abs(g["loss"][s_]), (s_, info, g["loss"][s_])
+        if s_ + 1 in (1, steps):
+            msd = qf.module.reference_state_dict("module.", flat=tr.exp_avg)
+            for i, (name, p, pt) in enumerate(zip(g["names"], qf.parameters(), qt.parameters())):
+                name = str(name)
+                n = p.numel()
+                got, ref = proj(p, 5000 + i), g["param_proj_%d" % (s_ + 1)][i]
+                assert abs(got[0] - ref[0]) <= 3e-4 * (s_ + 1) * 0.05 * np.sqrt(n) + 1e-4 * ref[0], (name, got, ref)
+                got, ref = proj(pt, 6000 + i), g["target_proj_%d" % (s_ + 1)][i]
+                assert abs(got[0] - ref[0]) <= 1e-4 * ref[0] + 1e-6, ("target", name, got, ref)
+                assert abs(got[1] - ref[1]) <= 1e-3 * ref[0] + 1e-6, ("target", name, got, ref)
+                gm, rm = proj(msd[name], 7000 + i), g["m_proj_%d" % (s_ + 1)][i]
+                # (a [1,1] bias moment is one signed sum over the batch: cancellation, so an absolute floor)
+                assert abs(gm[0] - rm[0]) <= 2e-3 * rm[0] + 2e-5, ("exp_avg", name, gm, rm)
