@@ -7,21 +7,29 @@ A "step" is one model rollout of HORIZON steps over ROWS start states per GPU (H
 synthetic data: obs 17, act 6, 7 members / 5 elites, 4x200 swish), i.e. ROWS*HORIZON transitions
 per GPU per step; actions are pre-generated U(-1,1) (the reference's own
 ``COMPOCollector(random_sample=True)`` mode), the done function is cheetah's.  Work per GPU is
-fixed as N grows ("scaling": "weak"); at N > 1 every rank also all-gathers the transitions it
-generated into a replicated pool buffer (NCCL), inside the timed region.
+fixed as N grows ("scaling": "weak").  At N > 1 the model pool is RANK-SHARDED (``dist.ShardedPool``):
+every rank's rollout kernel writes the transitions it generates into its own shard, nothing crosses
+NVLink in the timed region, and a sampler reads remote rows through the peer mappings (checked after the
+timed region against an NCCL all-gather: ``shard_check``).
 
-``value``   transitions/s, inputs resident in HBM, CUDA-event timed, max over ranks.
-``e2e``     same metric through the public API (``B200PEModel.step``) from pinned HOST buffers:
-            H2D of start states / actions / member indices and D2H of the generated
-            transitions are inside the timed region, as are the NumPy member draw and the
-            torch noise draw the reference also performs.
-``roofline`` the rollout kernel alone (events inside the C ABI), algorithmic FLOPs / launch.
-``cpu_baseline`` the CPU oracle (restatement of the reference's op sequence: all E members for
-            every row) on this box's host cores, bounded sample.
-``--impl reference`` times only that CPU arm (the reference itself is Python and cannot travel
-            to the GPU box; the oracle is pinned to it by tests/golden).
+``value``   transitions/s, inputs resident in HBM, CUDA-event timed, max over ranks; pool rows are written in
+            batch order (the reference pool's row order).  ``value_bucket_order`` = the same with rows grouped by
+            drawn member (a permutation); ``sustained`` = the headline loop run for >= 1 s.
+``e2e``     same metric through the public API (``B200PEModel.step_rows``) from pinned HOST buffers:
+            H2D of start states / actions and D2H of the generated transitions are inside the timed region,
+            as are the member draw (NumPy stream) and the torch noise draw the reference also performs.
+``roofline`` the rollout kernel alone (events inside the C ABI), algorithmic FLOPs / launch, against the
+            BURST bf16 peak (an isolated kernel); ``roofline.secondary`` = model-train, critic-update, REDQ,
+            TQC and MOPO entries, each with its own kernel time and fraction.
+``cpu_baseline`` the reference's own ``PEModel.step`` (``kind: reference``; the oracle port only when no
+            reference tree is present) on this box's host cores, bounded sample; plus ``train`` / ``redq`` /
+            ``tqc`` CPU figures and ``torch_eager`` = the reference modules as eager PyTorch on this B200.
+``--impl reference`` times only the CPU arm: reference ``PEModel.step`` over 1e5 states per step.
 """
 import argparse
+import warnings
+
+warnings.filterwarnings("ignore", category=SyntaxWarning)     # the reference tree predates Python 3.12
 import json
 import os
 import subprocess
@@ -49,8 +57,9 @@ def peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return {"tensor": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"], "src": "measured (sustained)"}
-    return {"tensor": 1400.0, "hbm": 6650.0, "src": "fallback"}
+        return {"tensor": d["bf16_tflops"], "tensor_sustained": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"],
+                "src": "MEASURED_PEAKS.json (burst bf16: kernels are timed alone)"}
+    return {"tensor": 1650.0, "tensor_sustained": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -107,69 +116,229 @@ def build_model(device):
     return m, p
 
 
-def cpu_arm(steps, warmup, threads=None):
-    """Reference CPU path (oracle restatement, kind 'port'): PEModel.step over a bounded sample."""
-    from oracle import pe_oracle as po
+def _reference():
+    """The reference tree, importable (see oracle/ref_shim.py), or None."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return None
+    ref_shim.install()
+    return ref_shim
+
+
+def ref_pe_model(device="cpu"):
+    """Reference PEModel (mirl/agents/mbpo/pe_model.py:191) with the bench's deterministic weights."""
     from tests.golden import cases
-    from tests.util import T, to_torch
+    shim = _reference()
+    import mirl.torch_modules.utils as ptu
+    from mirl.agents.mbpo.pe_model import PEModel
+    ptu.set_gpu_mode(device != "cpu")
+    cfg = cases.MBPO
+    m = PEModel(shim.FakeEnv("cheetah"), known=["done"], ensemble_size=cfg["E"], elite_number=cfg["elites"],
+                hidden_layers=list(cfg["hidden"]), activation=cfg["act"], connection="simple", reward_coef=1,
+                bound_reg_coef=2e-2, weight_decay=list(cases.WEIGHT_DECAY))
+    m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v))
+                       for k, v in cases.pe_state_dict(cases.pe_params(11, cfg)).items()})
+    m.remember_loss(LOSS_VEC7)
+    return m.to(ptu.device), ptu
+
+
+def cpu_arm(steps, warmup, threads=None, rows=None):
+    """CPU arm: the reference's own PEModel.step (kind 'reference') over a bounded sample, all host threads;
+    the oracle port (kind 'port') only when no reference tree is present.  Both draw the member indices and the
+    noise inside the step (pe_model.py:169,176), as the reference always does."""
+    from tests.golden import cases
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    p = to_torch(cases.pe_params(11, cases.MBPO))
-    _, elites = po.rank_elites(LOSS_VEC7, 7, 5)
-    B = CPU_SAMPLE_ROWS
+    B = rows or CPU_SAMPLE_ROWS
     o, a = cases.rollout_inputs(3, B)
-    o, a = T(o), T(a)
+    o, a = torch.from_numpy(o), torch.from_numpy(a)
     times = []
-    with torch.no_grad():
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            idx = torch.from_numpy(np.random.choice(elites, B))      # pe_model.py:169
-            eps = torch.randn(B, 18)                                 # pe_model.py:176
-            po.rollout_step(p, o, a, idx, eps, "cheetah")
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
+    if _reference() is not None:
+        kind = "reference"
+        m, _ = ref_pe_model("cpu")
+        what = "reference PEModel.step (mirl/agents/mbpo/pe_model.py:252)"
+        with torch.no_grad():
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                m.step(o, a)
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+    else:
+        from oracle import pe_oracle as po
+        from tests.util import to_torch
+        kind = "port"
+        what = "oracle restatement of PEModel.step"
+        p = to_torch(cases.pe_params(11, cases.MBPO))
+        _, elites = po.rank_elites(LOSS_VEC7, 7, 5)
+        with torch.no_grad():
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                idx = torch.from_numpy(np.random.choice(elites, B))      # pe_model.py:169
+                eps = torch.randn(B, 18)                                 # pe_model.py:176
+                po.rollout_step(p, o, a, idx, eps, "cheetah")
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
     sec = float(np.mean(times))
-    return {"value": B / sec, "unit": "transitions/s", "cores": threads, "kind": "port",
-            "sample": "%d steps of PEModel.step restatement (all 7 members, fp32 torch CPU) over "
-                      "%d states, %.2f s/step" % (steps, B, sec)}, sec
+    return {"value": B / sec, "unit": "transitions/s", "cores": threads, "kind": kind,
+            "sample": "%d steps of %s (all 7 members per row, fp32 torch CPU, member draw + noise draw inside) "
+                      "over %d states, %.2f s/step" % (steps, what, B, sec)}, sec
+
+
+def cpu_secondary(threads=None):
+    """CPU figures for the other metrics of BASELINE.json, through the reference's own classes when present:
+    PEModelTrainer.train_from_torch_batch (7 x 256), EnsembleQValue.value (REDQ random-2 min) and
+    TQCQValue.value (drop 8 %) at batch 256."""
+    from tests.golden import cases
+    out = {}
+    shim = _reference()
+    if shim is None:
+        return {"unavailable": "no reference tree on this box (oracle port timed for the rollout only)"}
+    import tempfile
+    from mirl.agents.mbpo.pe_model_trainer import PEModelTrainer
+    from mirl.utils.logger import logger
+    from mirl.values.distributional_value import TQCQValue
+    from mirl.values.ensemble_value import EnsembleQValue
+    torch.set_num_threads(threads or os.cpu_count())
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):            # the reference logger prints its log dir
+        logger.set_snapshot_dir(tempfile.mkdtemp())
+    m, _ = ref_pe_model("cpu")
+    tr = PEModelTrainer(shim.FakeEnv(), m, lr=1e-3, tb_log_freq=-1, silent=True)
+    bt = {k: torch.from_numpy(v) for k, v in cases.train_batch(600, 7, 256).items()}
+    for _ in range(2):
+        tr.train_from_torch_batch(bt)
+    t0 = time.perf_counter()
+    for _ in range(15):
+        tr.train_from_torch_batch(bt)
+    out["model_train_samples_per_s"] = 7 * 256 * 15 / (time.perf_counter() - t0)
+    env = shim.FakeEnv()
+    x = cases.critic_inputs(72, 256)
+    o, a = torch.from_numpy(x["obs"]), torch.from_numpy(x["act"])
+    q = EnsembleQValue(env, ensemble_size=10, hidden_layers=[256, 256], activation="relu")
+    t = TQCQValue(env, ensemble_size=5, number_head=25, hidden_layers=[512] * 3, activation="relu")
+    with torch.no_grad():
+        for name, fn, n in (("redq_targets_per_s", lambda: q.value(o, a, sample_number=2, batchwise_sample=True, mode="min"), 100),
+                            ("tqc_targets_per_s", lambda: t.value(o, a, percentage_drop=8, return_atoms=True), 40)):
+            fn(); fn()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            out[name] = 256 * n / (time.perf_counter() - t0)
+    out["kind"] = "reference"
+    out["cores"] = threads or os.cpu_count()
+    return out
+
+
+def torch_eager_arm(dev):
+    """"Reference torch" bar: the reference's own modules as eager PyTorch on this B200
+    (fp32 SGEMM, TF32 off), CUDA-event timed."""
+    from tests.golden import cases
+    if _reference() is None:
+        return {"unavailable": "no reference tree on this box"}
+    out = {}
+    try:
+        m, ptu = ref_pe_model("cuda")
+        B = 200_000
+        o, a = cases.rollout_inputs(3, B)
+        o, a = torch.from_numpy(o).to(ptu.device), torch.from_numpy(a).to(ptu.device)
+        with torch.no_grad():
+            for _ in range(3):
+                m.step(o, a)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                m.step(o, a)
+            e1.record()
+            torch.cuda.synchronize()
+        out["rollout_transitions_per_s"] = B * 10 / (e0.elapsed_time(e1) * 1e-3)
+        out["rollout_sample"] = "reference PEModel.step, %d states x 10 calls, eager fp32 on cuda (member draw on the host)" % B
+        import tempfile
+        from mirl.agents.mbpo.pe_model_trainer import PEModelTrainer
+        from mirl.utils.logger import logger
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):
+            logger.set_snapshot_dir(tempfile.mkdtemp())
+        from oracle import ref_shim
+        tr = PEModelTrainer(ref_shim.FakeEnv(), m, lr=1e-3, tb_log_freq=-1, silent=True)
+        bt = {k: torch.from_numpy(v).to(ptu.device) for k, v in cases.train_batch(600, 7, 256).items()}
+        for _ in range(5):
+            tr.train_from_torch_batch(bt)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            tr.train_from_torch_batch(bt)
+        torch.cuda.synchronize()
+        out["model_train_samples_per_s"] = 7 * 256 * 50 / (time.perf_counter() - t0)
+    except Exception as exc:                                # the reference's GPU path is not ours to fix
+        out["error"] = "%s: %s" % (type(exc).__name__, str(exc)[:200])
+    finally:
+        try:
+            import mirl.torch_modules.utils as ptu2
+            ptu2.set_gpu_mode(False)
+        except Exception:
+            pass
+    return out
 
 
 def secondary_metrics(dev, world, rank, timed):
-    """Model-train samples/s (members sharded over ranks, no collective in the step) and
-    REDQ / TQC critic-target throughput at batch 256 (replicas), device-resident inputs."""
+    """The other metrics of BASELINE.json, each with its own roofline entry: model-train samples/s (members
+    sharded over ranks, no collective in the step; one persistent launch per block of steps), the fused
+    critic update (REDQ shape), REDQ / TQC critic targets at batch 256 (replicas) and the MOPO penalised step."""
     import mirl_b200
     from mirl_b200.dist import member_partition
     from tests.golden import cases
     from tests.helpers_gpu import FakeEnv, make_critic, make_pe_model
     from tests.util import T
+    pk = peaks()
     E, B = 7, 256
     m, _ = make_pe_model(cases.MBPO, 11, device=dev)
     e0, e1 = member_partition(E, world)[rank]
     out = {}
-    if e1 > e0:
-        tr = mirl_b200.B200PEModelTrainer(FakeEnv(), m, tb_log_freq=-1, silent=True, members=(e0, e1))
-        bt = {k: T(v, dev) for k, v in cases.train_batch(600, E, B).items()}
-        ms = timed(lambda: tr.train_step_async(bt), 200, 20) / 200
-    else:
-        ms = timed(lambda: None, 200, 20) / 200
-    out["model_train_samples_per_s"] = E * B / (ms * 1e-3)
-    out["model_train_ms_per_step"] = ms
-    # forward + dX + dW = 3 GEMM passes of 2*sum(K_l*N_l) flops per sample (4x200 MLP, 23 -> 36)
+    tr = mirl_b200.B200PEModelTrainer(FakeEnv(), m, tb_log_freq=-1, silent=True, members=(e0, e1))
+    N = 100_000
+    data = {k: T(v, dev) for k, v in cases.train_batch(5, 1, N, shared=True).items()}
+    index = torch.from_numpy(np.random.RandomState(1).randint(N, size=(E, N))).to(dev)
+    block = 40                                                  # configs/mbpo.json:114 report_freq
+    ms = timed(lambda: tr.train_steps_async(data, index, N, B, 0, block), 10, 3) / (10 * block)
     mlp_macs = 23 * 200 + 3 * 200 * 200 + 200 * 36
-    out["model_train_tflops"] = 3 * 2 * mlp_macs * E * B / (ms * 1e-3) / 1e12
-    out["model_train_roofline_frac"] = out["model_train_tflops"] / peaks()["tensor"]
-    out["model_train_config"] = "7 members x batch 256 (bootstrap batches), fused fwd+NLL+bwd+Adam, members sharded over %d GPU(s)" % world
+    # forward + dX + dW = 781 600 FLOP per sample and member (SURVEY 8d); Adam: 24 B per parameter and step
+    tf = (2 * mlp_macs * 3 - 2 * 23 * 200) * E * B / (ms * 1e-3) / 1e12
+    out["model_train"] = {
+        "samples_per_s": E * B / (ms * 1e-3), "kernel_ms": ms, "bound": "latency (9 dependent GEMMs per step)",
+        "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
+        "adam_gbs": 24 * 132672 * E / (ms * 1e-3) / 1e9,
+        "config": "7 members x batch 256 bootstrap batches gathered on the device, fused fwd+NLL+bwd+Adam, "
+                  "%d steps per persistent launch, members sharded over %d GPU(s)" % (block, world)}
+    bt = {k: T(v, dev) for k, v in cases.train_batch(600, E, B).items()}
+    ms1 = timed(lambda: tr.train_step_async(bt), 100, 10) / 100
+    out["model_train"]["single_step_launch_ms"] = ms1
+    # fused critic update, REDQ shape (N3)
     q, _ = make_critic("redq", 71, device=dev)
-    t, _ = make_critic("tqc", 81, device=dev)
+    qt, _ = make_critic("redq", 171, device=dev)
     x = cases.critic_inputs(72, B)
     o, a = T(x["obs"], dev), T(x["act"], dev)
     r, d, lp = T(x["rewards"], dev), T(x["terminals"], dev), T(x["log_prob"], dev)
+    ct = mirl_b200.B200CriticTrainer(q, qt)
+    y = T(cases.critic_q_target(x), dev)
+    ms = timed(lambda: ct.update_async(o, a, y), 100, 10) / 100
+    cm = 23 * 256 + 256 * 256 + 256
+    tf = (2 * cm * 3) * 10 * B / (ms * 1e-3) / 1e12
+    out["critic_update"] = {"updates_per_s": 1e3 / ms, "kernel_ms": ms, "achieved": tf, "peak": pk["tensor"],
+                            "unit": "TFLOP/s", "frac": tf / pk["tensor"], "bound": "latency",
+                            "config": "REDQ: 10 critics 2x256 relu, batch 256: forward + MSE + backward + Adam + soft "
+                                      "target update in one launch"}
+    t, _ = make_critic("tqc", 81, device=dev)
     ms = timed(lambda: q.q_target(o, a, r, d, lp, alpha=0.2, sample_number=2, batchwise_sample=True), 200, 20) / 200
-    out["redq_targets_per_s"] = world * B / (ms * 1e-3)
-    out["redq_tflops"] = 2 * 2 * (23 * 256 + 256 * 256 + 256) * B / (ms * 1e-3) / 1e12      # 2 drawn members
+    tf = 2 * 2 * cm * B / (ms * 1e-3) / 1e12                                             # 2 drawn members
+    out["redq_target"] = {"targets_per_s": world * B / (ms * 1e-3), "kernel_ms": ms, "achieved": tf, "peak": pk["tensor"],
+                          "unit": "TFLOP/s", "frac": tf / pk["tensor"], "bound": "latency",
+                          "config": "batch 256; 10x(2x256) random-2 min + TD; replicas"}
     ms = timed(lambda: t.atoms_target(o, a, r, d, lp, alpha=0.2, percentage_drop=8), 200, 20) / 200
-    out["tqc_targets_per_s"] = world * B / (ms * 1e-3)
-    out["tqc_tflops"] = 5 * 2 * (23 * 512 + 2 * 512 * 512 + 512 * 25) * B / (ms * 1e-3) / 1e12
+    tf = 5 * 2 * (23 * 512 + 2 * 512 * 512 + 512 * 25) * B / (ms * 1e-3) / 1e12
+    out["tqc_target"] = {"targets_per_s": world * B / (ms * 1e-3), "kernel_ms": ms, "achieved": tf, "peak": pk["tensor"],
+                         "unit": "TFLOP/s", "frac": tf / pk["tensor"], "bound": "latency",
+                         "config": "batch 256; 5x(3x512)x25 drop 10 + TD; replicas"}
     # configs/offline_mopo.json: penalised rollout step (all elites per row + max-var penalty)
     mm, _ = make_pe_model(cases.MBPO, 11, "hopper", device=dev)
     mm.remember_loss(LOSS_VEC7)
@@ -180,9 +349,11 @@ def secondary_metrics(dev, world, rank, timed):
     em = torch.randn(Bm, 18, device=dev, generator=gm)
     im = torch.from_numpy(np.random.RandomState(5).choice(mm.elite_indices, Bm).astype(np.uint8)).to(dev)
     ms = timed(lambda: mm.step(om, am, indices=im, noise=em, return_distribution=True, penalty_type="max_var"), 20, 3) / 20
-    out["mopo_penalised_transitions_per_s"] = world * Bm / (ms * 1e-3)
-    out["mopo_config"] = "100k states, 5 elites evaluated per row (tcgen05 forward mode) + max_var penalty, per GPU replica"
-    out["critic_config"] = "batch 256; REDQ 10x(2x256) random-2 min + TD; TQC 5x(3x512)x25 drop 10 + TD; replicas"
+    tf = 5 * FLOP_PER_TRANSITION * Bm / (ms * 1e-3) / 1e12
+    out["mopo_step"] = {"transitions_per_s": world * Bm / (ms * 1e-3), "kernel_ms": ms, "achieved": tf,
+                        "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"], "bound": "tensor",
+                        "config": "100k states, 5 elites evaluated per row (tcgen05 forward mode) + max_var penalty, "
+                                  "per GPU replica"}
     return out
 
 
@@ -190,10 +361,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    base, sec = cpu_arm(steps, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    base, sec = cpu_arm(steps, warmup, rows=100_000)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "transitions/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args.gpus),
             "cpu_baseline": base,
@@ -206,8 +377,8 @@ def workload_config(n):
     return {"workload": "MBPO model rollout sweep point: %d start states/GPU x horizon %d, 7 members / "
                         "5 elites, 4x200 swish, obs17/act6, cheetah done" % (ROWS, HORIZON),
             "rows_per_gpu": ROWS, "horizon": HORIZON, "ensemble": 7, "elites": 5,
-            "parallelism": "rows sharded over %d GPU(s); every transition row is stored into all %d pool replicas "
-                           "by the rollout kernel itself (peer stores over NVLink), one 4-byte all-reduce per step" % (n, n),
+            "parallelism": "rows sharded over %d GPU(s); rank-sharded model pool (every rank's rollout kernel writes its own "
+                           "transitions into its own shard; samplers read remote rows through peer mappings)" % n,
             "l2_policy": "inputs larger than L2 (%.0f MB of obs/act/noise per step)" %
                          (ROWS * HORIZON * (24 + 72 + 1) / 1e6 + ROWS * 68 / 1e6)}
 
@@ -251,21 +422,24 @@ def main():
     rs = np.random.RandomState(99 + rank)
     idx_host = rs.choice(model.elite_indices, (H, B)).astype(np.uint8)
     idx = torch.from_numpy(idx_host).to(dev)
-    # Model pool of generated transitions, rows [o | a | o' | r | d] (42 floats), replicated on every
-    # rank: [H][world][B] rows.  The rollout kernel writes each row into every replica from its
-    # epilogue (local HBM + peer-mapped NVLink stores), so there is no separate gather pass.
-    from mirl_b200.dist import PeerPools
-    pools = PeerPools(H * world * B, model.row_stride(), device=dev)     # 44-float rows (16-byte aligned)
-    dests = pools.destinations()
+    # Model pool of generated transitions, rows [o | a | o' | r | d] (42 floats, 44-float stride), RANK-SHARDED:
+    # every rank keeps the [H][B] rows it generates in its own (IPC-exported) shard; the rollout kernel writes
+    # them from its epilogue.  The global index space is the replicated pool's ([h][rank][row]); a sampler reads
+    # rows of other ranks through the peer mappings (dist.ShardedPool).  Round 1 replicated every row into all N
+    # pools from the kernel: (N-1) x 176 B of NVLink ingress per transition capped N = 8 at 3.98 G/s.
+    from mirl_b200.dist import ShardedPool
+    pools = ShardedPool(H * B, model.row_stride(), device=dev, seed=11)
+    for h in range(H):
+        pools.reserve(B, counts=[B] * world)
 
-    def device_step():
+    def device_step(ordered=True):
         o = obs0
         for h in range(H):
-            # bucket order: a pool is a bag of samples, and a 128-row tile then leaves the SM as
-            # one bulk copy per replica; the next step chains on the next_obs columns in place
-            o, _, _ = model.step_rows(o, acts[h], dests, row_offset=(h * world + rank) * B,
-                                      indices=idx[h], noise=noise[h], ordered=False)
-        pools.fence()     # N>1: one stream-ordered 4-byte all-reduce = every replica is complete
+            # rows in batch order (the reference pool's order, mbpo_collector.py:69-83); the next step chains on
+            # the next_obs columns in place.  ordered=False = bucket order (grouped by drawn member, one bulk copy
+            # per 128-row tile), reported as value_bucket_order
+            o, _, _ = model.step_rows(o, acts[h], pools.local, row_offset=h * B,
+                                      indices=idx[h], noise=noise[h], ordered=ordered)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -290,9 +464,36 @@ def main():
     if rank == 0:
         sampler.start()
     total_ms = timed(device_step, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = world * B * H / (ms_per_step * 1e-3)
+    # the same loop for >= 1 s (the K-step region above is ~0.1 s: too short for the clock sampler and for
+    # power / thermal effects to show)
+    sus_steps = max(args.steps, int(1100.0 / ms_per_step) + 1)
+    sus_ms = timed(device_step, sus_steps, 0) / sus_steps
+    clocks = sampler.stop() if rank == 0 else None
+    sustained = {"value": world * B * H / (sus_ms * 1e-3), "unit": "transitions/s", "steps": sus_steps,
+                 "ms_per_step": sus_ms}
+    # rows in bucket order (grouped by drawn member: a permutation of the reference pool's rows)
+    ord_ms = timed(lambda: device_step(False), max(3, args.steps // 3), 2) / max(3, args.steps // 3)
+    value_bucket = world * B * H / (ord_ms * 1e-3)
+
+    # ---- shard check (outside the timed region): rows fetched through the peer mappings == an NCCL all-gather
+    shard_check = None
+    if world > 1:
+        device_step(True)
+        pools.fence()
+        torch.cuda.synchronize()
+        nchk = 65536
+        mine = pools.local[:nchk].contiguous()                           # block h = 0, first rows of every rank
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        rs_c = np.random.RandomState(3)
+        rr, bb = rs_c.randint(0, world, 8192), rs_c.randint(0, nchk, 8192)
+        got = pools.rows(rr.astype(np.int64) * B + bb)                    # global index of (h=0, rank r, row b)
+        want = torch.stack(gathered)[torch.from_numpy(rr).to(dev), torch.from_numpy(bb).to(dev)]
+        ok = torch.tensor([float(torch.equal(got, want))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        shard_check = "ok" if ok.item() == 1.0 else "MISMATCH"
 
     # ---- end to end through the public API from pinned host buffers ------------------------------
     h_obs0 = obs0.cpu().pin_memory()
@@ -373,20 +574,27 @@ def main():
     if rank == 0:
         pk = peaks()
         L.mb_profile_enable(1)
-        ks = []
-        for it in range(6):
-            model.step(obs0, acts[it % H], indices=idx[it % H], noise=noise[it % H])
+        ks, ks_rows = [], []
+        for it in range(8):
+            # the timed legs launch the pool-row variant (176 B written per row instead of 76)
+            model.step_rows(obs0, acts[it % H], pools.local, row_offset=(it % H) * B, indices=idx[it % H],
+                            noise=noise[it % H], ordered=True)
             ms = _lib.ctypes.c_float(0)
+            _lib.check(L.mb_profile_last_ms(_lib.ctypes.byref(ms)))
+            if it >= 2:
+                ks_rows.append(ms.value)
+            model.step(obs0, acts[it % H], indices=idx[it % H], noise=noise[it % H])
             _lib.check(L.mb_profile_last_ms(_lib.ctypes.byref(ms)))
             if it >= 2:
                 ks.append(ms.value)
         L.mb_profile_enable(0)
-        kms = float(np.mean(ks))
-        achieved = FLOP_PER_TRANSITION * B / (kms * 1e-3) / 1e12
-        roof = {"kernel": "k_pe_rollout_%s" % kernel, "bound": "tensor", "achieved": achieved,
-                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
-                "peak_source": pk["src"], "kernel_ms": kms, "launch_rows": B,
-                "hbm_gbs_algorithmic": BYTES_PER_TRANSITION * B / (kms * 1e-3) / 1e9,
+        kms, kms_rows = float(np.mean(ks)), float(np.mean(ks_rows))
+        achieved = FLOP_PER_TRANSITION * B / (kms_rows * 1e-3) / 1e12
+        roof = {"kernel": "k_pe_rollout_%s (pool-row variant, batch order)" % kernel, "bound": "tensor",
+                "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
+                "peak_source": pk["src"], "kernel_ms": kms_rows, "kernel_ms_plain_step": kms, "launch_rows": B,
+                "frac_of_sustained_peak": achieved / pk["tensor_sustained"],
+                "hbm_gbs_algorithmic": (BYTES_PER_TRANSITION + 100) * B / (kms_rows * 1e-3) / 1e9,
                 "traffic": None}
         prof = os.path.join(ROOT, "profiles", "rollout_traffic.json")
         if os.path.exists(prof):
@@ -397,13 +605,19 @@ def main():
     secondary = secondary_metrics(dev, world, rank, timed)
 
     if rank == 0:
+        roof["secondary"] = secondary
         base, _ = cpu_arm(3, 1)
+        base["secondary"] = cpu_secondary()
+        base["torch_eager"] = torch_eager_arm(dev)
+        base["asymmetry"] = ("the CPU arm draws member indices and noise inside every step (the reference always does); "
+                             "the GPU `value` leg uses pre-generated indices/noise, the `e2e` leg draws both inside")
         launches_per_step = H * 2          # k_bucket + k_pe_rollout_tc per horizon step
         line = {"metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(workload_config(world), kernel=kernel),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "value_bucket_order": value_bucket, "sustained": sustained, "shard_check": shard_check,
                 "roofline": roof, "cpu_baseline": base, "secondary": secondary}
         print(json.dumps(line))
     pools.close()

@@ -343,11 +343,13 @@ class B200PEModelTrainer(Component):
         evaluations go out as ONE persistent launch.
 
         Member-sharded (``members`` a strict slice, ``torch.distributed`` initialised): every rank
-        draws the same split / bootstrap table (same NumPy stream), trains its own members and stops
-        on its own members' counters (no collective inside the loop); afterwards the trained slices
-        are all-gathered so that the final evaluation, ``remember_loss`` and therefore
-        ``elite_indices`` are identical on every rank.  An empty slice (E=7 over 8 ranks) trains
-        nothing and still takes part in the exchange."""
+        draws the same split / bootstrap table (same NumPy stream) and trains its own members; there is
+        no collective in the training steps.  The reference keeps training EVERY member until all of
+        them have stalled (pe_model_trainer.py:259-263), so the stop decision is global: one 4-byte
+        all-reduce per evaluation point.  Afterwards the trained slices are all-gathered, so the final
+        evaluation, ``remember_loss`` and therefore ``elite_indices`` are identical on every rank -- and
+        identical to an unsharded run (members are independent).  An empty slice (E=7 over 8 ranks)
+        trains nothing and still takes part in the collectives."""
         from . import dist as mbdist
         model = self.model
         dev = model.device
@@ -369,7 +371,8 @@ class B200PEModelTrainer(Component):
         total_train_step = 0
         eval_stat, eval_loss, last = OrderedDict(), None, None
         continue_training = True
-        while e1 > e0:
+        sharded = (e0, e1) != (0, model.ensemble_size) and mbdist.world()[1] > 1
+        while True:
             if total_train_step % report_freq == 0:
                 eval_stat, eval_loss = self.eval_with_dataset(evald)
                 if total_train_step == 0:
@@ -391,6 +394,10 @@ class B200PEModelTrainer(Component):
                     eval_stat["mt/net_%d/not_improve" % i] = n
                     if e0 <= i < e1 and (max_not_improve < 0 or n < max_not_improve):
                         continue_training = True
+                if sharded:                                   # any member anywhere still improving?
+                    flag = torch.tensor([float(continue_training)], device=dev)
+                    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+                    continue_training = flag.item() > 0
             if total_train_step >= max_step:
                 continue_training = False
             if not continue_training:
@@ -410,8 +417,10 @@ class B200PEModelTrainer(Component):
         if load_best and e1 > e0 and self._best is not None:
             for i in range(e0, e1):
                 self._restore_member(i)
-        if (e0, e1) != (0, model.ensemble_size) and mbdist.world()[1] > 1:
-            mbdist.all_gather_members(model.module)          # every rank now holds every trained member
+        if sharded:
+            parts = [None] * mbdist.world()[1]
+            torch.distributed.all_gather_object(parts, (e0, e1))
+            mbdist.all_gather_members(model.module, parts)   # every rank now holds every trained member
         eval_stat, eval_loss = self.eval_with_dataset(evald)
         model.remember_loss(eval_loss)
         if last is not None:

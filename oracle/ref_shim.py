@@ -1,8 +1,9 @@
 """Import shim for the UNMODIFIED reference tree (container only; test infrastructure).
 
-Used only by ``tests/golden/gen_golden.py`` and by the container-only cross-checks in
-``tests/`` that are skipped when ``/root/reference`` is absent (it never exists on the GPU
-box).  Nothing in the product package imports this file.
+Used by ``tests/golden/gen_golden.py``, by the container-only cross-checks in ``tests/`` and by the
+reference arms of ``bench.py`` (CPU baseline, torch-eager-on-B200), which time the reference's OWN
+modules when a reference tree is present (``/root/reference`` here, ``baseline/_ref`` on the GPU box).
+Nothing in the product package imports this file.
 
 The reference eagerly imports every agent / environment (``mirl/agents/__init__.py:2-19``,
 ``mirl/environments/__init__.py:1-6``), which drags in simulators that are not installed
@@ -18,7 +19,23 @@ import sys
 import types
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("MIRL_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _resolve_root():
+    """MIRL_REFERENCE_ROOT, else the read-only tree of the build container, else the git-ignored copy
+    ``baseline/_ref`` that ``__graft_entry__.build()`` installs so that the reference's own modules can be
+    timed on the GPU box ("or its copy under baseline/_ref/ on the GPU box")."""
+    env = os.environ.get("MIRL_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "mirl")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 _ROOTS = {"gym", "gtimer", "matplotlib", "faiss", "termcolor", "kornia", "imageio",
           "dm_control", "dm_env", "mujoco_py", "robosuite", "tree", "d4rl", "skvideo"}

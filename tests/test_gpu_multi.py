@@ -17,3 +17,13 @@ def test_peer_store_rows_fill_every_replica():
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("peer rows OK") == 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_pool_and_member_sharded_training():
+    """ShardedPool sampling == replicated pool sampling; member-sharded train_with_pool == unsharded."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(ROOT, "tests", "mp_sharded.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("sharded pool OK") == 2 and out.stdout.count("sharded training OK") == 2
