@@ -191,7 +191,8 @@ int mb_pe_loss(const mb_pe_model* m, const mb_train_cfg* cfg, const float* obs,
 
 /* One PEModelTrainer.train_from_torch_batch (pe_model_trainer.py:85-106): forward, Gaussian
  * NLL + log-std bound + L2, backward, Adam -- for the members [member_begin, member_end) only
- * (member-sharded training: each rank passes its own slice; the others are untouched).
+ * (member-sharded training: each rank passes its own slice; the others are untouched; an empty slice is a
+ * no-op).
  * params/exp_avg/exp_avg_sq: packed blobs (same layout), updated in place.
  * step = 1-based Adam step count AFTER this update; if step_counter (device int32, optional) is
  * given, the call increments it on the device and uses it instead (the launch sequence then has

@@ -372,8 +372,9 @@ static int train_common(const char* who, const mb_pe_model* m, const mb_train_cf
     MB_CHECK_ARG(cfg != nullptr, "%s: null cfg", who);
     MB_CHECK_ARG(m->mlp.activation == MB_ACT_SWISH, "%s: only swish models are trainable", who);
     MB_CHECK_ARG(B >= 1 && B < (int64_t)1 << 24, "%s: B %lld out of range", who, (long long)B);
-    MB_CHECK_ARG(0 <= e0 && e0 < e1 && e1 <= m->mlp.ensemble_size, "%s: member slice [%d,%d) invalid", who, e0,
+    MB_CHECK_ARG(0 <= e0 && e0 <= e1 && e1 <= m->mlp.ensemble_size, "%s: member slice [%d,%d) invalid", who, e0,
                  e1);
+    if (e0 == e1) return MB_OK;            // an empty slice (E = 7 members over 8 ranks) is a no-op
     MB_CHECK_ARG(obs && act && delta && reward && ensemble_loss && loss_terms, "%s: null tensor", who);
     MB_CHECK_ARG(!cfg->ignore_terminal_state || done, "%s: ignore_terminal_state needs done", who);
     if (workspace == nullptr || workspace_bytes < mb_pe_train_workspace_bytes(m, B)) {
