@@ -289,6 +289,22 @@ int mb_critic_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, fl
                          int64_t B, float clip_error, float* target_params, float tau, float* ensemble_loss,
                          float* loss_terms, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- policy action inside the rollout loop: GaussianPolicy.action -> MeanLogstdGaussian.forward
+ * (mirl/policies/gaussian_policy.py:35-47, mirl/torch_modules/gaussian.py:55-97,199-204).  d describes the policy MLP
+ * as a 1-member ensemble (sizes[0] = obs_dim, sizes[L] = 2 * act_dim); eps[B][A] is the Normal.rsample() / sample()
+ * draw (NULL = deterministic: the mean).  Writes action[B][A] and, when non-NULL, log_prob[B][1], mean / std [B][A]
+ * (after mean_scale / std_scale / min_std).  workspace >= mb_policy_workspace_bytes. */
+enum { MB_LOGSTD_TANH = 0, MB_LOGSTD_CLAMP = 1, MB_LOGSTD_NO = 2 };   /* gaussian.py:17-30 bound_logstd */
+typedef struct {
+    float mean_scale, std_scale, min_std, logstd_extra_bias;   /* gaussian.py:34-44,170-197 */
+    int32_t bound_mode;                                         /* MB_LOGSTD_* */
+    int32_t squashed;                                           /* tanh squashing (gaussian_policy.py:13) */
+} mb_policy_cfg;
+size_t mb_policy_workspace_bytes(const mb_mlp_desc* d, int64_t B);
+int mb_policy_action(const mb_mlp_desc* d, const float* params, const float* obs, int obs_dim, int64_t B,
+                     const float* eps, const mb_policy_cfg* cfg, float* action, float* log_prob, float* mean,
+                     float* std, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- tcgen05 operand pack: bf16 hi/lo split of every member's weights in the UMMA
  * shared-memory layout the rollout kernel streams (rebuild after the weights change). */
 size_t mb_pe_tc_pack_bytes(const mb_pe_model* m);

@@ -39,6 +39,13 @@ class TrainCfg(Structure):
                 ("beta1", c_float), ("beta2", c_float), ("eps", c_float)]
 
 
+class PolicyCfg(Structure):
+    _fields_ = [("mean_scale", c_float), ("std_scale", c_float), ("min_std", c_float),
+                ("logstd_extra_bias", c_float), ("bound_mode", c_int32), ("squashed", c_int32)]
+
+
+LOGSTD_BOUND = {"tanh": 0, "clamp": 1, "no": 2}
+
 # name -> (restype, argtypes); one entry per symbol include/mirl_b200.h declares
 P = c_void_p
 SIGNATURES = {
@@ -77,6 +84,8 @@ SIGNATURES = {
     "mb_critic_train_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
     "mb_critic_train_step": (c_int, [POINTER(MlpDesc), P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P,
                                      c_int, c_int, P, c_int64, c_float, P, c_float, P, P, P, c_size_t, P]),
+    "mb_policy_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
+    "mb_policy_action": (c_int, [POINTER(MlpDesc), P, P, c_int, c_int64, P, POINTER(PolicyCfg), P, P, P, P, P, c_size_t, P]),
     "mb_critic_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
     "mb_critic_forward": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64, P, P, c_size_t, P]),
     "mb_critic_redq_target": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64,

@@ -58,6 +58,26 @@ if Pool is None:
             pass
 
 
+# ``policy`` items derive from mirl.policies.base_policy.Policy (mirl/policies/base_policy.py:10-34)
+Policy = None
+if HAVE_REFERENCE:
+    try:
+        from mirl.policies.base_policy import Policy            # noqa: F401
+    except Exception:                                           # pragma: no cover
+        Policy = None
+if Policy is None:
+
+    class Policy(object):
+        """mirl/policies/base_policy.py:10-34 (interface only)."""
+
+        def __init__(self, env):
+            self.action_shape = env.action_space.shape
+            self.observation_shape = env.observation_space.shape
+
+        def get_diagnostics(self):
+            return {}
+
+
 if not HAVE_REFERENCE:
 
     class Component:

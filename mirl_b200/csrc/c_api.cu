@@ -483,6 +483,34 @@ int mb_critic_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, fl
     return launch_train_fused(*d, a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t mb_policy_workspace_bytes(const mb_mlp_desc* d, int64_t B) {
+    if (!d) return 0;
+    if (B < 1) B = 1;
+    return (((size_t)B * d->sizes[d->num_layers] * sizeof(float) + 255) & ~size_t(255)) + critic_workspace_bytes(*d, B) + 256;
+}
+
+int mb_policy_action(const mb_mlp_desc* d, const float* params, const float* obs, int obs_dim, int64_t B,
+                     const float* eps, const mb_policy_cfg* cfg, float* action, float* log_prob, float* mean,
+                     float* std, void* workspace, size_t workspace_bytes, void* stream) {
+    const char* who = "mb_policy_action";
+    int rc = validate_desc(d, who);
+    if (rc) return rc;
+    MB_CHECK_ARG(d->ensemble_size == 1, "%s: the policy is a single network (ensemble_size %d)", who, d->ensemble_size);
+    MB_CHECK_ARG(obs_dim >= 1 && d->sizes[0] == obs_dim, "%s: mlp input %d != obs_dim %d", who, d->sizes[0], obs_dim);
+    MB_CHECK_ARG(d->sizes[d->num_layers] % 2 == 0, "%s: output width %d is not 2 * act_dim", who, d->sizes[d->num_layers]);
+    MB_CHECK_ARG(B >= 0 && B < (int64_t)1 << 31, "%s: B out of range", who);
+    MB_CHECK_ARG(cfg != nullptr && cfg->bound_mode >= 0 && cfg->bound_mode <= 2, "%s: bad cfg", who);
+    if (B == 0) return MB_OK;
+    MB_CHECK_ARG(params && obs && action, "%s: null tensor", who);
+    const size_t need = ((size_t)B * d->sizes[d->num_layers] * sizeof(float) + 255) & ~size_t(255);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, need);
+        return MB_EWORKSPACE;
+    }
+    return launch_policy_action(*d, params, obs, obs_dim, B, eps, *cfg, action, log_prob, mean, std, workspace,
+                                workspace_bytes, (cudaStream_t)stream);
+}
+
 static int check_critic(const char* who, const mb_mlp_desc* d, const float* params, const float* obs,
                         const float* act, int O, int A, int64_t B) {
     int rc = validate_desc(d, who);

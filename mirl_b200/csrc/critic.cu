@@ -502,3 +502,67 @@ int launch_critic_tqc(const mb_mlp_desc& d, const float* params, const float* ob
 }
 
 }  // namespace mb
+
+// ---- N1: policy action -------------------------------------------------------------------
+// GaussianPolicy.action -> MeanLogstdGaussian.forward (mirl/policies/gaussian_policy.py:35-47,
+// mirl/torch_modules/gaussian.py:55-97,199-204): out = MLP(obs) [B][2A]; mean, logstd = chunk(out);
+// logstd = bound(logstd + extra_bias); std = exp(logstd) * std_scale + min_std; mean *= mean_scale;
+// pre = mean + std * eps (eps = the Normal.rsample / sample draw, caller-supplied; NULL = deterministic);
+// action = tanh(pre) when squashed; log_prob = sum_j [ Normal.log_prob(pre) - (2 log 2 - softplus(2 pre) -
+// softplus(-2 pre)) ].  One thread per (row, action dim); a row's A lanes reduce the log-prob by shuffle.
+namespace mb {
+
+__global__ void k_policy_head(const float* __restrict__ out, const float* __restrict__ eps, int64_t B, int A,
+                              mb_policy_cfg cfg, float* __restrict__ action, float* __restrict__ log_prob,
+                              float* __restrict__ mean_out, float* __restrict__ std_out) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = t / A;
+    const int j = (int)(t - b * A);
+    float lp = 0.f;
+    if (b < B) {
+        float mean = out[b * 2 * A + j] * cfg.mean_scale;
+        float ls = out[b * 2 * A + A + j] + cfg.logstd_extra_bias;
+        if (cfg.bound_mode == MB_LOGSTD_TANH) ls = (tanhf(ls) + 1.f) * 6.f - 10.f;          // (max - min) / 2 = 6, min = -10
+        else if (cfg.bound_mode == MB_LOGSTD_CLAMP) ls = fminf(fmaxf(ls, -10.f), 2.f);
+        const float sd = expf(ls) * cfg.std_scale + cfg.min_std;
+        const float e = eps ? eps[b * A + j] : 0.f;
+        const float pre = mean + sd * e;
+        action[b * A + j] = cfg.squashed ? tanhf(pre) : pre;
+        if (mean_out) mean_out[b * A + j] = mean;
+        if (std_out) std_out[b * A + j] = sd;
+        // Normal(mean, sd).log_prob(pre) = -e^2 / 2 - log sd - log sqrt(2 pi)
+        lp = -0.5f * e * e - logf(sd) - 0.91893853320467274178f;
+        if (cfg.squashed) lp -= 2.f * 0.69314718055994530942f - softplusf_(2.f * pre) - softplusf_(-2.f * pre);
+    }
+    if (log_prob == nullptr) return;
+    // rows do not straddle warps when A divides 32; otherwise fall back to atomics on a zeroed output
+    if ((32 % A) == 0) {
+        for (int o = 1; o < A; o <<= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+        if (b < B && j == 0) log_prob[b] = lp;
+    } else if (b < B) {
+        atomicAdd(log_prob + b, lp);
+    }
+}
+
+int launch_policy_action(const mb_mlp_desc& d, const float* params, const float* obs, int O, int64_t B,
+                         const float* eps, const mb_policy_cfg& cfg, float* action, float* log_prob, float* mean,
+                         float* std, void* ws, size_t ws_bytes, cudaStream_t s) {
+    const int A = d.sizes[d.num_layers] / 2;
+    // [out B x 2A | critic workspace]
+    float* out = reinterpret_cast<float*>(ws);
+    const size_t out_bytes = ((size_t)B * 2 * A * sizeof(float) + 255) & ~size_t(255);
+    void* cws = ws_bytes > out_bytes + critic_workspace_bytes(d, B) ? (void*)((char*)ws + out_bytes) : nullptr;
+    int rc = launch_critic_forward(d, params, obs, obs, O, 0, B, out, cws, s);
+    if (rc) return rc;
+    if (log_prob && (32 % A) != 0) cudaMemsetAsync(log_prob, 0, sizeof(float) * B, s);
+    const int64_t total = B * A;
+    // a warp must hold whole rows for the shuffle reduction: 256 threads = 8 warps, A | 32
+    launch_pdl(k_policy_head, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, (const float*)out, eps, B, A, cfg,
+               action, log_prob, mean, std);
+    MB_CUDA_LAUNCH_CHECK("k_policy_head");
+    return MB_OK;
+}
+
+}  // namespace mb

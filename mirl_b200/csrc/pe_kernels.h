@@ -171,4 +171,9 @@ int launch_critic_tqc(const mb_mlp_desc& d, const float* params, const float* ob
                       const float* terminal, const float* log_prob, float alpha, float discount,
                       float* value, float* atoms, void* ws, cudaStream_t s);
 
+// ---- policy action (critic.cu): MLP forward (E = 1) + tanh-Gaussian head
+int launch_policy_action(const mb_mlp_desc& d, const float* params, const float* obs, int O, int64_t B,
+                         const float* eps, const mb_policy_cfg& cfg, float* action, float* log_prob, float* mean,
+                         float* std, void* ws, size_t ws_bytes, cudaStream_t s);
+
 }  // namespace mb

@@ -115,3 +115,20 @@ def critic_update(W, b, opt, target_W, target_b, obs, act, q_target, lr=3e-4, ta
     for tp, p in zip(list(target_W) + list(target_b), list(W) + list(b)):
         tp.copy_(tp * (1.0 - tau) + p * tau)
     return loss
+
+
+def policy_action(W, b, obs, eps=None, squashed=True, min_std=1e-4, mean_scale=1.0, std_scale=1.0,
+                  logstd_extra_bias=0.0, activation="relu"):
+    """GaussianPolicy.action -> Gaussian.forward over MeanLogstdGaussian.get_mean_std with bound_mode 'tanh'
+    (mirl/policies/gaussian_policy.py:35-47, mirl/torch_modules/gaussian.py:17-30,55-97,199-204).  ``W``/``b`` are
+    1-member lists ``[1,in,out]`` / ``[1,1,out]``; ``eps`` is the Normal draw (None = deterministic).
+    Returns action, log_prob [B,1], mean, std."""
+    out = mlp_forward(W, b, obs, activation)[0]
+    mean, ls = torch.chunk(out, 2, -1)
+    ls = (torch.tanh(ls + logstd_extra_bias) + 1) * 6.0 - 10.0          # (LOG_STD_MAX - LOG_STD_MIN) / 2 = 6
+    mean, std = mean * mean_scale, torch.exp(ls) * std_scale + min_std
+    pre = mean if eps is None else mean + std * eps
+    lp = -((pre - mean) ** 2) / (2 * std ** 2) - torch.log(std) - 0.5 * np.log(2 * np.pi)
+    if squashed:
+        lp = lp - (2 * np.log(2) - torch.nn.functional.softplus(2 * pre) - torch.nn.functional.softplus(-2 * pre))
+    return (torch.tanh(pre) if squashed else pre), lp.sum(-1, keepdim=True), mean, std

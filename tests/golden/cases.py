@@ -198,3 +198,12 @@ def critic_q_target(x):
     """Synthetic TD target ``[B,1]`` for the critic-update fixture (the real one comes from
     SACAgent.compute_q_target, which has its own fixture)."""
     return (3.0 * x["rewards"] + x["log_prob"]).astype(np.float32)
+
+
+def policy_state_dict(W, b):
+    """Reference ``GaussianPolicy.state_dict()`` keys (a plain MLP: ``module.net.{2l}.weight`` / ``.bias``)."""
+    sd = {}
+    for l in range(len(W)):
+        sd["module.net.%d.weight" % (2 * l)] = W[l][0]
+        sd["module.net.%d.bias" % (2 * l)] = b[l][0]
+    return sd

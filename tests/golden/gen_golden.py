@@ -502,6 +502,34 @@ def gen_critic_update():
         print(tag, out["loss"])
 
 
+def gen_policy():
+    """GaussianPolicy.action (gaussian_policy.py:35-47 -> gaussian.py:55-97,199-204), 17 -> 256 -> 256 -> 12 relu,
+    tanh-squashed: reparameterised and plain samples with log-prob / mean / std, and the deterministic action.
+    The fixture also records the standard-normal draw the reference consumed (replayed: torch.randn(B, A))."""
+    from mirl.policies.gaussian_policy import GaussianPolicy
+    env = ref_shim.FakeEnv()
+    pol = GaussianPolicy(env, hidden_layers=[256, 256], activation="relu")
+    W, b = cases.mlp_params(91, 1, [cases.OBS, 256, 256, 2 * cases.ACT])
+    pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(W, b).items()})
+    B = 300
+    o, _ = cases.rollout_inputs(92, B)
+    out = {}
+    with torch.no_grad():
+        for tag, rep in (("rsample", True), ("sample", False)):
+            torch.manual_seed(93)
+            a, info = pol.action(T(o), return_log_prob=True, reparameterize=rep, return_mean_std=True)
+            torch.manual_seed(93)
+            eps = torch.randn(B, cases.ACT)
+            assert torch.allclose(torch.tanh(info["mean"] + info["std"] * eps), a, atol=1e-6), tag
+            out["action_" + tag], out["log_prob_" + tag] = a.numpy(), info["log_prob"].numpy()
+            out["mean"], out["std"], out["eps"] = info["mean"].numpy(), info["std"].numpy(), eps.numpy()
+        with pol.deterministic_(True):
+            a, _ = pol.action(T(o))
+        out["action_deterministic"] = a.numpy()
+    out["keys"] = np.array(sorted(pol.state_dict().keys()))
+    np.savez(os.path.join(HERE, "policy.npz"), **out)
+
+
 def main():
     ref_shim.install()
     torch.set_num_threads(1)        # bitwise-stable reductions for the fixtures
@@ -510,7 +538,7 @@ def main():
         globals()["gen_" + only]()
     else:
         gen_forward(); gen_step(); gen_dist(); gen_loss(); gen_train(); gen_critics(); gen_keys(); gen_pool()
-        gen_trainloop(); gen_collect(); gen_extrapool(); gen_critic_update()
+        gen_trainloop(); gen_collect(); gen_extrapool(); gen_critic_update(); gen_policy()
     for f in sorted(os.listdir(HERE)):
         if f.endswith((".npz", ".json")):
             print("%8d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))

@@ -423,3 +423,37 @@ def test_fused_critic_update_matches_reference(tag, clip, steps):
                 gm, rm = proj(msd[name], 7000 + i), g["m_proj_%d" % (s_ + 1)][i]
                 # (a [1,1] bias moment is one signed sum over the batch: cancellation, so an absolute floor)
                 assert abs(gm[0] - rm[0]) <= 2e-3 * rm[0] + 2e-5, ("exp_avg", name, gm, rm)
+
+
+# ---- N1: policy action -------------------------------------------------------------------------------
+def test_gaussian_policy_action_matches_reference():
+    """B200GaussianPolicy.action against the reference GaussianPolicy (17 -> 256 -> 256 -> 12 relu, tanh-squashed):
+    reparameterised / plain samples from the recorded draw, log-prob, mean, std, deterministic action; state-dict
+    keys are the reference's."""
+    import mirl_b200
+    g = golden("policy.npz")
+    pol = mirl_b200.B200GaussianPolicy(FakeEnv(), hidden_layers=[256, 256], activation="relu")
+    W, b = cases.mlp_params(91, 1, [cases.OBS, 256, 256, 2 * cases.ACT])
+    pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(W, b).items()})
+    pol = pol.to("cuda")
+    assert sorted(pol.state_dict().keys()) == [str(k) for k in g["keys"]]
+    o, _ = cases.rollout_inputs(92, 300)
+    for tag, rep in (("rsample", True), ("sample", False)):
+        a, info = pol.action(T(o, "cuda"), return_log_prob=True, reparameterize=rep, return_mean_std=True,
+                             noise=T(g["eps"], "cuda"))
+        assert_close(a, g["action_" + tag], what="action " + tag)
+        assert_close(info["log_prob"], g["log_prob_" + tag], what="log_prob " + tag)
+        assert_close(info["mean"], g["mean"], what="mean")
+        assert_close(info["std"], g["std"], what="std")
+    with pol.deterministic_(True):
+        a, _ = pol.action(T(o, "cuda"))
+    assert_close(a, g["action_deterministic"], what="deterministic action")
+    # without noise= the draw comes from the device generator: same distribution, right shapes, in (-1, 1)
+    a, info = pol.action(T(o, "cuda"), return_log_prob=True)
+    assert a.shape == (300, cases.ACT) and info["log_prob"].shape == (300, 1) and float(a.abs().max()) < 1.0
+    # ragged / large batches through the tile kernels
+    big = torch.randn(70001, cases.OBS, device="cuda")
+    with pol.deterministic_(True):
+        a1, _ = pol.action(big)
+        a2, _ = pol.action(big[:4099])
+    assert torch.allclose(a1[:4099], a2, atol=2e-5)
