@@ -354,6 +354,32 @@ def secondary_metrics(dev, world, rank, timed):
                         "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"], "bound": "tensor",
                         "config": "100k states, 5 elites evaluated per row (tcgen05 forward mode) + max_var penalty, "
                                   "per GPU replica"}
+    # full MBPOCollector.imagine (mbpo_collector.py:34-54) on our classes: start-state draw from a device pool,
+    # per horizon step one policy action (B200GaussianPolicy: member/noise draws inside) and one rollout launch that
+    # inserts the transitions into the device pool in place -- configs/mbpo.json shape: 1e5 start states per call
+    from mirl_b200.collectors import B200MBPOCollector
+    env = FakeEnv("cheetah")
+    mc, _ = make_pe_model(cases.MBPO, 11, "cheetah", device=dev)
+    mc.remember_loss(LOSS_VEC7)
+    pol = mirl_b200.B200GaussianPolicy(env, hidden_layers=[256, 256], activation="relu")
+    pW, pb = cases.mlp_params(91, 1, [cases.OBS, 256, 256, 2 * cases.ACT])
+    pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(pW, pb).items()})
+    pol = pol.to(dev)
+    real = mirl_b200.B200DevicePool(env, max_size=200_000, device=dev)
+    real.add_samples(cases.dyn_samples(8001, 150_000))
+    out["imagine"] = {}
+    for depth in (5, 15):
+        imag = mirl_b200.B200DevicePool(env, max_size=10, device=dev, row_stride=mc.row_stride())
+        col = B200MBPOCollector(mc, pol, real, imag, depth_schedule=depth, number_sample=100_000, save_n=2,
+                                bathch_size=100_000)
+        np.random.seed(5)
+        col.imagine(0)                                             # sizes the pool (resize) and warms up
+        ms = timed(lambda: col.imagine(0), 5, 1) / 5
+        out["imagine"]["depth_%d" % depth] = {
+            "transitions_per_s": world * 100_000 * depth / (ms * 1e-3), "ms_per_call": ms,
+            "launches_per_horizon_step": "policy: 3 layer kernels + head; model: member draw or host draw, bucket, rollout"}
+    out["imagine"]["config"] = ("B200MBPOCollector.imagine: 1e5 start states, B200GaussianPolicy 17-256-256-12, "
+                                "transitions inserted into a B200DevicePool by the rollout kernel; per GPU replica")
     return out
 
 
@@ -459,6 +485,42 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
+
+    # ---- roofline of the dominant kernel (events inside the C ABI around that kernel only), measured FIRST:
+    # a kernel timed alone on a cool GPU is what the burst peak it is divided by was measured like
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        L.mb_profile_enable(1)
+        ks, ks_rows = [], []
+        for it in range(8):
+            # the timed legs launch the pool-row variant (176 B written per row instead of 76)
+            model.step_rows(obs0, acts[it % H], pools.local, row_offset=(it % H) * B, indices=idx[it % H],
+                            noise=noise[it % H], ordered=True)
+            ms = _lib.ctypes.c_float(0)
+            _lib.check(L.mb_profile_last_ms(_lib.ctypes.byref(ms)))
+            if it >= 2:
+                ks_rows.append(ms.value)
+            model.step(obs0, acts[it % H], indices=idx[it % H], noise=noise[it % H])
+            _lib.check(L.mb_profile_last_ms(_lib.ctypes.byref(ms)))
+            if it >= 2:
+                ks.append(ms.value)
+        L.mb_profile_enable(0)
+        kms, kms_rows = float(np.mean(ks)), float(np.mean(ks_rows))
+        achieved = FLOP_PER_TRANSITION * B / (kms_rows * 1e-3) / 1e12
+        roof = {"kernel": "k_pe_rollout_%s (pool-row variant, batch order)" % kernel, "bound": "tensor",
+                "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
+                "peak_source": pk["src"], "kernel_ms": kms_rows, "kernel_ms_plain_step": kms, "launch_rows": B,
+                "frac_of_sustained_peak": achieved / pk["tensor_sustained"],
+                "hbm_gbs_algorithmic": (BYTES_PER_TRANSITION + 100) * B / (kms_rows * 1e-3) / 1e9,
+                "traffic": None}
+        prof = os.path.join(ROOT, "profiles", "rollout_traffic.json")
+        if os.path.exists(prof):
+            with open(prof) as f:
+                tr_ = json.load(f)
+            # ncu capture of the plain-step variant (the pool-row variant writes 100 B more per row)
+            roof["traffic"] = tr_.get("k_pe_rollout_%s" % kernel)
+            roof["traffic_note"] = tr_.get("source")
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -568,38 +630,6 @@ def main():
            "h2d_bytes_per_step": B * O * 4 + H * (B * A * 4 + n_chunks * 627 * 4),
            "d2h_bytes_per_step": H * B * (O + 2) * 4, "ms_per_step": e2e_ms, "row_chunks": n_chunks,
            "steps_in_flight": depth}
-
-    # ---- roofline of the dominant kernel (events inside the C ABI around that kernel only) -------
-    roof = None
-    if rank == 0:
-        pk = peaks()
-        L.mb_profile_enable(1)
-        ks, ks_rows = [], []
-        for it in range(8):
-            # the timed legs launch the pool-row variant (176 B written per row instead of 76)
-            model.step_rows(obs0, acts[it % H], pools.local, row_offset=(it % H) * B, indices=idx[it % H],
-                            noise=noise[it % H], ordered=True)
-            ms = _lib.ctypes.c_float(0)
-            _lib.check(L.mb_profile_last_ms(_lib.ctypes.byref(ms)))
-            if it >= 2:
-                ks_rows.append(ms.value)
-            model.step(obs0, acts[it % H], indices=idx[it % H], noise=noise[it % H])
-            _lib.check(L.mb_profile_last_ms(_lib.ctypes.byref(ms)))
-            if it >= 2:
-                ks.append(ms.value)
-        L.mb_profile_enable(0)
-        kms, kms_rows = float(np.mean(ks)), float(np.mean(ks_rows))
-        achieved = FLOP_PER_TRANSITION * B / (kms_rows * 1e-3) / 1e12
-        roof = {"kernel": "k_pe_rollout_%s (pool-row variant, batch order)" % kernel, "bound": "tensor",
-                "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
-                "peak_source": pk["src"], "kernel_ms": kms_rows, "kernel_ms_plain_step": kms, "launch_rows": B,
-                "frac_of_sustained_peak": achieved / pk["tensor_sustained"],
-                "hbm_gbs_algorithmic": (BYTES_PER_TRANSITION + 100) * B / (kms_rows * 1e-3) / 1e9,
-                "traffic": None}
-        prof = os.path.join(ROOT, "profiles", "rollout_traffic.json")
-        if os.path.exists(prof):
-            with open(prof) as f:
-                roof["traffic"] = json.load(f).get(roof["kernel"])
 
     # ---- secondary metrics of BASELINE.json: model-train samples/s, REDQ / TQC targets/s ----------
     secondary = secondary_metrics(dev, world, rank, timed)

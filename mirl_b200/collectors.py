@@ -95,8 +95,13 @@ class B200MBPOCollector(Component):
             return None
         n = o.shape[0]
         start = pool.reserve(n)
-        if start is None:                                             # block would wrap around the ring
-            return None
+        if start is None:
+            # the block would wrap around the ring (or the pool keeps running statistics): the kernel fills a
+            # staging block and the ring insert is one device copy (simple_pool.py:125-150 semantics)
+            block = torch.empty(n, pool.row_stride, device=pool.rows.device)
+            next_o, _, d = self.model.step_rows(o.contiguous(), a.contiguous(), block, row_offset=0, ordered=True)
+            pool.add_rows(block)
+            return next_o, d
         next_o, _, d = self.model.step_rows(o.contiguous(), a.contiguous(), pool.rows, row_offset=start, ordered=True)
         return next_o, d
 
@@ -143,7 +148,10 @@ class B200MBPOCollector(Component):
                 out[k] = packed[:, c:c + w]
                 c += w
             samples = out
-        self.imagined_data_pool.add_samples({k: v.cpu().numpy() for k, v in samples.items()})
+        if hasattr(self.imagined_data_pool, "add_rows"):               # device pool: no D2H / H2D round trip
+            self.imagined_data_pool.add_samples(samples)
+        else:
+            self.imagined_data_pool.add_samples({k: v.cpu().numpy() for k, v in samples.items()})
 
     def _rewards(self, r, info):
         return r

@@ -171,6 +171,8 @@ def test_reference_factory_resolves_our_classes():
         "assert get_item_class('value', 'B200EnsembleQValue') is mirl_b200.B200EnsembleQValue\n"
         "assert get_item_class('value', 'B200TQCQValue') is mirl_b200.B200TQCQValue\n"
         "assert get_item_class('pool', 'B200DevicePool') is mirl_b200.B200DevicePool\n"
+        "assert get_item_class('pool', 'B200ExtraFieldPool') is mirl_b200.B200ExtraFieldPool\n"
+        "assert get_item_class('policy', 'B200GaussianPolicy') is mirl_b200.B200GaussianPolicy\n"
         "print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
@@ -196,3 +198,35 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == line["value"]
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_sharded_pool_index_space_is_the_replicated_pools():
+    """ShardedPool.locate: global row index -> (owner rank, local row), for ragged blocks, equals where an
+    all-gather in rank order would have put the rows of every block (no GPU needed: the bookkeeping only)."""
+    from mirl_b200.dist import ShardedPool
+    world = 3
+    pools = []
+    for r in range(world):
+        p = ShardedPool.__new__(ShardedPool)
+        p._np, p.rank, p.world, p.capacity = np, r, world, 10_000
+        p.reset()
+        pools.append(p)
+    rs = np.random.RandomState(0)
+    blocks = [list(rs.randint(0, 50, world)) for _ in range(7)] + [[0, 5, 0]]
+    owner_ref, local_ref = [], []
+    used = [0] * world
+    for counts in blocks:
+        for r in range(world):
+            assert pools[r].reserve(int(counts[r]), counts=[int(c) for c in counts]) == used[r]
+        for r in range(world):                                   # all-gather order inside a block: rank 0, 1, 2
+            owner_ref += [r] * counts[r]
+            local_ref += list(range(used[r], used[r] + counts[r]))
+            used[r] += counts[r]
+    total = sum(sum(c) for c in blocks)
+    assert len(pools[0]) == total == len(owner_ref)
+    g = rs.permutation(total)
+    for p in pools:
+        owner, local = p.locate(g)
+        assert np.array_equal(owner, np.asarray(owner_ref)[g]) and np.array_equal(local, np.asarray(local_ref)[g])
+    with pytest.raises(RuntimeError):
+        pools[0].reserve(20_000, counts=[20_000, 0, 0])
