@@ -163,6 +163,22 @@ def stream(device=None):
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def on_device(fn):
+    """Run a method with its object's CUDA device current: the C ABI launches on the CURRENT device's
+    stream and caches per-device kernel attributes, so a model on cuda:1 must not launch while cuda:0 is
+    current (round-1 advisor finding)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = self.device
+        if getattr(dev, "type", None) != "cuda":
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 def f32(t, device):
     """Contiguous fp32 tensor on ``device`` (no copy when it already is one)."""
     return t.to(device=device, dtype=torch.float32).contiguous()

@@ -134,7 +134,11 @@ __device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.f, 
 // activation and its derivative from one sigmoid: swish h = z s, h' = s (1 + z (1 - s)) = s + h (1 - s)
 __device__ __forceinline__ float act_both(float z, int act, float& deriv) {
     if (act == MB_ACT_RELU) { deriv = z > 0.f ? 1.f : 0.f; return fmaxf(z, 0.f); }
-    const float sg = fast_sigmoid(z);
+    // sigmoid(z) = 1/2 + 1/2 tanh(z/2): one MUFU op instead of ex2 + rcp.  MUFU.TANH on sm_100a is far more
+    // accurate than the 2^-11 the PTX manual guarantees (measured in the rollout kernel: same 4e-6 error)
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    const float sg = fmaf(0.5f, t, 0.5f);
     const float h = z * sg;
     deriv = fmaf(h, 1.f - sg, sg);
     return h;
@@ -257,6 +261,10 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
         mbar_init(empty0, kWarps);
         mbar_init(empty0 + 8, kWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int t = tid; t < a.act_bytes / 4; t += kThreads) {      // padding columns must hold finite values
+        reinterpret_cast<uint32_t*>(act0)[t] = 0u;
+        reinterpret_cast<uint32_t*>(act1)[t] = 0u;
     }
     __syncthreads();
     // Ring protocol.  Use number u (0, 1, 2, ... over the whole kernel) occupies stage u & 1.  The issuer
@@ -478,13 +486,19 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                         if (fwd) {
                             // the backward pass needs act'(z), not z: keep that (one sigmoid serves both)
                             float d0 = 0.f, d1 = 0.f;
+#ifdef MB_EXP_NOACT
+                            d0 = d1 = 1.f;
+#else
                             if (n < out_w) v0 = act_both(v0, act_kind, d0); else v0 = (n == out_w) ? 1.f : 0.f;
                             if (n + 1 < out_w) v1 = act_both(v1, act_kind, d1); else v1 = (n + 1 == out_w) ? 1.f : 0.f;
+#endif
                             *reinterpret_cast<float2*>(zrow + i * a.z_stride + n) = make_float2(d0, d1);
                             split2(v0, v1, hi, lo);
+#ifndef MB_EXP_NOGSTORE
                             const int64_t o = grow[h] + (tile >> 1) * h_strip_stride + (((tile & 1) ^ gsw[h]) << 3);
                             *reinterpret_cast<uint32_t*>(hbuf + o) = hi;
                             *reinterpret_cast<uint32_t*>(hbuf + o + h_half) = lo;
+#endif
                         } else {
                             const float2 d = *reinterpret_cast<const float2*>(zrow + i * a.z_stride + n);
                             v0 = n < out_w ? v0 * d.x : 0.f;
@@ -499,30 +513,28 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     }
                 };
 
-                // padding columns of the produced operand beyond the tiles the epilogue writes (shared
-                // memory and global): zeros, except the bias "1" when column N falls there
-                if (!last_fwd) {
-                    const int c0 = nt_total * 8;
-                    const int wpad = dstride - c0;
+                // Padding columns of the produced operand beyond the tiles the epilogue writes: the only one whose
+                // VALUE matters is the bias column (column N of a forward operand must be exactly 1: it multiplies
+                // the bias row of the next layer's pack and yields db in phase B); every other padding column only
+                // ever meets zero weights, so any finite value will do -- the buffers are zeroed once at kernel start
+                // and only ever hold finite bf16 values afterwards.  (Rewriting all of them every pass cost ~650
+                // cycles per pass.)  When N is not a multiple of 8 the epilogue's last tile writes the 1 itself.
+                if (fwd && !last_fwd) {
+                    // global h_{l+1}: columns [N, Kp) -- phase B loads them into shared memory as part of its
+                    // strips, so they must be finite there too (column N = 1, the rest 0)
+                    const int c0 = out_w & ~7, wpad = lo_.Kp - c0;
                     for (int t = tid; t < kRows * wpad; t += kT) {
-                        const int i = t & (kRows - 1), c = c0 + (t >> 4);
-                        const float v = (fwd && c == out_w) ? 1.f : 0.f;
-                        const __nv_bfloat16 vb = __float2bfloat16(v), zb = __float2bfloat16(0.f);
-                        Dh[i * dstride + c] = vb;
-                        Dl[i * dstride + c] = zb;
-                        const int b = row0 + i;
-                        if (fwd) {
-                            if (c < lo_.Kp) {
-                                const int unit = ((c >> 3) & 1) ^ ((b >> 2) & 1);
-                                const int64_t o = h_elem_off(lo_, a.E, e, a.Bp, b, c >> 4, 0) + unit * 8 + (c & 7);
-                                hbuf[o] = vb;
-                                hbuf[o + (int64_t)(lo_.Kp >> 4) * a.E * a.Bp * 16] = zb;
-                            }
-                        } else {
-                            const int64_t o = g_elem_off(lo_, e, a.Bp, b, 0) + c;
-                            gbuf[o] = zb;
-                            gbuf[o + (int64_t)kChunk * lo_.Ns] = zb;
+                        const int i = t & (kRows - 1), c = c0 + (t >> 4), b = row0 + i;
+                        if (c < out_w) continue;                              // written by the last tile
+                        const __nv_bfloat16 vb = __float2bfloat16(c == out_w ? 1.f : 0.f);
+                        if (c == out_w) {
+                            Dh[i * dstride + c] = vb;
+                            Dl[i * dstride + c] = __float2bfloat16(0.f);
                         }
+                        const int unit = ((c >> 3) & 1) ^ ((b >> 2) & 1);
+                        const int64_t o = h_elem_off(lo_, a.E, e, a.Bp, b, c >> 4, 0) + unit * 8 + (c & 7);
+                        hbuf[o] = vb;
+                        hbuf[o + h_half] = __float2bfloat16(0.f);
                     }
                 }
                 TL_SET(60 + pass * 6 + 1);

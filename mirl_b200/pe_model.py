@@ -293,6 +293,7 @@ class B200PEModel(Component, nn.Module):
         self._draw_snaps.append(snap)
         return key, pos, produced
 
+    @_lib.on_device
     def draw_members(self, B):
         """``np.random.choice(elite, B)`` (pe_model.py:165-169) generated on the device from
         NumPy's own global MT19937 state: the returned uint8 indices are bit-identical to the
@@ -364,6 +365,7 @@ class B200PEModel(Component, nn.Module):
         return out
 
     # ---- rollout -------------------------------------------------------------------------------
+    @_lib.on_device
     def step(self, obs, action, return_distribution=False, indices=None, noise=None,
              penalty_type=None, penalty_coef=1.0):
         """``PEModel.step`` (pe_model.py:252-283): ``(next_obs [B,O], reward [B,1], done [B,1],
@@ -451,6 +453,7 @@ class B200PEModel(Component, nn.Module):
         (bulk-copy) output."""
         return (self.row_width() + 3) // 4 * 4
 
+    @_lib.on_device
     def step_rows(self, obs, action, dest, row_offset=0, indices=None, noise=None, ordered=True):
         """``PEModel.step`` fused with the collector's pool-row assembly (mbpo_collector.py:69-83):
         every transition is written as a row ``[obs | act | next_obs | reward | done | 0-padding]``
@@ -521,6 +524,7 @@ class B200PEModel(Component, nn.Module):
                 {k: v.cpu().numpy() for k, v in info.items()})
 
     # ---- distribution / loss ---------------------------------------------------------------------
+    @_lib.on_device
     def predict_distribution(self, obs, action, normalize=True):
         """Per-member Gaussian of the NORMALISED delta/reward: ``mean, logstd`` ``[E,B,O+1]``
         (MLP forward + ``_get_mean_logstd``, pe_model.py:110-151).  Inputs ``[B,.]`` are shared
@@ -565,6 +569,7 @@ class B200PEModel(Component, nn.Module):
         bound = self.bound_reg_coef * (mod.logstd_bound(0).sum() - mod.logstd_bound(1).sum())
         return l2, bound
 
+    @_lib.on_device
     def compute_loss(self, obs, action, delta, reward=None, done=None, ignore_terminal_state=True,
                      n_step=0, log=False):
         """``PEModel.compute_loss`` (pe_model.py:285-307): ``(loss, ensemble_loss [E])`` for a

@@ -124,6 +124,7 @@ class B200PEModelTrainer(Component):
             _lib.ptr(t["rewards"]), _lib.ptr(t["terminals"]), B, e0, e1, _lib.ptr(self._ensemble_loss),
             _lib.ptr(self._loss_terms), _lib.ptr(self._ws), self._ws.numel(), _lib.stream()))
 
+    @_lib.on_device
     def train_step_async(self, batch):
         """Enqueue one fused training step; returns device tensors
         ``(ensemble_loss [E], loss_terms [3] = sum_e loss_e, l2, bound)`` without synchronising
@@ -435,6 +436,10 @@ class B200PEModelTrainer(Component):
 
     def end_epoch(self, epoch):
         pass
+
+    @property
+    def device(self):
+        return self.model.device
 
     @property
     def networks(self):

@@ -90,6 +90,7 @@ class _CriticBase(nn.Module, QValue):
         lead = tuple(obs.shape[:-1])
         return obs.reshape(-1, obs.shape[-1]), action.reshape(-1, action.shape[-1]), lead
 
+    @_lib.on_device
     def _ensemble(self, obs2, act2):
         E, N = self.ensemble_size, self.module.output_size
         B = obs2.shape[0]
@@ -158,6 +159,7 @@ class B200EnsembleQValue(_CriticBase):
             _lib.ptr(value), _lib.ptr(ws), ws.numel(), _lib.stream()))
         return value
 
+    @_lib.on_device
     def value(self, obs, action, sample_number=2, batchwise_sample=False, mode="min",
               return_ensemble=False, only_return_ensemble=False, _td=None):
         """ensemble_value.py:65-107; only the drawn members are evaluated."""
@@ -183,6 +185,7 @@ class B200EnsembleQValue(_CriticBase):
             info["ensemble_value"] = self._ensemble_shaped(obs2, act2, lead)
         return value, info
 
+    @_lib.on_device
     def q_target(self, next_obs, next_action, rewards, terminals, log_prob, alpha, discount=0.99,
                  **v_pi_kwargs):
         """``SACAgent.compute_q_target`` arithmetic (sac_agent.py:80-85) fused into the value
@@ -222,6 +225,7 @@ class B200TQCQValue(_CriticBase):
             _lib.ptr(ws), ws.numel(), _lib.stream()))
         return value, atoms
 
+    @_lib.on_device
     def value(self, obs, action, number_drop=None, percentage_drop=None, return_atoms=False,
               return_ensemble=False, only_return_ensemble=False):
         """distributional_value.py:59-93."""
@@ -239,6 +243,7 @@ class B200TQCQValue(_CriticBase):
             info["ensemble_atoms"] = ens.reshape(ens.shape[:-2] + (-1,))
         return value.reshape(lead + (1,)), info
 
+    @_lib.on_device
     def atoms_target(self, next_obs, next_action, rewards, terminals, log_prob, alpha,
                      discount=0.99, number_drop=None, percentage_drop=None):
         """``TQCAgent.compute_q_target`` (tqc_agent.py:41-57) fused: truncated sorted atoms of
