@@ -281,13 +281,25 @@ int mb_critic_tqc_target(const mb_mlp_desc* d, const float* params, const float*
  * persistent launch (the kernel of mb_pe_train_steps with an MSE head): forward, loss, backward, Adam and
  * target <- (1 - tau) target + tau params.  obs/act [B][.] are shared by the members; q_target [B][out].
  * target_params (same blob layout) may be NULL (no target update this step, sac_agent.py:165-166).
- * ensemble_loss[E] = each member's share of the loss; loss_terms[0] = the loss.  Layer widths up to 256. */
+ * ensemble_loss[E] = each member's share of the loss; loss_terms[0] = the loss.  Layer widths up to 256 run the
+ * persistent kernel; wider critics run the same update as a chain of launches (tcgen05 layer GEMMs, head, Adam,
+ * soft update). */
 size_t mb_critic_train_workspace_bytes(const mb_mlp_desc* d, int64_t B);
 int mb_critic_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, float* exp_avg_sq,
                          int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
                          const float* obs, const float* act, int obs_dim, int act_dim, const float* q_target,
                          int64_t B, float clip_error, float* target_params, float tau, float* ensemble_loss,
                          float* loss_terms, void* workspace, size_t workspace_bytes, void* stream);
+
+/* TQC critic update: TQCAgent.compute_qf_loss (tqc_agent.py:59-66) = quantile_huber_loss_f (tqc_agent.py:5-14) of
+ * the [E][B][Q] ensemble atoms (TQCQValue.value(only_return_ensemble=True), distributional_value.py:73-77) against
+ * atoms_target[B][n_target] (mb_critic_tqc_target's atoms), + Adam + soft target update as above.  d->sizes[L] = Q.
+ * Workspace: mb_critic_train_workspace_bytes.  configs/tqc.json: E 5, 3 x 512 relu, Q 25, n_target 115. */
+int mb_tqc_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, float* exp_avg_sq,
+                      int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                      const float* obs, const float* act, int obs_dim, int act_dim, const float* atoms_target,
+                      int n_target, int64_t B, float* target_params, float tau, float* ensemble_loss,
+                      float* loss_terms, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- policy action inside the rollout loop: GaussianPolicy.action -> MeanLogstdGaussian.forward
  * (mirl/policies/gaussian_policy.py:35-47, mirl/torch_modules/gaussian.py:55-97,199-204).  d describes the policy MLP

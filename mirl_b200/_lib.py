@@ -84,6 +84,8 @@ SIGNATURES = {
     "mb_critic_train_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
     "mb_critic_train_step": (c_int, [POINTER(MlpDesc), P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P,
                                      c_int, c_int, P, c_int64, c_float, P, c_float, P, P, P, c_size_t, P]),
+    "mb_tqc_train_step": (c_int, [POINTER(MlpDesc), P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P,
+                                  c_int, c_int, P, c_int, c_int64, P, c_float, P, P, P, c_size_t, P]),
     "mb_policy_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
     "mb_policy_action": (c_int, [POINTER(MlpDesc), P, P, c_int, c_int64, P, POINTER(PolicyCfg), P, P, P, P, P, c_size_t, P]),
     "mb_critic_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),

@@ -427,8 +427,14 @@ int mb_pe_loss_grads(const mb_pe_model* m, const mb_train_cfg* cfg, const float*
 
 /* ---- critic update: DDPGAgent.compute_qf_loss + qf_optimizer.step + soft target update ------------------ */
 size_t mb_critic_train_workspace_bytes(const mb_mlp_desc* d, int64_t B) {
-    if (!d || !fused_train_supported(*d, 1)) return 0;
-    return fused_train_workspace_bytes(*d, B < 1 ? 1 : B);
+    if (!d || validate_desc(d, "mb_critic_train_workspace_bytes")) return 0;
+    B = B < 1 ? 1 : B;
+    size_t n = critic_chain_workspace_bytes(*d, B);
+    if (fused_train_supported(*d, 1)) {
+        const size_t f = fused_train_workspace_bytes(*d, B);
+        n = f > n ? f : n;
+    }
+    return n;
 }
 
 int mb_critic_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, float* exp_avg_sq,
@@ -445,9 +451,12 @@ int mb_critic_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, fl
     MB_CHECK_ARG(params && exp_avg && exp_avg_sq && obs && act && q_target && ensemble_loss && loss_terms,
                  "%s: null tensor", who);
     MB_CHECK_ARG(adam_steps_done >= 0, "%s: adam_steps_done < 0", who);
-    if (!fused_train_supported(*d, d->ensemble_size)) {
-        set_error("%s: layer widths above 256 (or more members than SMs) are not covered by the fused kernel", who);
-        return MB_EUNSUPPORTED;
+    if (!fused_train_supported(*d, d->ensemble_size)) {     // wide critics: per-layer launches
+        MB_CHECK_ARG(workspace && workspace_bytes >= critic_chain_workspace_bytes(*d, B), "%s: workspace too small", who);
+        return launch_critic_train_chain(*d, CRITIC_HEAD_MSE, params, exp_avg, exp_avg_sq, adam_steps_done, lr, beta1,
+                                         beta2, eps, obs, act, obs_dim, act_dim, q_target, d->sizes[d->num_layers], B,
+                                         clip_error, target_params, tau, ensemble_loss, loss_terms, workspace,
+                                         (cudaStream_t)stream);
     }
     FusedArgs a{};
     a.e0 = 0;
@@ -481,6 +490,27 @@ int mb_critic_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, fl
     a.ensemble_loss = ensemble_loss;
     a.loss_terms = loss_terms;
     return launch_train_fused(*d, a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mb_tqc_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, float* exp_avg_sq,
+                      int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                      const float* obs, const float* act, int obs_dim, int act_dim, const float* atoms_target,
+                      int n_target, int64_t B, float* target_params, float tau, float* ensemble_loss,
+                      float* loss_terms, void* workspace, size_t workspace_bytes, void* stream) {
+    const char* who = "mb_tqc_train_step";
+    int rc = validate_desc(d, who);
+    if (rc) return rc;
+    MB_CHECK_ARG(obs_dim >= 1 && act_dim >= 0 && d->sizes[0] == obs_dim + act_dim, "%s: mlp input %d != obs+act %d", who,
+                 d->sizes[0], obs_dim + act_dim);
+    MB_CHECK_ARG(B >= 1 && B < (int64_t)1 << 20, "%s: B out of range", who);
+    MB_CHECK_ARG(n_target >= 1, "%s: n_target < 1", who);
+    MB_CHECK_ARG(params && exp_avg && exp_avg_sq && obs && act && atoms_target && ensemble_loss && loss_terms,
+                 "%s: null tensor", who);
+    MB_CHECK_ARG(adam_steps_done >= 0, "%s: adam_steps_done < 0", who);
+    MB_CHECK_ARG(workspace && workspace_bytes >= critic_chain_workspace_bytes(*d, B), "%s: workspace too small", who);
+    return launch_critic_train_chain(*d, CRITIC_HEAD_QUANTILE, params, exp_avg, exp_avg_sq, adam_steps_done, lr, beta1,
+                                     beta2, eps, obs, act, obs_dim, act_dim, atoms_target, n_target, B, 0.f,
+                                     target_params, tau, ensemble_loss, loss_terms, workspace, (cudaStream_t)stream);
 }
 
 size_t mb_policy_workspace_bytes(const mb_mlp_desc* d, int64_t B) {

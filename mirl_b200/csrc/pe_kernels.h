@@ -157,6 +157,16 @@ int launch_pe_train(const PeDev& m, void* tc_pack, const mb_train_cfg& cfg, floa
 int launch_pe_train_fwd_tc(const PeDev& m, void* pack, const float* obs, const float* act, int64_t B, int e0,
                            int ne, float* const* zsave, float* head_raw, cudaStream_t s);
 
+// critic update as a chain of launches (tensor-core layer GEMMs + head + Adam + soft target update):
+// MSE head for DDPG/SAC/REDQ critics wider than the persistent kernel covers, quantile-Huber head for TQC
+enum { CRITIC_HEAD_MSE = 0, CRITIC_HEAD_QUANTILE = 1 };
+size_t critic_chain_workspace_bytes(const mb_mlp_desc& d, int64_t B);
+int launch_critic_train_chain(const mb_mlp_desc& d, int head_kind, float* params, float* exp_avg, float* exp_avg_sq,
+                              int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                              const float* obs, const float* act, int O, int A, const float* target, int T,
+                              int64_t B, float clip_error, float* target_params, float tau, float* ensemble_loss,
+                              float* loss_terms, void* ws, cudaStream_t s);
+
 // ---- critic targets (critic.cu)
 size_t critic_workspace_bytes(const mb_mlp_desc& d, int64_t B);
 int launch_critic_forward(const mb_mlp_desc& d, const float* params, const float* obs,

@@ -697,4 +697,203 @@ int launch_pe_train(const PeDev& m, void* tc_pack, const mb_train_cfg& cfg, floa
     return MB_OK;
 }
 
+// ---- critic update as a chain of launches (widths above 256: TQC's 3 x 512, configs/tqc.json) --
+// Same maths as the persistent kernel's critic mode (train_fused.cu) for networks it does not cover, plus the
+// quantile-Huber head of TQC (tqc_agent.py:5-14).  Input [obs | act] is shared by the members
+// (ensemble_value.py:59-63, distributional_value.py:95-101); every member sees the same target.
+struct CriticWs {
+    float* x0;                     // [B][IN]
+    float* z[MB_MAX_LAYERS];       // [E][B][sizes[l+1]] pre-activations, l < L-1
+    float* out;                    // [E][B][Nout]
+    float* g[MB_MAX_LAYERS];       // dL/d(output of layer l) [E][B][sizes[l+1]]
+    float* grads;
+};
+
+size_t critic_chain_workspace_bytes(const mb_mlp_desc& d, int64_t B) {
+    const int64_t E = d.ensemble_size;
+    int64_t f = round_up4(B * d.sizes[0]);
+    for (int l = 0; l < d.num_layers; ++l) f += 2 * round_up4(E * B * d.sizes[l + 1]);
+    f += round_up4(param_count(d, false));
+    return (size_t)f * sizeof(float) + 256;
+}
+
+static CriticWs critic_carve(const mb_mlp_desc& d, int64_t B, void* ws) {
+    CriticWs w{};
+    const int64_t E = d.ensemble_size;
+    const int L = d.num_layers;
+    float* p = reinterpret_cast<float*>(ws);
+    w.x0 = p; p += round_up4(B * d.sizes[0]);
+    for (int l = 0; l < L; ++l) {
+        float* t = p; p += round_up4(E * B * d.sizes[l + 1]);
+        if (l + 1 < L) w.z[l] = t; else w.out = t;
+    }
+    for (int l = 0; l < L; ++l) { w.g[l] = p; p += round_up4(E * B * d.sizes[l + 1]); }
+    w.grads = p;
+    return w;
+}
+
+__global__ void k_critic_prep(const float* __restrict__ obs, const float* __restrict__ act, int O, int A, int64_t B,
+                              float* __restrict__ x0, float* __restrict__ ensemble_loss, int E,
+                              float* __restrict__ loss_terms) {
+    pdl_trigger();
+    pdl_wait();
+    const int IN = O + A;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < E) ensemble_loss[t] = 0.f;
+    if (t < 3) loss_terms[t] = 0.f;
+    if (t >= B * IN) return;
+    const int64_t b = t / IN;
+    const int j = (int)(t - b * IN);
+    x0[t] = j < O ? obs[b * O + j] : act[b * A + (j - O)];
+}
+
+// One thread per (member, row, output): loss share and dL/d(output).
+//   CRITIC_HEAD_MSE:      F.mse_loss against the shared target [B][Q] (ddpg_agent.py:138-149)
+//   CRITIC_HEAD_QUANTILE: quantile_huber_loss_f against target atoms [B][T] (tqc_agent.py:5-14)
+__global__ void k_critic_head(int kind, const float* __restrict__ out, const float* __restrict__ target, int T,
+                              int64_t B, int E, int Q, float clip_error, float* __restrict__ g,
+                              float* __restrict__ ensemble_loss, float* __restrict__ loss_terms) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t per = B * Q, total = per * E;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float part = 0.f;
+    int e = -1;
+    if (t < total) {
+        e = (int)(t / per);
+        const int64_t r = t - (int64_t)e * per;
+        const int64_t b = r / Q;
+        const int j = (int)(r - b * Q);
+        const float q = out[t];
+        if (kind == CRITIC_HEAD_MSE) {
+            const float wgt = 1.f / ((float)E * (float)B * (float)Q);
+            float diff = q - target[b * Q + j];
+            if (clip_error > 0.f) diff = fminf(fmaxf(diff, -clip_error), clip_error);
+            part = diff * diff * wgt;
+            g[t] = 2.f * diff * wgt;
+        } else {
+            const float wgt = 1.f / ((float)E * (float)B * (float)Q * (float)T);
+            const float tau = ((float)j + 0.5f) / (float)Q;
+            const float* tg = target + b * T;
+            float gr = 0.f;
+            for (int k = 0; k < T; ++k) {
+                const float dl = __ldg(tg + k) - q;
+                const float ad = fabsf(dl);
+                const float hub = ad > 1.f ? ad - 0.5f : 0.5f * dl * dl;
+                const float w = fabsf(tau - (dl < 0.f ? 1.f : 0.f));
+                part += w * hub;
+                gr -= w * fminf(fmaxf(dl, -1.f), 1.f);       // d huber / d q = -clip(delta, -1, 1)
+            }
+            part *= wgt;
+            g[t] = gr * wgt;
+        }
+    }
+    // warps never straddle two members when B*Q is a multiple of 32; otherwise one atomic per thread
+    const bool uniform = (per & 31) == 0;
+    if (uniform) {
+        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == 0 && e >= 0) { atomicAdd(ensemble_loss + e, part); atomicAdd(loss_terms, part); }
+    } else if (e >= 0) {
+        atomicAdd(ensemble_loss + e, part);
+        atomicAdd(loss_terms, part);
+    }
+}
+
+// ptu.soft_update_from_to (torch_modules/utils.py:151-155) after the optimizer step
+__global__ void k_soft_update(const float* __restrict__ p, float* __restrict__ tp, float tau, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        tp[i] = tp[i] * (1.f - tau) + p[i] * tau;
+}
+
+int launch_critic_train_chain(const mb_mlp_desc& d, int head_kind, float* params, float* exp_avg, float* exp_avg_sq,
+                              int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                              const float* obs, const float* act, int O, int A, const float* target, int T,
+                              int64_t B, float clip_error, float* target_params, float tau, float* ensemble_loss,
+                              float* loss_terms, void* ws, cudaStream_t s) {
+    const int L = d.num_layers, E = d.ensemble_size, Q = d.sizes[L];
+    if (E > 32) { set_error("critic chain: ensemble_size %d > 32", E); return MB_EUNSUPPORTED; }
+    CriticWs w = critic_carve(d, B, ws);
+    {
+        int64_t total = B * d.sizes[0];
+        total = total < E ? E : total;
+        launch_pdl(k_critic_prep, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, obs, act, O, A, B, w.x0,
+                   ensemble_loss, E, loss_terms);
+        MB_CUDA_LAUNCH_CHECK("k_critic_prep");
+    }
+    for (int l = 0; l < L; ++l) {
+        TgBatch tb = tg_members(0, E);
+        tb.nops = 1;
+        TgOp& o = tb.op[0];
+        o.mode = TG_FWD;
+        o.M = (int)B; o.N = d.sizes[l + 1]; o.R = d.sizes[l];
+        o.a = l == 0 ? w.x0 : w.z[l - 1]; o.lda = o.R; o.a_ss = l == 0 ? 0 : (int64_t)B * o.R;
+        o.a_act = l == 0 ? -1 : d.activation;
+        o.b = params + w_offset(d, l); o.ldb = o.N; o.b_ms = (int64_t)o.R * o.N;
+        o.bias = params + b_offset(d, l); o.bias_ms = o.N;
+        o.out = l + 1 < L ? w.z[l] : w.out; o.ldo = o.N; o.out_ss = (int64_t)B * o.N;
+        int rc = launch_tc_gemm(tb, s);
+        if (rc) return rc;
+    }
+    {
+        const int64_t total = (int64_t)E * B * Q;
+        launch_pdl(k_critic_head, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, head_kind,
+                   (const float*)w.out, target, T, B, E, Q, clip_error, w.g[L - 1], ensemble_loss, loss_terms);
+        MB_CUDA_LAUNCH_CHECK("k_critic_head");
+    }
+    TgBatch dwb = tg_members(0, E);
+    for (int l = L - 1; l >= 0; --l) {
+        const int K = d.sizes[l], N = d.sizes[l + 1];
+        TgOp& o = dwb.op[dwb.nops++];
+        o.mode = TG_DW;
+        o.M = K + 1; o.N = N; o.R = (int)B;
+        o.a = l == 0 ? w.x0 : w.z[l - 1]; o.lda = K; o.a_ss = l == 0 ? 0 : (int64_t)B * K; o.a_trans = 1;
+        o.a_act = l == 0 ? -1 : d.activation;
+        o.a_ones_row = K;
+        o.b = w.g[l]; o.ldb = N; o.b_ss = (int64_t)B * N;
+        o.w = params + w_offset(d, l); o.w_ms = (int64_t)K * N; o.wd = 0.f;
+        o.out = w.grads + w_offset(d, l); o.ldo = N; o.out_ms = (int64_t)K * N;
+        o.out_ones = w.grads + b_offset(d, l); o.out_ones_ms = N;
+        o.l2_acc = nullptr;
+        if (l > 0) {
+            TgBatch xb = tg_members(0, E);
+            xb.nops = 1;
+            TgOp& x = xb.op[0];
+            x.mode = TG_DX;
+            x.M = (int)B; x.N = K; x.R = N;
+            x.a = w.g[l]; x.lda = N; x.a_ss = (int64_t)B * N;
+            x.b = params + w_offset(d, l); x.ldb = N; x.b_ms = (int64_t)K * N; x.b_trans = 1;
+            x.z = w.z[l - 1]; x.ldz = K; x.z_ss = (int64_t)B * K; x.z_act = d.activation;
+            x.out = w.g[l - 1]; x.ldo = K; x.out_ss = (int64_t)B * K;
+            int rc = launch_tc_gemm(xb, s);
+            if (rc) return rc;
+        }
+    }
+    int rc = launch_tc_gemm(dwb, s);
+    if (rc) return rc;
+    AdamSegs segs;
+    segs.n = 0;
+    const int64_t n = param_count(d, false);
+    int64_t maxlen = 0;
+    for (int l = 0; l < L; ++l) {
+        const int64_t wn = (int64_t)E * d.sizes[l] * d.sizes[l + 1], bn = (int64_t)E * d.sizes[l + 1];
+        segs.off[segs.n] = w_offset(d, l); segs.len[segs.n++] = wn;
+        segs.off[segs.n] = b_offset(d, l); segs.len[segs.n++] = bn;
+        maxlen = wn > maxlen ? wn : maxlen;
+    }
+    const double hstep = (double)(adam_steps_done + 1);
+    const double bc1 = 1.0 - pow((double)beta1, hstep), bc2 = 1.0 - pow((double)beta2, hstep);
+    const int64_t nb = (maxlen + 255) / 256;
+    launch_pdl(k_adam, dim3((unsigned)(nb < 1184 ? nb : 1184), (unsigned)segs.n), dim3(256), 0, s, segs, params, exp_avg, exp_avg_sq,
+               (const float*)w.grads, beta1, beta2, eps, (float)(lr / bc1), (float)sqrt(bc2), (const float*)nullptr);
+    MB_CUDA_LAUNCH_CHECK("k_adam");
+    if (target_params != nullptr) {
+        launch_pdl(k_soft_update, dim3((unsigned)(nb < 1184 ? nb : 1184)), dim3(256), 0, s, (const float*)params,
+                   target_params, tau, n);
+        MB_CUDA_LAUNCH_CHECK("k_soft_update");
+    }
+    return MB_OK;
+}
+
 }  // namespace mb

@@ -267,6 +267,7 @@ k_tc_gemm(TgBatch gb, int nt_max) {
         return x;
     };
     const float* zb = mode == TG_DX ? op.z + (int64_t)slot * op.z_ss : nullptr;
+    const bool z_relu = op.z_act == MB_ACT_RELU;
     const float* wb = mode == TG_DW ? op.w + (int64_t)e * op.w_ms : nullptr;
     float* ob = op.out + (int64_t)slot * op.out_ss + (int64_t)e * op.out_ms;
     const int64_t ldz = op.ldz, ldo = op.ldo;
@@ -302,6 +303,7 @@ k_tc_gemm(TgBatch gb, int nt_max) {
             } else if (mode == TG_DX) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    if (z_relu) { vv[i] = cc[i] > 0.f ? vv[i] : 0.f; continue; }
                     const float sg = rcp_ftz(1.0f + ex2_ftz(cc[i] * -1.4426950408889634f));
                     vv[i] *= sg * (1.f + cc[i] * (1.f - sg));
                 }

@@ -258,10 +258,14 @@ class B200CriticTrainer(object):
     """Fused critic update for REDQ / SAC ensembles: forward over all E critics, ``F.mse_loss`` against
     the expanded target (optional ``clip_error``), backward, ``torch.optim.Adam`` and the soft target
     update, in one launch (``mb_critic_train_step``; the reference issues ~300 ATen calls plus a Python loop
-    over 6*E parameter tensors, torch_modules/utils.py:151-155).
+    over 6*E parameter tensors, torch_modules/utils.py:151-155).  Critics wider than 256 run the same update
+    as a chain of tensor-core layer GEMM launches.
 
     ``qf`` and ``qf_target`` are ``B200EnsembleQValue`` of the same shape; ``qf_lr``, ``soft_target_tau``,
-    ``target_update_freq`` and ``clip_error`` are the ``DDPGAgent`` arguments (ddpg_agent.py:44-60)."""
+    ``target_update_freq`` and ``clip_error`` are the ``DDPGAgent`` arguments (ddpg_agent.py:44-60).
+
+    With ``B200TQCQValue`` critics the loss is TQC's ``quantile_huber_loss_f`` (tqc_agent.py:5-14,59-66) and
+    ``q_target`` is ``atoms_target [B, n_target]`` (``mb_tqc_train_step``)."""
 
     def __init__(self, qf, qf_target=None, qf_lr=3e-4, soft_target_tau=5e-3, target_update_freq=1,
                  clip_error=None, optimizer_class="Adam", optimizer_kwargs={}):
@@ -295,12 +299,16 @@ class B200CriticTrainer(object):
         mod = qf.module
         obs, actions, q_target = (_lib.f32(t, dev) for t in (obs, actions, q_target))
         B = obs.shape[0]
-        assert obs.dim() == 2 and q_target.shape == (B, mod.output_size)
+        quantile = isinstance(qf, B200TQCQValue)
+        assert obs.dim() == 2 and q_target.dim() == 2 and q_target.shape[0] == B
+        assert quantile or q_target.shape[1] == mod.output_size
+        if quantile and self.clip_error:
+            raise NotImplementedError("clip_error applies to the MSE critic loss only (ddpg_agent.py:142-146)")
         if self.exp_avg.device != dev:
             self.exp_avg, self.exp_avg_sq = self.exp_avg.to(dev), self.exp_avg_sq.to(dev)
         need = L.mb_critic_train_workspace_bytes(ctypes.byref(mod.desc), B)
         if need == 0:
-            raise NotImplementedError("the fused critic update covers layer widths up to 256")
+            raise NotImplementedError("critic shape not covered: %s" % _lib.lib().mb_last_error().decode())
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         el = torch.zeros(mod.ensemble_size, device=dev)
@@ -308,13 +316,16 @@ class B200CriticTrainer(object):
         tgt = None
         if self.qf_target is not None and self.num_train_steps % self.target_update_freq == 0:
             tgt = self.qf_target.module.flat.data
-        with torch.cuda.device(dev):
-            _lib.check(L.mb_critic_train_step(
-                ctypes.byref(mod.desc), _lib.ptr(mod.flat.data), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+        head = (ctypes.byref(mod.desc), _lib.ptr(mod.flat.data), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                 self.num_train_steps, float(self.qf_lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                _lib.ptr(obs), _lib.ptr(actions), qf.observation_shape[0], qf.action_shape[0], _lib.ptr(q_target), B,
-                float(self.clip_error or 0.0), _lib.ptr(tgt), float(self.soft_target_tau), _lib.ptr(el), _lib.ptr(terms),
-                _lib.ptr(self._ws), self._ws.numel(), _lib.stream(dev)))
+                _lib.ptr(obs), _lib.ptr(actions), qf.observation_shape[0], qf.action_shape[0], _lib.ptr(q_target))
+        tail = (_lib.ptr(tgt), float(self.soft_target_tau), _lib.ptr(el), _lib.ptr(terms), _lib.ptr(self._ws),
+                self._ws.numel(), _lib.stream(dev))
+        with torch.cuda.device(dev):
+            if quantile:
+                _lib.check(L.mb_tqc_train_step(*head, int(q_target.shape[1]), B, *tail))
+            else:
+                _lib.check(L.mb_critic_train_step(*head, B, float(self.clip_error or 0.0), *tail))
         self.num_train_steps += 1
         mod.mark_weights_changed()
         if tgt is not None:

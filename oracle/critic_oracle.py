@@ -80,8 +80,22 @@ def tqc_atoms(W, b, obs, act, number_drop=None, percentage_drop=None, activation
     return torch.mean(atoms, dim=-1, keepdim=True), atoms
 
 
+def quantile_huber(samples, atoms):
+    """quantile_huber_loss_f, mirl/agents/tqc_agent.py:5-14: ``samples [B,T]`` target atoms, ``atoms [E,B,Q]``.
+    Returns the loss and its hand-written gradient with respect to ``atoms``."""
+    delta = samples[None, :, :, None] - atoms[..., None, :]               # [E,B,T,Q]
+    ad = delta.abs()
+    huber = torch.where(ad > 1, ad - 0.5, 0.5 * delta * delta)
+    Q = atoms.shape[-1]
+    tau = torch.arange(Q, dtype=atoms.dtype) / Q + 0.5 / Q
+    wgt = (tau - (delta < 0).to(atoms.dtype)).abs()
+    loss = (wgt * huber).mean()
+    grad = -(wgt * delta.clamp(-1.0, 1.0)).sum(2) / delta.numel()
+    return loss, grad
+
+
 def critic_update(W, b, opt, target_W, target_b, obs, act, q_target, lr=3e-4, tau=5e-3, clip_error=None,
-                  activation="relu"):
+                  activation="relu", head="mse"):
     """Critic half of SACAgent.train_from_torch_batch (mirl/agents/sac_agent.py:160-166):
     DDPGAgent.compute_qf_loss (ddpg_agent.py:138-149: F.mse_loss of the [E,B,out] ensemble prediction against
     the expanded target, optional clip_error), hand-written backward, torch.optim.Adam (ddpg_agent.py:82-86)
@@ -98,11 +112,14 @@ def critic_update(W, b, opt, target_W, target_b, obs, act, q_target, lr=3e-4, ta
         if l < L - 1:
             hs.append(torch.relu(z))
     q = zs[-1]
-    diff = q - q_target.unsqueeze(0)
-    if clip_error is not None and clip_error > 0:
-        diff = torch.clamp(diff, -clip_error, clip_error)
-    loss = (diff * diff).mean()
-    g = 2.0 * diff / diff.numel()
+    if head == "quantile":                 # TQCAgent.compute_qf_loss, tqc_agent.py:59-66; q_target = atoms [B,T]
+        loss, g = quantile_huber(q_target, q)
+    else:
+        diff = q - q_target.unsqueeze(0)
+        if clip_error is not None and clip_error > 0:
+            diff = torch.clamp(diff, -clip_error, clip_error)
+        loss = (diff * diff).mean()
+        g = 2.0 * diff / diff.numel()
     gW, gb = [None] * L, [None] * L
     for l in range(L - 1, -1, -1):
         gW[l] = hs[l].transpose(1, 2).matmul(g)

@@ -200,6 +200,15 @@ def critic_q_target(x):
     return (3.0 * x["rewards"] + x["log_prob"]).astype(np.float32)
 
 
+def tqc_atoms_target(x, seed, n_target=115):
+    """Synthetic target atoms ``[B, n_target]`` for the TQC critic-update fixture (ascending per row, like
+    TQCAgent.compute_q_target's sorted-and-truncated atoms; spread wide enough that both Huber branches occur)."""
+    rs = np.random.RandomState(seed)
+    B = x["rewards"].shape[0]
+    spread = np.sort(rs.standard_normal((B, n_target)), axis=1)
+    return (x["rewards"] + 0.5 * x["log_prob"] + 1.5 * spread).astype(np.float32)
+
+
 def policy_state_dict(W, b):
     """Reference ``GaussianPolicy.state_dict()`` keys (a plain MLP: ``module.net.{2l}.weight`` / ``.bias``)."""
     sd = {}

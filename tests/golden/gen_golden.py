@@ -502,6 +502,50 @@ def gen_critic_update():
         print(tag, out["loss"])
 
 
+def gen_tqc_update():
+    """Critic half of TQCAgent's update (sac_agent.py:160-166 with tqc_agent.py:59-66): TQCAgent.compute_qf_loss called
+    on the reference classes (TQCQValue 5 x [512,512,512] relu x 25 quantiles, configs/tqc.json), torch.optim.Adam
+    (lr 3e-4) and ptu.soft_update_from_to(qf, qf_target, 5e-3): five updates on batch 256 against 115 target atoms."""
+    import types
+    import mirl.torch_modules.utils as ptu
+    from mirl.agents.tqc_agent import TQCAgent
+    from mirl.values.distributional_value import TQCQValue
+    env = ref_shim.FakeEnv()
+    c = cases.TQC
+    sizes = [23] + c["hidden"] + [c["out"]]
+
+    def build(seed):
+        q = TQCQValue(env, ensemble_size=c["E"], number_head=c["out"], hidden_layers=list(c["hidden"]),
+                      activation=c["act"])
+        W, b = cases.mlp_params(seed, c["E"], sizes)
+        q.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(W, b).items()})
+        return q
+    qf, qt = build(73), build(173)
+    opt = torch.optim.Adam(qf.parameters(), lr=3e-4)
+    stub = types.SimpleNamespace(qf=qf, _log_q_info=lambda *a: {})
+    out = {"loss": []}
+    steps = 5
+    for s_ in range(steps):
+        x = cases.critic_inputs(740 + s_, 256)
+        atoms_target = T(cases.tqc_atoms_target(x, 760 + s_))
+        loss, _ = TQCAgent.compute_qf_loss(stub, T(x["obs"]), T(x["act"]), atoms_target)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ptu.soft_update_from_to(qf, qt, 5e-3)
+        out["loss"].append(float(loss))
+        if s_ + 1 in (1, steps):
+            names = [n for n, _ in qf.named_parameters()]
+            out["param_proj_%d" % (s_ + 1)] = np.stack([proj(p, 5000 + i) for i, p in enumerate(qf.parameters())])
+            out["target_proj_%d" % (s_ + 1)] = np.stack([proj(p, 6000 + i) for i, p in enumerate(qt.parameters())])
+            out["m_proj_%d" % (s_ + 1)] = np.stack([proj(opt.state[p]["exp_avg"], 7000 + i)
+                                                     for i, p in enumerate(qf.parameters())])
+    out["loss"] = np.array(out["loss"], dtype=np.float64)
+    out["names"] = np.array(names)
+    np.savez(os.path.join(HERE, "tqc_update.npz"), **out)
+    print("tqc_update", out["loss"])
+
+
 def gen_policy():
     """GaussianPolicy.action (gaussian_policy.py:35-47 -> gaussian.py:55-97,199-204), 17 -> 256 -> 256 -> 12 relu,
     tanh-squashed: reparameterised and plain samples with log-prob / mean / std, and the deterministic action.
@@ -538,7 +582,7 @@ def main():
         globals()["gen_" + only]()
     else:
         gen_forward(); gen_step(); gen_dist(); gen_loss(); gen_train(); gen_critics(); gen_keys(); gen_pool()
-        gen_trainloop(); gen_collect(); gen_extrapool(); gen_critic_update(); gen_policy()
+        gen_trainloop(); gen_collect(); gen_extrapool(); gen_critic_update(); gen_tqc_update(); gen_policy()
     for f in sorted(os.listdir(HERE)):
         if f.endswith((".npz", ".json")):
             print("%8d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))

@@ -425,6 +425,73 @@ def test_fused_critic_update_matches_reference(tag, clip, steps):
                 assert abs(gm[0] - rm[0]) <= 2e-3 * rm[0] + 2e-5, ("exp_avg", name, gm, rm)
 
 
+def test_tqc_critic_update_matches_reference():
+    """B200CriticTrainer on B200TQCQValue critics against the reference's TQCAgent.compute_qf_loss
+    (quantile_huber_loss_f) + torch.optim.Adam + soft_update_from_to run (configs/tqc.json shape: 5 critics,
+    3x512 relu, 25 quantiles, 115 target atoms, batch 256): loss curve, parameters, moments, target network."""
+    import mirl_b200
+    from tests.helpers_gpu import make_critic
+    g = golden("tqc_update.npz")
+    qf, _ = make_critic("tqc", 73)
+    qt, _ = make_critic("tqc", 173)
+    tr = mirl_b200.B200CriticTrainer(qf, qt, qf_lr=3e-4, soft_target_tau=5e-3)
+    assert tr.supported()
+    steps = len(g["loss"])
+    for s_ in range(steps):
+        x = cases.critic_inputs(740 + s_, 256)
+        info = tr.update(T(x["obs"], "cuda"), T(x["act"], "cuda"), T(cases.tqc_atoms_target(x, 760 + s_), "cuda"))
+        assert abs(info["qf/loss"] - g["loss"][s_]) <= 1e-3 * abs(g["loss"][s_]), (s_, info, g["loss"][s_])
+        if s_ + 1 in (1, steps):
+            msd = qf.module.reference_state_dict("module.", flat=tr.exp_avg)
+            for i, (name, p, pt) in enumerate(zip(g["names"], qf.parameters(), qt.parameters())):
+                name = str(name)
+                n = p.numel()
+                got, ref = proj(p, 5000 + i), g["param_proj_%d" % (s_ + 1)][i]
+                assert abs(got[0] - ref[0]) <= 3e-4 * (s_ + 1) * 0.05 * np.sqrt(n) + 1e-4 * ref[0], (name, got, ref)
+                got, ref = proj(pt, 6000 + i), g["target_proj_%d" % (s_ + 1)][i]
+                assert abs(got[0] - ref[0]) <= 1e-4 * ref[0] + 1e-6, ("target", name, got, ref)
+                assert abs(got[1] - ref[1]) <= 1e-3 * ref[0] + 1e-6, ("target", name, got, ref)
+                gm, rm = proj(msd[name], 7000 + i), g["m_proj_%d" % (s_ + 1)][i]
+                assert abs(gm[0] - rm[0]) <= 2e-3 * rm[0] + 2e-5, ("exp_avg", name, gm, rm)
+
+
+def test_wide_critic_update_chain_matches_oracle():
+    """mb_critic_train_step on critics wider than the persistent kernel covers (3 members, 2x384 relu,
+    batch 200, clip_error): the launch-chain path against critic_oracle.critic_update (pinned to the reference by
+    the critic_update fixtures), three steps with the soft target update."""
+    import mirl_b200
+    from oracle import critic_oracle as co
+    E, sizes = 3, [23, 384, 384, 1]
+    W, b = cases.mlp_params(75, E, sizes)
+    tW, tb = cases.mlp_params(175, E, sizes)
+
+    def build(W_, b_):
+        q = mirl_b200.B200EnsembleQValue(FakeEnv(), ensemble_size=E, hidden_layers=sizes[1:-1], activation="relu")
+        q.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(W_, b_).items()})
+        return q.to("cuda")
+    qf, qt = build(W, b), build(tW, tb)
+    tr = mirl_b200.B200CriticTrainer(qf, qt, qf_lr=1e-3, soft_target_tau=0.01, clip_error=0.7)
+    oW, ob = [T(a.copy()) for a in W], [T(a.copy()) for a in b]
+    otW, otb = [T(a.copy()) for a in tW], [T(a.copy()) for a in tb]
+    opt = {"step": 0, "m": [torch.zeros_like(t) for t in oW + ob], "v": [torch.zeros_like(t) for t in oW + ob]}
+    rs = np.random.RandomState(5)
+    for s_ in range(3):
+        x = cases.critic_inputs(770 + s_, 200)
+        tgt = rs.standard_normal((200, 1)).astype(np.float32)
+        want = co.critic_update(oW, ob, opt, otW, otb, T(x["obs"]), T(x["act"]), T(tgt), lr=1e-3, tau=0.01,
+                                clip_error=0.7)
+        info = tr.update(T(x["obs"], "cuda"), T(x["act"], "cuda"), T(tgt, "cuda"))
+        assert abs(info["qf/loss"] - float(want)) <= 1e-3 * abs(float(want)), (s_, info, float(want))
+    sd, tsd = qf.module.reference_state_dict("module."), qt.module.reference_state_dict("module.")
+    for l in range(len(oW)):
+        for e in range(E):
+            for key, o_, ot_ in (("weight", oW[l][e], otW[l][e]), ("bias", ob[l][e], otb[l][e])):
+                name = "module.net.%d.%s_net%d" % (2 * l, key, e)
+                # Adam's first steps move every weight by about lr whatever the gradient's size: compare to that scale
+                assert (sd[name].cpu() - o_).abs().max() <= 0.15 * 3 * 1e-3, name
+                assert_close(tsd[name].cpu(), ot_, what="target " + name)
+
+
 # ---- N1: policy action -------------------------------------------------------------------------------
 def test_gaussian_policy_action_matches_reference():
     """B200GaussianPolicy.action against the reference GaussianPolicy (17 -> 256 -> 256 -> 12 relu, tanh-squashed):
