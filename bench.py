@@ -329,6 +329,16 @@ def secondary_metrics(dev, world, rank, timed):
                             "config": "REDQ: 10 critics 2x256 relu, batch 256: forward + MSE + backward + Adam + soft "
                                       "target update in one launch"}
     t, _ = make_critic("tqc", 81, device=dev)
+    tt, _ = make_critic("tqc", 181, device=dev)
+    tct = mirl_b200.B200CriticTrainer(t, tt)
+    ya = T(cases.tqc_atoms_target(x, 73), dev)
+    ms = timed(lambda: tct.update_async(o, a, ya), 100, 10) / 100
+    tm = 23 * 512 + 2 * 512 * 512 + 512 * 25
+    tf = (2 * tm * 3) * 5 * B / (ms * 1e-3) / 1e12
+    out["tqc_update"] = {"updates_per_s": 1e3 / ms, "kernel_ms": ms, "achieved": tf, "peak": pk["tensor"],
+                         "unit": "TFLOP/s", "frac": tf / pk["tensor"], "bound": "latency (11 launches)",
+                         "config": "TQC: 5 critics 3x512 relu x 25 quantiles, batch 256, 115 target atoms: tcgen05 layer "
+                                   "GEMM chain + quantile-Huber head + Adam + soft target update"}
     ms = timed(lambda: q.q_target(o, a, r, d, lp, alpha=0.2, sample_number=2, batchwise_sample=True), 200, 20) / 200
     tf = 2 * 2 * cm * B / (ms * 1e-3) / 1e12                                             # 2 drawn members
     out["redq_target"] = {"targets_per_s": world * B / (ms * 1e-3), "kernel_ms": ms, "achieved": tf, "peak": pk["tensor"],

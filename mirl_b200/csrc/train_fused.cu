@@ -58,8 +58,11 @@ constexpr int kT = kWarps * 32;
 constexpr int kThreads = kT;
 constexpr int kIssuer = kWarps - 1;
 constexpr int kRows = 16;        // batch rows per block (one MMA M tile)
-constexpr int kChunk = 64;       // batch rows per streamed chunk of phase B (and the ring's stage size)
-constexpr int kWChunk = 8 * kWarps;  // weight rows per streamed chunk of phase A: one dX output tile per warp (= 64)
+constexpr int kChunk = 32;       // batch rows per streamed chunk of phase B (and the ring's stage size)
+constexpr int kWChunk = 32;      // weight rows per streamed chunk of phase A: 2 forward k-steps, 4 dX output tiles
+constexpr int kStages = 4;       // ring depth: up to three bulk copies in flight behind the chunk being consumed
+constexpr int kNK = kChunk / 16; // k-steps per chunk
+constexpr int kNormMax = 512;    // cached normaliser columns: inputs (<= 256) + deltas (<= 256)
 constexpr int kMaxStrips = 4;    // 16-row weight strips per phase-B job
 constexpr int kSweep = 4;        // float4 per thread and batch of the Adam sweep (5 measured 3 % slower: register pressure)
 
@@ -112,6 +115,12 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     return v;
 }
 // G CTAs of one member: arrive (after the CTA's global writes) / wait until `target` arrivals
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void member_arrive(unsigned* cnt) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -164,12 +173,12 @@ struct StepScalars { float step_size, bc2_sqrt; };
 
 // ------------------------------------------------------------------------------------------------------
 // Global layouts of the phase-A -> phase-B hand-over (bf16 elements):
-//   g_l : [E][Bp/64][hi|lo][64][Ns]   a 64-row chunk of both halves is ONE bulk copy into the ring
-//   h_l : [hi|lo][Kp/16 strips][E][Bp][16]   a job's strip x 64 rows is one 2 KB bulk copy; the two 16-byte
+//   g_l : [E][Bp/32][hi|lo][32][Ns]   a 32-row chunk of both halves is ONE bulk copy into the ring
+//   h_l : [hi|lo][Kp/16 strips][E][Bp][16]   a job's strip x 32 rows is one 1 KB bulk copy; the two 16-byte
 //         units of a row are swapped for rows with bit 2 set, which makes the transposed ldmatrix reads of
 //         the 32-byte-stride tile bank-conflict free
 __device__ __forceinline__ int64_t g_elem_off(const FusedLayer& ly, int e, int Bp, int b, int half) {
-    return ly.g_off + ((((int64_t)e * (Bp >> 6) + (b >> 6)) * 2 + half) * kChunk + (b & 63)) * ly.Ns;
+    return ly.g_off + ((((int64_t)e * (Bp / kChunk) + (b / kChunk)) * 2 + half) * kChunk + (b % kChunk)) * ly.Ns;
 }
 __device__ __forceinline__ int64_t h_elem_off(const FusedLayer& ly, int E, int e, int Bp, int b, int strip, int half) {
     return ly.h_off + ((((int64_t)half * (ly.Kp >> 4) + strip) * E + e) * Bp + b) * 16;
@@ -178,13 +187,16 @@ __device__ __forceinline__ int64_t h_elem_off(const FusedLayer& ly, int E, int e
 
 // ---- branch-free inner loops (the guarded generic loops below them keep every k-step behind a branch,
 // which stops ptxas from overlapping a k-step's fragment loads with the previous k-step's MMAs) -----------
-// forward: a full 64-row chunk (4 k-steps), NTW n-tiles per warp (tiles warp, warp+8, ...)
-template <int NTW>
-__device__ __forceinline__ void fwd_chunk4(float (&acc)[4][4], const __nv_bfloat16* Ah, const __nv_bfloat16* Al,
-                                           const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int a_off, int b_off, int Ns,
-                                           int warp) {
+// forward: a chunk of NK k-steps (64 rows: 4), NTW n-tiles per warp (tiles warp, warp+8, ...)
+template <int NK, int NTW>
+__device__ __forceinline__ void fwd_chunk(float (&acc)[4][4], const __nv_bfloat16* Ah, const __nv_bfloat16* Al,
+                                          const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int a_off, int b_off, int Ns,
+                                          int warp) {
+#ifdef MB_EXP_NOMMA
+    return;
+#endif
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < NK; ++kk) {
         uint32_t ah[4], al[4];
         ldsm_x4(ah, smem_u32(Ah + a_off + kk * 16));
         ldsm_x4(al, smem_u32(Al + a_off + kk * 16));
@@ -199,13 +211,24 @@ __device__ __forceinline__ void fwd_chunk4(float (&acc)[4][4], const __nv_bfloat
         for (int i = 0; i < NTW; ++i) mma3(acc[i], ah, al, bh[i], bl[i]);
     }
 }
-// phase B: a full 64-row chunk (4 groups of 16 batch rows), NS strips x NTW n-tiles per warp
+template <int NTW>
+__device__ __forceinline__ void fwd_chunk_nk(int nk, float (&acc)[4][4], const __nv_bfloat16* Ah, const __nv_bfloat16* Al,
+                                             const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int a_off, int b_off, int Ns,
+                                             int warp) {
+    switch (nk) {
+    case 4: fwd_chunk<4, NTW>(acc, Ah, Al, Wh, Wl, a_off, b_off, Ns, warp); break;
+    case 3: fwd_chunk<3, NTW>(acc, Ah, Al, Wh, Wl, a_off, b_off, Ns, warp); break;
+    case 2: fwd_chunk<2, NTW>(acc, Ah, Al, Wh, Wl, a_off, b_off, Ns, warp); break;
+    default: fwd_chunk<1, NTW>(acc, Ah, Al, Wh, Wl, a_off, b_off, Ns, warp); break;
+    }
+}
+// phase B: a full chunk (kNK groups of 16 batch rows), NS strips x NTW n-tiles per warp
 template <int NS, int NTW>
-__device__ __forceinline__ void dw_chunk4(float (&acc)[kMaxStrips][4][4], const __nv_bfloat16* Gh, const __nv_bfloat16* Gl,
-                                          const __nv_bfloat16* Hh, const __nv_bfloat16* Hl, int g_off, int Ns, int warp,
-                                          int lane) {
+__device__ __forceinline__ void dw_chunk(float (&acc)[kMaxStrips][4][4], const __nv_bfloat16* Gh, const __nv_bfloat16* Gl,
+                                         const __nv_bfloat16* Hh, const __nv_bfloat16* Hl, int g_off, int Ns, int warp,
+                                         int lane) {
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < kNK; ++kk) {
         uint32_t bh[NTW][2], bl[NTW][2];
 #pragma unroll
         for (int i = 0; i < NTW; ++i) {
@@ -225,6 +248,17 @@ __device__ __forceinline__ void dw_chunk4(float (&acc)[kMaxStrips][4][4], const 
         }
     }
 }
+template <int NTW>
+__device__ __forceinline__ void dw_chunk_ns(int ns, float (&acc)[kMaxStrips][4][4], const __nv_bfloat16* Gh,
+                                            const __nv_bfloat16* Gl, const __nv_bfloat16* Hh, const __nv_bfloat16* Hl,
+                                            int g_off, int Ns, int warp, int lane) {
+    switch (ns) {
+    case 4: dw_chunk<4, NTW>(acc, Gh, Gl, Hh, Hl, g_off, Ns, warp, lane); break;
+    case 3: dw_chunk<3, NTW>(acc, Gh, Gl, Hh, Hl, g_off, Ns, warp, lane); break;
+    case 2: dw_chunk<2, NTW>(acc, Gh, Gl, Hh, Hl, g_off, Ns, warp, lane); break;
+    default: dw_chunk<1, NTW>(acc, Gh, Gl, Hh, Hl, g_off, Ns, warp, lane); break;
+    }
+}
 
 // KS = compile-time bound of the dX reduction length in k-steps (its operand fragments live in registers)
 // NT = n-tiles (8 columns) per consumer warp: widths up to 8 * kWarps * NT
@@ -239,28 +273,32 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
     const int L = a.L;
     const int act_kind = a.act;
 
-    // [stage 0 | stage 1 | act 0 | act 1 | z | head | red]
+    // [stage 0 .. kStages-1 | act 0 | act 1 | z | head | red]
+    const int ring_bytes = kStages * a.stage_bytes;
     __nv_bfloat16* const stage0 = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-    __nv_bfloat16* const stage1 = reinterpret_cast<__nv_bfloat16*>(smem_raw + a.stage_bytes);
-    __nv_bfloat16* const act0 = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * a.stage_bytes);
-    __nv_bfloat16* const act1 = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * a.stage_bytes + a.act_bytes);
-    float* const zbuf = reinterpret_cast<float*>(smem_raw + 2 * a.stage_bytes + 2 * a.act_bytes);
-    float* const headbuf = reinterpret_cast<float*>(smem_raw + 2 * a.stage_bytes + 2 * a.act_bytes + a.z_bytes);
-    float* const redbuf = reinterpret_cast<float*>(smem_raw + 2 * a.stage_bytes + 2 * a.act_bytes + a.z_bytes + a.head_bytes);
-    auto stage_ptr = [&](int s) { return s ? stage1 : stage0; };
+    __nv_bfloat16* const act0 = reinterpret_cast<__nv_bfloat16*>(smem_raw + ring_bytes);
+    __nv_bfloat16* const act1 = reinterpret_cast<__nv_bfloat16*>(smem_raw + ring_bytes + a.act_bytes);
+    float* const zbuf = reinterpret_cast<float*>(smem_raw + ring_bytes + 2 * a.act_bytes);
+    float* const headbuf = reinterpret_cast<float*>(smem_raw + ring_bytes + 2 * a.act_bytes + a.z_bytes);
+    float* const redbuf = reinterpret_cast<float*>(smem_raw + ring_bytes + 2 * a.act_bytes + a.z_bytes + a.head_bytes);
+    auto stage_ptr = [&](int s) { return reinterpret_cast<__nv_bfloat16*>(smem_raw + s * a.stage_bytes); };
     auto act_ptr = [&](int s) { return s ? act1 : act0; };
+    // phase B: h tiles of a stage, [hi|lo][strip][kChunk rows][16], carved from the two act buffers (contiguous)
+    auto htile_ptr = [&](int s) { return act0 + s * (2 * kMaxStrips * kChunk * 16); };
     __shared__ StepScalars s_sc;
     __shared__ float s_part[kWarps];
-    __shared__ int64_t s_rowidx[kRows];
+    __shared__ int64_t s_rowidx[3][kRows];            // [step parity]: the step's first block (prefetched); [2]: further blocks
+    __shared__ float s_norm[2 * kNormMax];            // [mean | std + eps] of [obs | act | delta] (constant over the launch)
     __shared__ float s_tgt[kRows][64 + 1];            // head targets of the block (normalised delta | reward) and the loss mask
     __shared__ float s_bound[2][64];                  // max / min log-std of this member
-    __shared__ __align__(8) uint64_t s_bar[4];        // full[2] ("chunk landed"), empty[2] ("chunk consumed")
-    const uint32_t full0 = smem_u32(&s_bar[0]), empty0 = smem_u32(&s_bar[2]);
+    __shared__ __align__(8) uint64_t s_bar[2 * kStages];   // full[] ("chunk landed"), empty[] ("chunk consumed")
+    __shared__ float4 s_xchg[4][2][32];               // dX: partial tiles handed between the two warps of a pair
+    const uint32_t full0 = smem_u32(&s_bar[0]), empty0 = smem_u32(&s_bar[kStages]);
     if (tid == 0) {
-        mbar_init(full0, 1);
-        mbar_init(full0 + 8, 1);
-        mbar_init(empty0, kWarps);
-        mbar_init(empty0 + 8, kWarps);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, kWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int t = tid; t < a.act_bytes / 4; t += kThreads) {      // padding columns must hold finite values
@@ -268,20 +306,20 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
         reinterpret_cast<uint32_t*>(act1)[t] = 0u;
     }
     __syncthreads();
-    // Ring protocol.  Use number u (0, 1, 2, ... over the whole kernel) occupies stage u & 1.  The issuer
+    // Ring protocol.  Use number u (0, 1, 2, ... over the whole kernel) occupies stage u % kStages.  The issuer
     // (lane 0 of warp kIssuer, which has the fewest tiles) waits for the stage's previous use to be released
-    // by all 8 warps and issues the bulk copy of use u + 1 before it consumes use u; a warp waits for the
-    // copy to land, computes, and releases.  No CTA-wide barrier per chunk.
+    // by all 8 warps and keeps up to kStages - 1 bulk copies in flight behind the use being consumed; a warp
+    // waits for the copy to land, computes, and releases.  No CTA-wide barrier per chunk.
     uint32_t use = 0, use_p = 0;                      // uses consumed (every thread) / issued (issuer warp)
     auto producer_acquire = [&]() -> int {            // -> stage
-        const int s = use_p & 1;
-        if (use_p >= 2) mbar_wait(empty0 + 8 * s, ((use_p >> 1) & 1) ^ 1);
+        const int s = use_p % kStages;
+        if (use_p >= kStages) mbar_wait(empty0 + 8 * s, ((use_p / kStages) & 1) ^ 1);
         ++use_p;
         return s;
     };
     auto consumer_wait = [&]() -> int {
-        const int s = use & 1;
-        mbar_wait(full0 + 8 * s, (use >> 1) & 1);
+        const int s = use % kStages;
+        mbar_wait(full0 + 8 * s, (use / kStages) & 1);
         ++use;
         return s;
     };
@@ -329,13 +367,42 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
     const int npass = 2 * L - 1;
     auto pass_layer = [&](int p) { return p < L ? p : 2 * L - 1 - p; };
     double b1t = a.beta1_pow0, b2t = a.beta2_pow0;    // beta^t as running products (thread 0)
+    // batch of a step inside the epoch schedule (pe_model_trainer.py:240,268): first row and row count
+    auto sched = [&](int step_, int64_t& j0_, int& B_) {
+        const int64_t kb = (a.first_step + step_) % a.steps_per_epoch;
+        j0_ = kb * a.batch_size;
+        B_ = (int)min((int64_t)a.batch_size, a.train_length - j0_);
+    };
+    // data row of batch row b (-1 beyond the batch): the bootstrap table when there is one (pe_model_trainer.py:179)
+    auto row_index = [&](int64_t j0_, int B_, int b) -> int64_t {
+        if (b >= B_) return -1;
+        return a.index ? a.index[(int64_t)e * a.index_stride + j0_ + b]
+                       : (a.per_member_rows ? (int64_t)e * a.batch_size + b : (int64_t)b);
+    };
+    // the first block's row indices of step s live in s_rowidx[s & 1], fetched while step s - 1 is in phase B
+    auto prefetch_rows = [&](int step_) {
+        if (step_ >= a.nsteps || tid >= kRows) return;
+        int64_t j0_;
+        int B_;
+        sched(step_, j0_, B_);
+        s_rowidx[step_ & 1][tid] = row_index(j0_, B_, slot * kRows + tid);
+    };
+    prefetch_rows(0);
+    if (a.norm != nullptr) {
+        const int O = a.O, A = a.A, IN = O + A;
+        for (int c = tid; c < IN + O; c += kThreads) {
+            const float* mu = c < O ? a.norm + c : (c < IN ? a.norm + 2 * O + (c - O) : a.norm + 2 * O + 2 * A + (c - IN));
+            const int w = c < O ? O : (c < IN ? A : O);
+            s_norm[c] = mu[0];
+            s_norm[kNormMax + c] = mu[w] + kNormEps;
+        }
+    }
+    __syncthreads();
 
     for (int step = 0; step < a.nsteps; ++step) {
-        // batch of this step inside the epoch schedule (pe_model_trainer.py:240,268)
-        const int64_t tglob = a.first_step + step;
-        const int64_t kb = tglob % a.steps_per_epoch;
-        const int64_t j0 = kb * a.batch_size;
-        const int B = (int)min((int64_t)a.batch_size, a.train_length - j0);
+        int64_t j0;
+        int B;
+        sched(step, j0, B);
         const int nblk = (B + kRows - 1) / kRows;
         const float invB = 1.f / (float)B;
         float* const eloss = a.ensemble_loss + (int64_t)step * a.E;
@@ -354,7 +421,6 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 if (warp != kIssuer || ip >= npass) return;
                 const FusedLayer& ly = a.ly[pass_layer(ip)];
                 const int st = producer_acquire();
-                fence_proxy_async();
                 if (lane == 0) {
                     const int rows = min(kWChunk, ly.Kp - ic * kWChunk);
                     const uint32_t bytes = (uint32_t)rows * ly.Ns * 4;
@@ -365,73 +431,95 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 }
                 if (++ic * kWChunk >= ly.Kp) { ic = 0; ++ip; }
             };
-            issue_w();
-            // ---- row indices of the block, then the normalised inputs [obs | act | 1 | 0...] as bf16 hi/lo
-            if (tid < kRows) {
-                const int b = row0 + tid;
-                int64_t r = -1;
-                if (b < B) r = a.index ? a.index[(int64_t)e * a.index_stride + j0 + b]
-                                       : (a.per_member_rows ? (int64_t)e * a.batch_size + b : (int64_t)b);
-                s_rowidx[tid] = r;
+            for (int i = 0; i < kStages - 1; ++i) issue_w();
+            // ---- row indices of the block (the step's first block: fetched a step ahead), then every global
+            // operand of the staging in ONE round trip: the raw loads of the inputs and of the head operands are
+            // issued before any of them is consumed (normaliser statistics sit in shared memory)
+            int64_t* const ridx = s_rowidx[blk == slot ? (step & 1) : 2];
+            if (blk != slot) {
+                if (tid < kRows) ridx[tid] = row_index(j0, B, row0 + tid);
+                consumer_sync();
             }
-            consumer_sync();
             {
                 const FusedLayer& l0 = a.ly[0];
-                const int As = l0.As, IN = l0.K, O = a.O;
+                const int As = l0.As, IN = l0.K, O = a.O, A = a.A, D = a.D;
+                const bool nll = a.head_kind == FUSED_HEAD_NLL;
                 __nv_bfloat16* ah = act0;
                 __nv_bfloat16* al = ah + kRows * a.as_max;
-                for (int t = tid; t < kRows * (As / 2); t += kT) {
-                    const int i = t / (As / 2), j = (t % (As / 2)) * 2;
-                    const int64_t r = s_rowidx[i];
-                    float v[2] = {0.f, 0.f};
-                    if (r >= 0) {
+                const int items1 = kRows * (As / 2), items2 = nll ? kRows * (D + 1) : 0;
+                float bnd = 0.f;
+                const bool has_bnd = nll && tid < 2 * 64 && (tid & 63) < D;
+                if (has_bnd) bnd = __ldcg(a.params + ((tid >> 6) ? a.minls_off : a.maxls_off) + (int64_t)e * D + (tid & 63));
+                for (int base = 0; base < max(items1, items2); base += 2 * kT) {
+                    float xr[2][2], hr[2];
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int c = j + q;
-                            if (c < O) {
-                                const float x = a.obs[r * O + c];
-                                v[q] = a.norm ? (x - a.norm[c]) / (a.norm[O + c] + kNormEps) : x;
-                            } else if (c < IN) {
-                                const int ca = c - O;
-                                const float x = a.actn[r * a.A + ca];
-                                v[q] = a.norm ? (x - a.norm[2 * O + ca]) / (a.norm[2 * O + a.A + ca] + kNormEps) : x;
-                            } else if (c == IN) {
-                                v[q] = 1.f;
+                    for (int u = 0; u < 2; ++u) {
+                        const int t = base + tid + u * kT;
+                        xr[u][0] = xr[u][1] = hr[u] = 0.f;
+                        if (t < items1) {
+                            const int i = t / (As / 2), j = (t % (As / 2)) * 2;
+                            const int64_t r = ridx[i];
+                            if (r >= 0) {
+#pragma unroll
+                                for (int q = 0; q < 2; ++q) {
+                                    const int c = j + q;
+                                    if (c < O) xr[u][q] = __ldg(a.obs + r * O + c);
+                                    else if (c < IN) xr[u][q] = __ldg(a.actn + r * A + (c - O));
+                                }
+                            }
+                        }
+                        if (t < items2) {
+                            const int i = t / (D + 1), j = t - i * (D + 1);
+                            const int64_t r = ridx[i];
+                            if (r >= 0) {
+                                if (j < O) hr[u] = __ldg(a.delta + r * O + j);
+                                else if (j == O) hr[u] = __ldg(a.reward + r);
+                                else hr[u] = a.cfg.ignore_terminal_state ? __ldg(a.done + r) : 0.f;
                             }
                         }
                     }
-                    uint32_t hi, lo;
-                    split2(v[0], v[1], hi, lo);
-                    *reinterpret_cast<uint32_t*>(ah + i * As + j) = hi;
-                    *reinterpret_cast<uint32_t*>(al + i * As + j) = lo;
-                    // h_0 for phase B (strip-major, swizzled 16-byte units): 4 bytes per thread
-                    if (j < l0.Kp) {
-                        const int b = row0 + i, unit = ((j >> 3) & 1) ^ ((b >> 2) & 1);
-                        const int64_t o = h_elem_off(l0, a.E, e, a.Bp, b, j >> 4, 0) + unit * 8 + (j & 7);
-                        *reinterpret_cast<uint32_t*>(hbuf + o) = hi;
-                        *reinterpret_cast<uint32_t*>(hbuf + o + (int64_t)(l0.Kp >> 4) * a.E * a.Bp * 16) = lo;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int t = base + tid + u * kT;
+                        if (t < items1) {
+                            const int i = t / (As / 2), j = (t % (As / 2)) * 2;
+                            const bool live = ridx[i] >= 0;
+                            float v[2] = {0.f, 0.f};
+                            if (live) {
+#pragma unroll
+                                for (int q = 0; q < 2; ++q) {
+                                    const int c = j + q;
+                                    // Normalizer.process (normalizer.py:17-18); s_norm = [mean | std + eps] per column
+                                    if (c < IN) v[q] = a.norm ? (xr[u][q] - s_norm[c]) / s_norm[kNormMax + c] : xr[u][q];
+                                    else if (c == IN) v[q] = 1.f;
+                                }
+                            }
+                            uint32_t hi, lo;
+                            split2(v[0], v[1], hi, lo);
+                            *reinterpret_cast<uint32_t*>(ah + i * As + j) = hi;
+                            *reinterpret_cast<uint32_t*>(al + i * As + j) = lo;
+                            // h_0 for phase B (strip-major, swizzled 16-byte units): 4 bytes per thread
+                            if (j < l0.Kp) {
+                                const int b = row0 + i, unit = ((j >> 3) & 1) ^ ((b >> 2) & 1);
+                                const int64_t o = h_elem_off(l0, a.E, e, a.Bp, b, j >> 4, 0) + unit * 8 + (j & 7);
+                                *reinterpret_cast<uint32_t*>(hbuf + o) = hi;
+                                *reinterpret_cast<uint32_t*>(hbuf + o + (int64_t)(l0.Kp >> 4) * a.E * a.Bp * 16) = lo;
+                            }
+                        }
+                        // head operands of this block: fetched now, consumed five layers later
+                        if (t < items2) {
+                            const int i = t / (D + 1), j = t - i * (D + 1);
+                            float v = 0.f;
+                            if (ridx[i] >= 0) {
+                                if (j < O) v = (hr[u] - s_norm[IN + j]) / s_norm[kNormMax + IN + j];
+                                else if (j == O) v = hr[u];
+                                else v = 1.f - hr[u];
+                            }
+                            s_tgt[i][j < D ? j : 64] = v;
+                        }
                     }
                 }
-            }
-            // head operands of this block: fetched now, consumed five layers later (their latency hides
-            // behind the forward pass instead of sitting in front of the loss)
-            if (a.head_kind == FUSED_HEAD_NLL) {
-                const int D = a.D, O = a.O;
-                const float* dmean = a.norm + 2 * O + 2 * a.A;
-                const float* dstd = dmean + O;
-                for (int t = tid; t < kRows * (D + 1); t += kT) {
-                    const int i = t / (D + 1), j = t - i * (D + 1);
-                    const int64_t r = s_rowidx[i];
-                    float v = 0.f;
-                    if (r >= 0) {
-                        if (j < O) v = (a.delta[r * O + j] - dmean[j]) / (dstd[j] + kNormEps);
-                        else if (j == O) v = a.reward[r];
-                        else v = a.cfg.ignore_terminal_state ? 1.f - a.done[r] : 1.f;
-                    }
-                    s_tgt[i][j < D ? j : 64] = v;
-                }
-                if (tid < 2 * 64 && (tid & 63) < D)
-                    s_bound[tid >> 6][tid & 63] = __ldcg(a.params + ((tid >> 6) ? a.minls_off : a.maxls_off) + (int64_t)e * D + (tid & 63));
+                if (has_bnd) s_bound[tid >> 6][tid & 63] = bnd;
             }
             consumer_sync();
 
@@ -472,6 +560,9 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 // The epilogue of a tile writes the produced operand to shared memory (next pass) AND to
                 // global memory in phase B's layout -- no separate copy pass.
                 auto epilogue_tile = [&](int tile, const float (&c)[4]) {
+#ifdef MB_EXP_NOEPI
+                    return;
+#endif
                     // accumulator fragment: rows lane/4 and lane/4+8, columns n0 + 2*(lane%4), +1
                     const int n = tile * 8 + 2 * (lane & 3);
 #pragma unroll
@@ -558,39 +649,14 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                         const int nk = rows / 16;
                         // reduction over the chunk's rows; warp owns n-tiles warp, warp+8, ...
                         const int ntw = nt_total > warp ? (nt_total - warp + kWarps - 1) / kWarps : 0;
-                        bool fast = false;
-                        if constexpr (NT == 4) {
-                            if (nk == 4 && ntw == 4) {
-                                fwd_chunk4<4>(acc, Ah, Al, Wh, Wl, a_lane_off + c * kWChunk, b_lane_off, Ns, warp);
-                                fast = true;
-                            } else if (nk == 4 && ntw == 3) {
-                                fwd_chunk4<3>(acc, Ah, Al, Wh, Wl, a_lane_off + c * kWChunk, b_lane_off, Ns, warp);
-                                fast = true;
-                            }
-                        }
-                        if (!fast)
-#pragma unroll
-                        for (int kk = 0; kk < kChunk / 16; ++kk) {
-                            if (kk >= nk) break;
-                            const int kcol = c * kChunk + kk * 16;
-                            uint32_t ah[4], al[4];
-                            ldsm_x4(ah, smem_u32(Ah + a_lane_off + kcol));
-                            ldsm_x4(al, smem_u32(Al + a_lane_off + kcol));
-                            uint32_t bh[NT][2], bl[NT][2];
-#pragma unroll
-                            for (int i = 0; i < NT; ++i) {
-                                const int tile = warp + kWarps * i;
-                                if (tile < nt_total) {
-                                    const int off = kk * 16 * Ns + b_lane_off + tile * 8;
-                                    ldsm_x2_t(bh[i], smem_u32(Wh + off));
-                                    ldsm_x2_t(bl[i], smem_u32(Wl + off));
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < NT; ++i) {
-                                const int tile = warp + kWarps * i;
-                                if (tile < nt_total) mma3(acc[i], ah, al, bh[i], bl[i]);
-                            }
+                        static_assert(NT == 4, "the forward dispatch covers 0..4 n-tiles per warp");
+                        const int ao = a_lane_off + c * kWChunk;
+                        switch (ntw) {                               // warp-uniform; 0: nothing to do for this warp
+                        case 4: fwd_chunk_nk<4>(nk, acc, Ah, Al, Wh, Wl, ao, b_lane_off, Ns, warp); break;
+                        case 3: fwd_chunk_nk<3>(nk, acc, Ah, Al, Wh, Wl, ao, b_lane_off, Ns, warp); break;
+                        case 2: fwd_chunk_nk<2>(nk, acc, Ah, Al, Wh, Wl, ao, b_lane_off, Ns, warp); break;
+                        case 1: fwd_chunk_nk<1>(nk, acc, Ah, Al, Wh, Wl, ao, b_lane_off, Ns, warp); break;
+                        default: break;
                         }
                         consumer_release(st);
                     }
@@ -601,66 +667,95 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                         if (tile < nt_total) epilogue_tile(tile, acc[i]);
                     }
                 } else {
-                    // dX: every chunk needs the whole g_l operand (the reduction runs over its columns).  The hi
-                    // fragments of all k-steps are loaded ONCE per pass and stay in registers (re-reading both
-                    // halves per chunk made the pass shared-memory-bandwidth bound: 8 warps x 4 chunks x 13 KB);
-                    // the lo halves are re-read -- keeping them too costs 52 more registers and spills
-                    uint32_t gfh[KS][4];
+                    // dX: every chunk needs the whole g_l operand (the reduction runs over its columns).  A chunk of
+                    // 32 weight rows is 4 output tiles; the 8 warps work as 4 PAIRS that split the reduction: warp w
+                    // takes tile (w & 3) and k-steps [0, KH) (w < 4) or [KH, KS) -- so BOTH halves of its share of
+                    // the g operand stay in registers for the whole pass (one warp per tile re-read the lo half for
+                    // every chunk and was bound by ldmatrix bandwidth: 40 cycles of fragment loads per 24 of MMA).
+                    // The two partial tiles meet in shared memory; the finishing warp alternates with the chunk.
+                    constexpr int KH = (KS + 1) / 2;
+                    const int upper = warp >> 2, pair = warp & 3;
+                    const int k_begin = upper ? KH : 0;
+                    const int k_count = max(0, min(ly.ksteps_out - k_begin, KH));
+                    uint32_t gfh[KH][4], gfl[KH][4];
 #pragma unroll
-                    for (int kk = 0; kk < KS; ++kk) {
-                        if (kk < ly.ksteps_out) ldsm_x4(gfh[kk], smem_u32(Ah + a_lane_off + kk * 16));
+                    for (int kk = 0; kk < KH; ++kk) {
+                        if (kk < k_count) {
+                            ldsm_x4(gfh[kk], smem_u32(Ah + a_lane_off + (k_begin + kk) * 16));
+                            ldsm_x4(gfl[kk], smem_u32(Al + a_lane_off + (k_begin + kk) * 16));
+                        }
                     }
+                    // one ldmatrix.x4 per k-step: matrices {hi k-lo, hi k-hi, lo k-lo, lo k-hi} of the tile's 8 weight rows
+                    const int w_lane_row = (pair * 8 + (lane & 7)) * Ns + 8 * ((lane >> 3) & 1) + k_begin * 16;
                     for (int c = 0; c < nchunks; ++c) {
                         issue_w();
                         const int st = consumer_wait();
                         if (c == 0) TL_SET(60 + pass * 6 + 2);
                         const int rows = min(kWChunk, ly.Kp - c * kWChunk);
                         const __nv_bfloat16* Wh = stage_ptr(st);
-                        const __nv_bfloat16* Wl = Wh + rows * Ns;
-                        // chunk rows = output columns k; warp owns output tile 8c + warp; full reduction over n.
-                        // six independent accumulator chains (3 terms x even/odd k-step): one tile per warp
-                        // would otherwise be a 39-deep dependent MMA chain
-                        const int tile = c * (kWChunk / 8) + warp;
+                        const int tile = c * (kWChunk / 8) + pair;
                         if (tile < nt_total) {
+                            // six independent accumulator chains (3 terms x even/odd k-step)
                             float c6[6][4];
 #pragma unroll
                             for (int i = 0; i < 6; ++i)
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) c6[i][q] = 0.f;
-                            const int b_lane_off = (warp * 8 + (lane & 7)) * Ns + 8 * ((lane >> 3) & 1);
-                            if (ly.ksteps_out == KS) {
+                            const __nv_bfloat16* Wp = Wh + w_lane_row + (lane >> 4) * (rows * Ns);
+#ifdef MB_EXP_NOMMA
+                            if (false) {
+#else
+                            if (k_count == KH) {
+#endif
 #pragma unroll
-                                for (int kk = 0; kk < KS; ++kk) {
-                                    uint32_t bh[2], bl[2], gl4[4];
-                                    ldsm_x4(gl4, smem_u32(Al + a_lane_off + kk * 16));
-                                    ldsm_x2(bh, smem_u32(Wh + b_lane_off + kk * 16));
-                                    ldsm_x2(bl, smem_u32(Wl + b_lane_off + kk * 16));
+                                for (int kk = 0; kk < KH; ++kk) {
+                                    uint32_t b4[4];
+                                    ldsm_x4(b4, smem_u32(Wp + kk * 16));
+                                    const uint32_t bh[2] = {b4[0], b4[1]}, bl[2] = {b4[2], b4[3]};
                                     const int o = (kk & 1) * 3;
-                                    mma16816(c6[o + 0], gl4, bh);
+                                    mma16816(c6[o + 0], gfl[kk], bh);
                                     mma16816(c6[o + 1], gfh[kk], bl);
                                     mma16816(c6[o + 2], gfh[kk], bh);
                                 }
                             } else {
 #pragma unroll
-                                for (int kk = 0; kk < KS; ++kk) {
-                                    if (kk < ly.ksteps_out) {
-                                        uint32_t bh[2], bl[2], gl4[4];
-                                        ldsm_x4(gl4, smem_u32(Al + a_lane_off + kk * 16));
-                                        ldsm_x2(bh, smem_u32(Wh + b_lane_off + kk * 16));
-                                        ldsm_x2(bl, smem_u32(Wl + b_lane_off + kk * 16));
+                                for (int kk = 0; kk < KH; ++kk) {
+#ifdef MB_EXP_NOMMA
+                                    break;
+#endif
+                                    if (kk < k_count) {
+                                        uint32_t b4[4];
+                                        ldsm_x4(b4, smem_u32(Wp + kk * 16));
+                                        const uint32_t bh[2] = {b4[0], b4[1]}, bl[2] = {b4[2], b4[3]};
                                         const int o = (kk & 1) * 3;
-                                        mma16816(c6[o + 0], gl4, bh);
+                                        mma16816(c6[o + 0], gfl[kk], bh);
                                         mma16816(c6[o + 1], gfh[kk], bl);
                                         mma16816(c6[o + 2], gfh[kk], bh);
                                     }
                                 }
                             }
-                            consumer_release(st);              // the stage is free before the epilogue maths
+                            consumer_release(st);              // the stage is free before the exchange and the epilogue
                             float cacc[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
                                 cacc[q] = ((c6[0][q] + c6[3][q]) + (c6[1][q] + c6[4][q])) + (c6[2][q] + c6[5][q]);
-                            epilogue_tile(tile, cacc);
+                            const int par = c & 1;             // finishing warp of this chunk: lower (0) / upper (1)
+#ifdef MB_EXP_NOXCHG
+                            if (upper == par) epilogue_tile(tile, cacc);
+                            continue;
+#endif
+                            if (upper != par) {
+                                s_xchg[pair][par][lane] = make_float4(cacc[0], cacc[1], cacc[2], cacc[3]);
+                                __threadfence_block();
+                                named_arrive(2 + 4 * par + pair, 64);
+                            } else {
+                                named_sync(2 + 4 * par + pair, 64);
+                                const float4 o4 = s_xchg[pair][par][lane];
+                                // fixed order: lower half of the reduction first
+                                if (upper) { cacc[0] = o4.x + cacc[0]; cacc[1] = o4.y + cacc[1]; cacc[2] = o4.z + cacc[2]; cacc[3] = o4.w + cacc[3]; }
+                                else { cacc[0] += o4.x; cacc[1] += o4.y; cacc[2] += o4.z; cacc[3] += o4.w; }
+                                epilogue_tile(tile, cacc);
+                            }
                         } else {
                             consumer_release(st);
                         }
@@ -688,7 +783,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     if (a.head_kind == FUSED_HEAD_NLL) {
                         for (int t = tid; t < kRows * D; t += kT) {
                             const int i = t / D, j = t - i * D;
-                            if (s_rowidx[i] < 0) continue;
+                            if (ridx[i] < 0) continue;
                             const float mu = headbuf[i * a.head_stride + j], raw = headbuf[i * a.head_stride + D + j];
                             const float mx = s_bound[0][j], mn = s_bound[1][j];
                             const float aa = mx - raw;
@@ -760,6 +855,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 cur ^= 1;
             }
         }
+        prefetch_rows(step + 1);
         TL_SET(1);
         TL_ALL(230);
         bar_target += G;
@@ -804,7 +900,6 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
             auto issue_b = [&](int c) {
                 if (warp != kIssuer) return;
                 const int st = producer_acquire();
-                fence_proxy_async();        // the ring doubles as epilogue scratch (generic-proxy writes)
                 const uint32_t fb = full0 + 8 * st;
                 const uint32_t gbytes = (uint32_t)kChunk * Ns * 4;
                 if (lane == 0) {
@@ -814,41 +909,30 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 __syncwarp();
                 if (lane < 2 * ns) {
                     const int half = lane / ns, sl = lane - half * ns;
-                    bulk_g2s(smem_u32(act_ptr(st) + (half * ns + sl) * (kChunk * 16)),
+                    bulk_g2s(smem_u32(htile_ptr(st) + (half * ns + sl) * (kChunk * 16)),
                              hbuf + h_elem_off(ly, a.E, e, a.Bp, c * kChunk, jb.strip0 + sl, half), kChunk * 16 * 2, fb);
                 }
             };
             const int g_lane_off = (lane & 15) * Ns;
-            issue_b(0);
+            for (int c = 0; c < kStages - 1 && c < nchunksB; ++c) issue_b(c);
             for (int c = 0; c < nchunksB; ++c) {
-                if (c + 1 < nchunksB) issue_b(c + 1);
+                if (c + kStages - 1 < nchunksB) issue_b(c + kStages - 1);
                 const int st = consumer_wait();
                 const __nv_bfloat16* Gh = stage_ptr(st);
                 const __nv_bfloat16* Gl = Gh + kChunk * Ns;
-                const __nv_bfloat16* Hh = act_ptr(st);        // [hi|lo][strip][64 rows][16], swizzled units
+                const __nv_bfloat16* Hh = htile_ptr(st);      // [hi|lo][strip][kChunk rows][16], swizzled units
                 const __nv_bfloat16* Hl = Hh + ns * (kChunk * 16);
                 const int groups = min(kChunk / 16, nblk - c * (kChunk / 16));
                 const int ntw = nt_total > warp ? (nt_total - warp + kWarps - 1) / kWarps : 0;
                 bool fast = false;
-                if constexpr (NT == 4) {
-                    if (groups == 4 && (ntw >= 3 || ntw <= 1)) {
-                        fast = true;
-                        if (ntw == 4) {
-                            if (ns == 4) dw_chunk4<4, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else if (ns == 3) dw_chunk4<3, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else if (ns == 2) dw_chunk4<2, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else dw_chunk4<1, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                        } else if (ntw == 3) {
-                            if (ns == 4) dw_chunk4<4, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else if (ns == 3) dw_chunk4<3, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else if (ns == 2) dw_chunk4<2, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else dw_chunk4<1, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                        } else if (ntw == 1) {                  // narrow layers (the 36-wide head): one tile per warp
-                            if (ns == 4) dw_chunk4<4, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else if (ns == 3) dw_chunk4<3, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else if (ns == 2) dw_chunk4<2, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                            else dw_chunk4<1, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
-                        }                                       // ntw == 0: nothing to do for this warp
+                if (groups == kNK) {
+                    fast = true;
+                    switch (ntw) {                               // warp-uniform; 0: nothing to do for this warp
+                    case 4: dw_chunk_ns<4>(ns, acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane); break;
+                    case 3: dw_chunk_ns<3>(ns, acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane); break;
+                    case 2: dw_chunk_ns<2>(ns, acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane); break;
+                    case 1: dw_chunk_ns<1>(ns, acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane); break;
+                    default: break;
                     }
                 }
                 if (!fast)
@@ -993,6 +1077,10 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     }
                 }
             }
+            // The ring doubled as scratch (generic-proxy writes); the next bulk copies write it through the async
+            // proxy: every thread orders its own accesses before the barrier (one fence per job -- a fence in
+            // front of every bulk copy cost the issuer warp, and with it the whole CTA, ~400 cycles per chunk)
+            fence_proxy_async();
             consumer_sync();                                  // scratch no longer needed: the next job may refill the ring
         }
         // L2 term of the loss (mlp.py:170-178), from the pre-update weights
@@ -1111,16 +1199,16 @@ int fused_plan(const mb_mlp_desc& d, int ne, int64_t batch_size, int nsm, FusedA
     a.as_max = as_max;
     a.z_stride = (zmax + 7) / 8 * 8 + 4;          // act'(z) rows: float2 stores of whole 8-column tiles
     a.head_stride = d.sizes[L] + 1;
-    a.stage_bytes = kChunk * ns_max * 2 * 2;
-    // act buffers: phase A [hi|lo] x 16 x as_max; phase B h tiles [hi|lo] x 64 x (16*kMaxStrips+8)
+    a.stage_bytes = kChunk * ns_max * 2 * 2;             // kChunk == kWChunk rows of both halves
+    // act buffers: phase A [hi|lo] x 16 x as_max; phase B: the h tiles of the ring's stages
     int act_b = 2 * kRows * as_max * 2;
-    const int htile_b = 2 * kMaxStrips * kChunk * 16 * 2;        // [hi|lo][strip][64][16]
+    const int htile_b = kStages / 2 * (2 * kMaxStrips * kChunk * 16 * 2);   // per act buffer: kStages/2 x [hi|lo][strip][kChunk][16]
     a.act_bytes = act_b > htile_b ? act_b : htile_b;
     a.z_bytes = (L > 1 ? (L - 1) : 1) * kRows * a.z_stride * 4;
     a.head_bytes = (kRows * a.head_stride * 4 + 15) / 16 * 16;
     a.nblk_max = a.Bp / kRows;
     sz.part_bytes = (size_t)E * a.nblk_max * kFusedPartStride * 4;
-    sz.smem = 2 * (size_t)a.stage_bytes + 2 * (size_t)a.act_bytes + a.z_bytes + a.head_bytes + 2 * kRows * 64 * 4;
+    sz.smem = kStages * (size_t)a.stage_bytes + 2 * (size_t)a.act_bytes + a.z_bytes + a.head_bytes + 2 * kRows * 64 * 4;
     sz.pack_bytes = (size_t)pack_elems * 2;
     sz.h_bytes = (size_t)h_elems * 2;
     sz.g_bytes = (size_t)g_elems * 2;
