@@ -58,13 +58,20 @@ constexpr int kT = kWarps * 32;
 constexpr int kThreads = kT;
 constexpr int kIssuer = kWarps - 1;
 constexpr int kRows = 16;        // batch rows per block (one MMA M tile)
-constexpr int kChunk = 32;       // batch rows per streamed chunk of phase B (and the ring's stage size)
-constexpr int kWChunk = 32;      // weight rows per streamed chunk of phase A: 2 forward k-steps, 4 dX output tiles
-constexpr int kStages = 4;       // ring depth: up to three bulk copies in flight behind the chunk being consumed
-constexpr int kNK = kChunk / 16; // k-steps per chunk
+constexpr int kChunk = 64;       // batch rows per streamed chunk of phase B (and the ring's stage size)
+constexpr int kWChunk = 8 * kWarps;  // weight rows per streamed chunk of phase A: one dX output tile per warp (= 64)
 constexpr int kNormMax = 512;    // cached normaliser columns: inputs (<= 256) + deltas (<= 256)
-constexpr int kMaxStrips = 4;    // 16-row weight strips per phase-B job
-constexpr int kSweep = 4;        // float4 per thread and batch of the Adam sweep (5 measured 3 % slower: register pressure)
+// Register budget: the kernel is one function, and whatever ptxas spills are kernel-lifetime values that get
+// reloaded inside the hot loops of EVERY phase.  3 strips x 4 tiles of dW accumulators and 2 float4 per thread
+// and sweep batch compile without a single spill (4 / 4: 88 bytes, and the whole step 4 % slower).
+#ifndef MB_MAX_STRIPS
+#define MB_MAX_STRIPS 3
+#endif
+#ifndef MB_SWEEP
+#define MB_SWEEP 2
+#endif
+constexpr int kMaxStrips = MB_MAX_STRIPS;    // 16-row weight strips per phase-B job
+constexpr int kSweep = MB_SWEEP;   // float4 per thread and batch of the Adam sweep
 
 // ---- PTX helpers -----------------------------------------------------------------------------------
 // ldmatrix reads shared memory: volatile + memory clobber keeps it behind the barriers that publish
@@ -115,12 +122,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     return v;
 }
 // G CTAs of one member: arrive (after the CTA's global writes) / wait until `target` arrivals
-__device__ __forceinline__ void named_arrive(int id, int nthreads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __device__ __forceinline__ void member_arrive(unsigned* cnt) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -173,12 +174,12 @@ struct StepScalars { float step_size, bc2_sqrt; };
 
 // ------------------------------------------------------------------------------------------------------
 // Global layouts of the phase-A -> phase-B hand-over (bf16 elements):
-//   g_l : [E][Bp/32][hi|lo][32][Ns]   a 32-row chunk of both halves is ONE bulk copy into the ring
-//   h_l : [hi|lo][Kp/16 strips][E][Bp][16]   a job's strip x 32 rows is one 1 KB bulk copy; the two 16-byte
+//   g_l : [E][Bp/64][hi|lo][64][Ns]   a 64-row chunk of both halves is ONE bulk copy into the ring
+//   h_l : [hi|lo][Kp/16 strips][E][Bp][16]   a job's strip x 64 rows is one 2 KB bulk copy; the two 16-byte
 //         units of a row are swapped for rows with bit 2 set, which makes the transposed ldmatrix reads of
 //         the 32-byte-stride tile bank-conflict free
 __device__ __forceinline__ int64_t g_elem_off(const FusedLayer& ly, int e, int Bp, int b, int half) {
-    return ly.g_off + ((((int64_t)e * (Bp / kChunk) + (b / kChunk)) * 2 + half) * kChunk + (b % kChunk)) * ly.Ns;
+    return ly.g_off + ((((int64_t)e * (Bp >> 6) + (b >> 6)) * 2 + half) * kChunk + (b & 63)) * ly.Ns;
 }
 __device__ __forceinline__ int64_t h_elem_off(const FusedLayer& ly, int E, int e, int Bp, int b, int strip, int half) {
     return ly.h_off + ((((int64_t)half * (ly.Kp >> 4) + strip) * E + e) * Bp + b) * 16;
@@ -192,9 +193,6 @@ template <int NK, int NTW>
 __device__ __forceinline__ void fwd_chunk(float (&acc)[4][4], const __nv_bfloat16* Ah, const __nv_bfloat16* Al,
                                           const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int a_off, int b_off, int Ns,
                                           int warp) {
-#ifdef MB_EXP_NOMMA
-    return;
-#endif
 #pragma unroll
     for (int kk = 0; kk < NK; ++kk) {
         uint32_t ah[4], al[4];
@@ -222,13 +220,13 @@ __device__ __forceinline__ void fwd_chunk_nk(int nk, float (&acc)[4][4], const _
     default: fwd_chunk<1, NTW>(acc, Ah, Al, Wh, Wl, a_off, b_off, Ns, warp); break;
     }
 }
-// phase B: a full chunk (kNK groups of 16 batch rows), NS strips x NTW n-tiles per warp
+// phase B: a full 64-row chunk (4 groups of 16 batch rows), NS strips x NTW n-tiles per warp
 template <int NS, int NTW>
-__device__ __forceinline__ void dw_chunk(float (&acc)[kMaxStrips][4][4], const __nv_bfloat16* Gh, const __nv_bfloat16* Gl,
-                                         const __nv_bfloat16* Hh, const __nv_bfloat16* Hl, int g_off, int Ns, int warp,
-                                         int lane) {
+__device__ __forceinline__ void dw_chunk4(float (&acc)[kMaxStrips][4][4], const __nv_bfloat16* Gh, const __nv_bfloat16* Gl,
+                                          const __nv_bfloat16* Hh, const __nv_bfloat16* Hl, int g_off, int Ns, int warp,
+                                          int lane) {
 #pragma unroll
-    for (int kk = 0; kk < kNK; ++kk) {
+    for (int kk = 0; kk < 4; ++kk) {
         uint32_t bh[NTW][2], bl[NTW][2];
 #pragma unroll
         for (int i = 0; i < NTW; ++i) {
@@ -248,17 +246,6 @@ __device__ __forceinline__ void dw_chunk(float (&acc)[kMaxStrips][4][4], const _
         }
     }
 }
-template <int NTW>
-__device__ __forceinline__ void dw_chunk_ns(int ns, float (&acc)[kMaxStrips][4][4], const __nv_bfloat16* Gh,
-                                            const __nv_bfloat16* Gl, const __nv_bfloat16* Hh, const __nv_bfloat16* Hl,
-                                            int g_off, int Ns, int warp, int lane) {
-    switch (ns) {
-    case 4: dw_chunk<4, NTW>(acc, Gh, Gl, Hh, Hl, g_off, Ns, warp, lane); break;
-    case 3: dw_chunk<3, NTW>(acc, Gh, Gl, Hh, Hl, g_off, Ns, warp, lane); break;
-    case 2: dw_chunk<2, NTW>(acc, Gh, Gl, Hh, Hl, g_off, Ns, warp, lane); break;
-    default: dw_chunk<1, NTW>(acc, Gh, Gl, Hh, Hl, g_off, Ns, warp, lane); break;
-    }
-}
 
 // KS = compile-time bound of the dX reduction length in k-steps (its operand fragments live in registers)
 // NT = n-tiles (8 columns) per consumer warp: widths up to 8 * kWarps * NT
@@ -273,32 +260,29 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
     const int L = a.L;
     const int act_kind = a.act;
 
-    // [stage 0 .. kStages-1 | act 0 | act 1 | z | head | red]
-    const int ring_bytes = kStages * a.stage_bytes;
+    // [stage 0 | stage 1 | act 0 | act 1 | z | head | red]
     __nv_bfloat16* const stage0 = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-    __nv_bfloat16* const act0 = reinterpret_cast<__nv_bfloat16*>(smem_raw + ring_bytes);
-    __nv_bfloat16* const act1 = reinterpret_cast<__nv_bfloat16*>(smem_raw + ring_bytes + a.act_bytes);
-    float* const zbuf = reinterpret_cast<float*>(smem_raw + ring_bytes + 2 * a.act_bytes);
-    float* const headbuf = reinterpret_cast<float*>(smem_raw + ring_bytes + 2 * a.act_bytes + a.z_bytes);
-    float* const redbuf = reinterpret_cast<float*>(smem_raw + ring_bytes + 2 * a.act_bytes + a.z_bytes + a.head_bytes);
-    auto stage_ptr = [&](int s) { return reinterpret_cast<__nv_bfloat16*>(smem_raw + s * a.stage_bytes); };
+    __nv_bfloat16* const stage1 = reinterpret_cast<__nv_bfloat16*>(smem_raw + a.stage_bytes);
+    __nv_bfloat16* const act0 = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * a.stage_bytes);
+    __nv_bfloat16* const act1 = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * a.stage_bytes + a.act_bytes);
+    float* const zbuf = reinterpret_cast<float*>(smem_raw + 2 * a.stage_bytes + 2 * a.act_bytes);
+    float* const headbuf = reinterpret_cast<float*>(smem_raw + 2 * a.stage_bytes + 2 * a.act_bytes + a.z_bytes);
+    float* const redbuf = reinterpret_cast<float*>(smem_raw + 2 * a.stage_bytes + 2 * a.act_bytes + a.z_bytes + a.head_bytes);
+    auto stage_ptr = [&](int s) { return s ? stage1 : stage0; };
     auto act_ptr = [&](int s) { return s ? act1 : act0; };
-    // phase B: h tiles of a stage, [hi|lo][strip][kChunk rows][16], carved from the two act buffers (contiguous)
-    auto htile_ptr = [&](int s) { return act0 + s * (2 * kMaxStrips * kChunk * 16); };
     __shared__ StepScalars s_sc;
     __shared__ float s_part[kWarps];
     __shared__ int64_t s_rowidx[3][kRows];            // [step parity]: the step's first block (prefetched); [2]: further blocks
     __shared__ float s_norm[2 * kNormMax];            // [mean | std + eps] of [obs | act | delta] (constant over the launch)
     __shared__ float s_tgt[kRows][64 + 1];            // head targets of the block (normalised delta | reward) and the loss mask
     __shared__ float s_bound[2][64];                  // max / min log-std of this member
-    __shared__ __align__(8) uint64_t s_bar[2 * kStages];   // full[] ("chunk landed"), empty[] ("chunk consumed")
-    __shared__ float4 s_xchg[4][2][32];               // dX: partial tiles handed between the two warps of a pair
-    const uint32_t full0 = smem_u32(&s_bar[0]), empty0 = smem_u32(&s_bar[kStages]);
+    __shared__ __align__(8) uint64_t s_bar[4];        // full[2] ("chunk landed"), empty[2] ("chunk consumed")
+    const uint32_t full0 = smem_u32(&s_bar[0]), empty0 = smem_u32(&s_bar[2]);
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) {
-            mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, kWarps);
-        }
+        mbar_init(full0, 1);
+        mbar_init(full0 + 8, 1);
+        mbar_init(empty0, kWarps);
+        mbar_init(empty0 + 8, kWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int t = tid; t < a.act_bytes / 4; t += kThreads) {      // padding columns must hold finite values
@@ -306,20 +290,20 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
         reinterpret_cast<uint32_t*>(act1)[t] = 0u;
     }
     __syncthreads();
-    // Ring protocol.  Use number u (0, 1, 2, ... over the whole kernel) occupies stage u % kStages.  The issuer
+    // Ring protocol.  Use number u (0, 1, 2, ... over the whole kernel) occupies stage u & 1.  The issuer
     // (lane 0 of warp kIssuer, which has the fewest tiles) waits for the stage's previous use to be released
-    // by all 8 warps and keeps up to kStages - 1 bulk copies in flight behind the use being consumed; a warp
-    // waits for the copy to land, computes, and releases.  No CTA-wide barrier per chunk.
+    // by all 8 warps and issues the bulk copy of use u + 1 before it consumes use u; a warp waits for the
+    // copy to land, computes, and releases.  No CTA-wide barrier per chunk.
     uint32_t use = 0, use_p = 0;                      // uses consumed (every thread) / issued (issuer warp)
     auto producer_acquire = [&]() -> int {            // -> stage
-        const int s = use_p % kStages;
-        if (use_p >= kStages) mbar_wait(empty0 + 8 * s, ((use_p / kStages) & 1) ^ 1);
+        const int s = use_p & 1;
+        if (use_p >= 2) mbar_wait(empty0 + 8 * s, ((use_p >> 1) & 1) ^ 1);
         ++use_p;
         return s;
     };
     auto consumer_wait = [&]() -> int {
-        const int s = use % kStages;
-        mbar_wait(full0 + 8 * s, (use / kStages) & 1);
+        const int s = use & 1;
+        mbar_wait(full0 + 8 * s, (use >> 1) & 1);
         ++use;
         return s;
     };
@@ -421,6 +405,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 if (warp != kIssuer || ip >= npass) return;
                 const FusedLayer& ly = a.ly[pass_layer(ip)];
                 const int st = producer_acquire();
+                fence_proxy_async();
                 if (lane == 0) {
                     const int rows = min(kWChunk, ly.Kp - ic * kWChunk);
                     const uint32_t bytes = (uint32_t)rows * ly.Ns * 4;
@@ -431,7 +416,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 }
                 if (++ic * kWChunk >= ly.Kp) { ic = 0; ++ip; }
             };
-            for (int i = 0; i < kStages - 1; ++i) issue_w();
+            issue_w();
             // ---- row indices of the block (the step's first block: fetched a step ahead), then every global
             // operand of the staging in ONE round trip: the raw loads of the inputs and of the head operands are
             // issued before any of them is consumed (normaliser statistics sit in shared memory)
@@ -560,9 +545,6 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 // The epilogue of a tile writes the produced operand to shared memory (next pass) AND to
                 // global memory in phase B's layout -- no separate copy pass.
                 auto epilogue_tile = [&](int tile, const float (&c)[4]) {
-#ifdef MB_EXP_NOEPI
-                    return;
-#endif
                     // accumulator fragment: rows lane/4 and lane/4+8, columns n0 + 2*(lane%4), +1
                     const int n = tile * 8 + 2 * (lane & 3);
 #pragma unroll
@@ -667,95 +649,66 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                         if (tile < nt_total) epilogue_tile(tile, acc[i]);
                     }
                 } else {
-                    // dX: every chunk needs the whole g_l operand (the reduction runs over its columns).  A chunk of
-                    // 32 weight rows is 4 output tiles; the 8 warps work as 4 PAIRS that split the reduction: warp w
-                    // takes tile (w & 3) and k-steps [0, KH) (w < 4) or [KH, KS) -- so BOTH halves of its share of
-                    // the g operand stay in registers for the whole pass (one warp per tile re-read the lo half for
-                    // every chunk and was bound by ldmatrix bandwidth: 40 cycles of fragment loads per 24 of MMA).
-                    // The two partial tiles meet in shared memory; the finishing warp alternates with the chunk.
-                    constexpr int KH = (KS + 1) / 2;
-                    const int upper = warp >> 2, pair = warp & 3;
-                    const int k_begin = upper ? KH : 0;
-                    const int k_count = max(0, min(ly.ksteps_out - k_begin, KH));
-                    uint32_t gfh[KH][4], gfl[KH][4];
+                    // dX: every chunk needs the whole g_l operand (the reduction runs over its columns).  The hi
+                    // fragments of all k-steps are loaded ONCE per pass and stay in registers (re-reading both
+                    // halves per chunk made the pass shared-memory-bandwidth bound: 8 warps x 4 chunks x 13 KB);
+                    // the lo halves are re-read -- keeping them too costs 52 more registers and spills
+                    uint32_t gfh[KS][4];
 #pragma unroll
-                    for (int kk = 0; kk < KH; ++kk) {
-                        if (kk < k_count) {
-                            ldsm_x4(gfh[kk], smem_u32(Ah + a_lane_off + (k_begin + kk) * 16));
-                            ldsm_x4(gfl[kk], smem_u32(Al + a_lane_off + (k_begin + kk) * 16));
-                        }
+                    for (int kk = 0; kk < KS; ++kk) {
+                        if (kk < ly.ksteps_out) ldsm_x4(gfh[kk], smem_u32(Ah + a_lane_off + kk * 16));
                     }
-                    // one ldmatrix.x4 per k-step: matrices {hi k-lo, hi k-hi, lo k-lo, lo k-hi} of the tile's 8 weight rows
-                    const int w_lane_row = (pair * 8 + (lane & 7)) * Ns + 8 * ((lane >> 3) & 1) + k_begin * 16;
                     for (int c = 0; c < nchunks; ++c) {
                         issue_w();
                         const int st = consumer_wait();
                         if (c == 0) TL_SET(60 + pass * 6 + 2);
                         const int rows = min(kWChunk, ly.Kp - c * kWChunk);
                         const __nv_bfloat16* Wh = stage_ptr(st);
-                        const int tile = c * (kWChunk / 8) + pair;
+                        const __nv_bfloat16* Wl = Wh + rows * Ns;
+                        // chunk rows = output columns k; warp owns output tile 8c + warp; full reduction over n.
+                        // six independent accumulator chains (3 terms x even/odd k-step): one tile per warp
+                        // would otherwise be a 39-deep dependent MMA chain
+                        const int tile = c * (kWChunk / 8) + warp;
                         if (tile < nt_total) {
-                            // six independent accumulator chains (3 terms x even/odd k-step)
                             float c6[6][4];
 #pragma unroll
                             for (int i = 0; i < 6; ++i)
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) c6[i][q] = 0.f;
-                            const __nv_bfloat16* Wp = Wh + w_lane_row + (lane >> 4) * (rows * Ns);
-#ifdef MB_EXP_NOMMA
-                            if (false) {
-#else
-                            if (k_count == KH) {
-#endif
+                            const int b_lane_off = (warp * 8 + (lane & 7)) * Ns + 8 * ((lane >> 3) & 1);
+                            if (ly.ksteps_out == KS) {
 #pragma unroll
-                                for (int kk = 0; kk < KH; ++kk) {
-                                    uint32_t b4[4];
-                                    ldsm_x4(b4, smem_u32(Wp + kk * 16));
-                                    const uint32_t bh[2] = {b4[0], b4[1]}, bl[2] = {b4[2], b4[3]};
+                                for (int kk = 0; kk < KS; ++kk) {
+                                    uint32_t bh[2], bl[2], gl4[4];
+                                    ldsm_x4(gl4, smem_u32(Al + a_lane_off + kk * 16));
+                                    ldsm_x2(bh, smem_u32(Wh + b_lane_off + kk * 16));
+                                    ldsm_x2(bl, smem_u32(Wl + b_lane_off + kk * 16));
                                     const int o = (kk & 1) * 3;
-                                    mma16816(c6[o + 0], gfl[kk], bh);
+                                    mma16816(c6[o + 0], gl4, bh);
                                     mma16816(c6[o + 1], gfh[kk], bl);
                                     mma16816(c6[o + 2], gfh[kk], bh);
                                 }
                             } else {
 #pragma unroll
-                                for (int kk = 0; kk < KH; ++kk) {
-#ifdef MB_EXP_NOMMA
-                                    break;
-#endif
-                                    if (kk < k_count) {
-                                        uint32_t b4[4];
-                                        ldsm_x4(b4, smem_u32(Wp + kk * 16));
-                                        const uint32_t bh[2] = {b4[0], b4[1]}, bl[2] = {b4[2], b4[3]};
+                                for (int kk = 0; kk < KS; ++kk) {
+                                    if (kk < ly.ksteps_out) {
+                                        uint32_t bh[2], bl[2], gl4[4];
+                                        ldsm_x4(gl4, smem_u32(Al + a_lane_off + kk * 16));
+                                        ldsm_x2(bh, smem_u32(Wh + b_lane_off + kk * 16));
+                                        ldsm_x2(bl, smem_u32(Wl + b_lane_off + kk * 16));
                                         const int o = (kk & 1) * 3;
-                                        mma16816(c6[o + 0], gfl[kk], bh);
+                                        mma16816(c6[o + 0], gl4, bh);
                                         mma16816(c6[o + 1], gfh[kk], bl);
                                         mma16816(c6[o + 2], gfh[kk], bh);
                                     }
                                 }
                             }
-                            consumer_release(st);              // the stage is free before the exchange and the epilogue
+                            consumer_release(st);              // the stage is free before the epilogue maths
                             float cacc[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
                                 cacc[q] = ((c6[0][q] + c6[3][q]) + (c6[1][q] + c6[4][q])) + (c6[2][q] + c6[5][q]);
-                            const int par = c & 1;             // finishing warp of this chunk: lower (0) / upper (1)
-#ifdef MB_EXP_NOXCHG
-                            if (upper == par) epilogue_tile(tile, cacc);
-                            continue;
-#endif
-                            if (upper != par) {
-                                s_xchg[pair][par][lane] = make_float4(cacc[0], cacc[1], cacc[2], cacc[3]);
-                                __threadfence_block();
-                                named_arrive(2 + 4 * par + pair, 64);
-                            } else {
-                                named_sync(2 + 4 * par + pair, 64);
-                                const float4 o4 = s_xchg[pair][par][lane];
-                                // fixed order: lower half of the reduction first
-                                if (upper) { cacc[0] = o4.x + cacc[0]; cacc[1] = o4.y + cacc[1]; cacc[2] = o4.z + cacc[2]; cacc[3] = o4.w + cacc[3]; }
-                                else { cacc[0] += o4.x; cacc[1] += o4.y; cacc[2] += o4.z; cacc[3] += o4.w; }
-                                epilogue_tile(tile, cacc);
-                            }
+                            epilogue_tile(tile, cacc);
                         } else {
                             consumer_release(st);
                         }
@@ -900,6 +853,7 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
             auto issue_b = [&](int c) {
                 if (warp != kIssuer) return;
                 const int st = producer_acquire();
+                fence_proxy_async();        // the ring doubles as epilogue scratch (generic-proxy writes)
                 const uint32_t fb = full0 + 8 * st;
                 const uint32_t gbytes = (uint32_t)kChunk * Ns * 4;
                 if (lane == 0) {
@@ -909,30 +863,50 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 __syncwarp();
                 if (lane < 2 * ns) {
                     const int half = lane / ns, sl = lane - half * ns;
-                    bulk_g2s(smem_u32(htile_ptr(st) + (half * ns + sl) * (kChunk * 16)),
+                    bulk_g2s(smem_u32(act_ptr(st) + (half * ns + sl) * (kChunk * 16)),
                              hbuf + h_elem_off(ly, a.E, e, a.Bp, c * kChunk, jb.strip0 + sl, half), kChunk * 16 * 2, fb);
                 }
             };
             const int g_lane_off = (lane & 15) * Ns;
-            for (int c = 0; c < kStages - 1 && c < nchunksB; ++c) issue_b(c);
+            issue_b(0);
             for (int c = 0; c < nchunksB; ++c) {
-                if (c + kStages - 1 < nchunksB) issue_b(c + kStages - 1);
+                if (c + 1 < nchunksB) issue_b(c + 1);
                 const int st = consumer_wait();
                 const __nv_bfloat16* Gh = stage_ptr(st);
                 const __nv_bfloat16* Gl = Gh + kChunk * Ns;
-                const __nv_bfloat16* Hh = htile_ptr(st);      // [hi|lo][strip][kChunk rows][16], swizzled units
+                const __nv_bfloat16* Hh = act_ptr(st);        // [hi|lo][strip][64 rows][16], swizzled units
                 const __nv_bfloat16* Hl = Hh + ns * (kChunk * 16);
                 const int groups = min(kChunk / 16, nblk - c * (kChunk / 16));
                 const int ntw = nt_total > warp ? (nt_total - warp + kWarps - 1) / kWarps : 0;
                 bool fast = false;
-                if (groups == kNK) {
-                    fast = true;
-                    switch (ntw) {                               // warp-uniform; 0: nothing to do for this warp
-                    case 4: dw_chunk_ns<4>(ns, acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane); break;
-                    case 3: dw_chunk_ns<3>(ns, acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane); break;
-                    case 2: dw_chunk_ns<2>(ns, acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane); break;
-                    case 1: dw_chunk_ns<1>(ns, acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane); break;
-                    default: break;
+                if constexpr (NT == 4) {
+                    if (groups == 4 && (ntw >= 3 || ntw <= 1)) {
+                        fast = true;
+                        if (ntw == 4) {
+#if MB_MAX_STRIPS >= 4
+                            if (ns == 4) dw_chunk4<4, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else
+#endif
+                            if (ns == 3) dw_chunk4<3, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 2) dw_chunk4<2, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else dw_chunk4<1, 4>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                        } else if (ntw == 3) {
+#if MB_MAX_STRIPS >= 4
+                            if (ns == 4) dw_chunk4<4, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else
+#endif
+                            if (ns == 3) dw_chunk4<3, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 2) dw_chunk4<2, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else dw_chunk4<1, 3>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                        } else if (ntw == 1) {                  // narrow layers (the 36-wide head): one tile per warp
+#if MB_MAX_STRIPS >= 4
+                            if (ns == 4) dw_chunk4<4, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else
+#endif
+                            if (ns == 3) dw_chunk4<3, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else if (ns == 2) dw_chunk4<2, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                            else dw_chunk4<1, 1>(acc, Gh, Gl, Hh, Hl, g_lane_off, Ns, warp, lane);
+                        }                                       // ntw == 0: nothing to do for this warp
                     }
                 }
                 if (!fast)
@@ -1077,10 +1051,6 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                     }
                 }
             }
-            // The ring doubled as scratch (generic-proxy writes); the next bulk copies write it through the async
-            // proxy: every thread orders its own accesses before the barrier (one fence per job -- a fence in
-            // front of every bulk copy cost the issuer warp, and with it the whole CTA, ~400 cycles per chunk)
-            fence_proxy_async();
             consumer_sync();                                  // scratch no longer needed: the next job may refill the ring
         }
         // L2 term of the loss (mlp.py:170-178), from the pre-update weights
@@ -1199,16 +1169,16 @@ int fused_plan(const mb_mlp_desc& d, int ne, int64_t batch_size, int nsm, FusedA
     a.as_max = as_max;
     a.z_stride = (zmax + 7) / 8 * 8 + 4;          // act'(z) rows: float2 stores of whole 8-column tiles
     a.head_stride = d.sizes[L] + 1;
-    a.stage_bytes = kChunk * ns_max * 2 * 2;             // kChunk == kWChunk rows of both halves
-    // act buffers: phase A [hi|lo] x 16 x as_max; phase B: the h tiles of the ring's stages
+    a.stage_bytes = kChunk * ns_max * 2 * 2;
+    // act buffers: phase A [hi|lo] x 16 x as_max; phase B h tiles [hi|lo] x 64 x (16*kMaxStrips+8)
     int act_b = 2 * kRows * as_max * 2;
-    const int htile_b = kStages / 2 * (2 * kMaxStrips * kChunk * 16 * 2);   // per act buffer: kStages/2 x [hi|lo][strip][kChunk][16]
+    const int htile_b = 2 * kMaxStrips * kChunk * 16 * 2;        // [hi|lo][strip][64][16]
     a.act_bytes = act_b > htile_b ? act_b : htile_b;
     a.z_bytes = (L > 1 ? (L - 1) : 1) * kRows * a.z_stride * 4;
     a.head_bytes = (kRows * a.head_stride * 4 + 15) / 16 * 16;
     a.nblk_max = a.Bp / kRows;
     sz.part_bytes = (size_t)E * a.nblk_max * kFusedPartStride * 4;
-    sz.smem = kStages * (size_t)a.stage_bytes + 2 * (size_t)a.act_bytes + a.z_bytes + a.head_bytes + 2 * kRows * 64 * 4;
+    sz.smem = 2 * (size_t)a.stage_bytes + 2 * (size_t)a.act_bytes + a.z_bytes + a.head_bytes + 2 * kRows * 64 * 4;
     sz.pack_bytes = (size_t)pack_elems * 2;
     sz.h_bytes = (size_t)h_elems * 2;
     sz.g_bytes = (size_t)g_elems * 2;
