@@ -635,9 +635,10 @@ def main():
             landed[p].synchronize()                # the caller owns the transitions now
 
     e2e_steps = max(2, min(args.steps, 5))
-    # three timed regions, median reported: the host side of this leg (pinned-memory bandwidth, PCIe) varies from
-    # box to box and run to run far more than the device side (one region in ~10 lands 2-3x slower)
-    e2e_runs = [timed(e2e_step, e2e_steps, 3 if i == 0 else 0) / e2e_steps for i in range(3)]
+    # seven timed regions, median reported: the host side of this leg (pinned-memory bandwidth, PCIe) is shared with
+    # the other tenants of the box and varies from run to run far more than the device side (a region can land
+    # 2-3x slower than its neighbours); every region's time is kept in ms_per_step_runs
+    e2e_runs = [timed(e2e_step, e2e_steps, 3 if i == 0 else 0) / e2e_steps for i in range(7)]
     e2e_ms = float(np.median(e2e_runs))
     e2e = {"value": world * B * H / (e2e_ms * 1e-3), "unit": "transitions/s",
            "h2d_bytes_per_step": B * O * 4 + H * (B * A * 4 + n_chunks * 627 * 4),
