@@ -344,6 +344,24 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
             *reinterpret_cast<uint32_t*>(pm + pack_row_off(k, 1, ly.Kp, ly.Ns) + n) = lo;
         }
     }
+    // Padding columns of the global copy of h_{l+1} (phase B's operand) beyond the tiles the forward epilogue
+    // writes: column N is the bias column (exactly 1: it yields db), the rest 0 -- constants, written once for
+    // the row blocks this CTA owns (phase B loads them into shared memory as part of its strips, so they must
+    // be finite; rewriting them in every forward pass cost ~0.5 k cycles per pass)
+    for (int blk = slot; blk < a.nblk_max; blk += G) {
+        for (int l = 0; l + 1 < L; ++l) {
+            const FusedLayer& nx = a.ly[l + 1];
+            const int N = a.ly[l].N, c0 = (N + 7) & ~7, wpad = nx.Kp - c0;
+            const int64_t half = (int64_t)(nx.Kp >> 4) * a.E * a.Bp * 16;
+            for (int t = tid; t < kRows * wpad; t += kThreads) {
+                const int i = t & (kRows - 1), c = c0 + (t >> 4), b = blk * kRows + i;
+                const int unit = ((c >> 3) & 1) ^ ((b >> 2) & 1);
+                const int64_t o = h_elem_off(nx, a.E, e, a.Bp, b, c >> 4, 0) + unit * 8 + (c & 7);
+                hbuf[o] = __float2bfloat16(c == N ? 1.f : 0.f);
+                hbuf[o + half] = __float2bfloat16(0.f);
+            }
+        }
+    }
     bar_target += G;
     member_arrive(bar);
     member_wait(bar, bar_target);
@@ -593,23 +611,10 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
                 // ever meets zero weights, so any finite value will do -- the buffers are zeroed once at kernel start
                 // and only ever hold finite bf16 values afterwards.  (Rewriting all of them every pass cost ~650
                 // cycles per pass.)  When N is not a multiple of 8 the epilogue's last tile writes the 1 itself.
-                if (fwd && !last_fwd) {
-                    // global h_{l+1}: columns [N, Kp) -- phase B loads them into shared memory as part of its
-                    // strips, so they must be finite there too (column N = 1, the rest 0)
-                    const int c0 = out_w & ~7, wpad = lo_.Kp - c0;
-                    for (int t = tid; t < kRows * wpad; t += kT) {
-                        const int i = t & (kRows - 1), c = c0 + (t >> 4), b = row0 + i;
-                        if (c < out_w) continue;                              // written by the last tile
-                        const __nv_bfloat16 vb = __float2bfloat16(c == out_w ? 1.f : 0.f);
-                        if (c == out_w) {
-                            Dh[i * dstride + c] = vb;
-                            Dl[i * dstride + c] = __float2bfloat16(0.f);
-                        }
-                        const int unit = ((c >> 3) & 1) ^ ((b >> 2) & 1);
-                        const int64_t o = h_elem_off(lo_, a.E, e, a.Bp, b, c >> 4, 0) + unit * 8 + (c & 7);
-                        hbuf[o] = vb;
-                        hbuf[o + h_half] = __float2bfloat16(0.f);
-                    }
+                // (the constant padding columns of the GLOBAL copy of h_{l+1} are written once, by the prologue)
+                if (fwd && !last_fwd && (out_w & 7) == 0 && tid < kRows) {
+                    Dh[tid * dstride + out_w] = __float2bfloat16(1.f);
+                    Dl[tid * dstride + out_w] = __float2bfloat16(0.f);
                 }
                 TL_SET(60 + pass * 6 + 1);
                 // per-lane ldmatrix offsets (elements) that do not depend on the chunk
