@@ -154,6 +154,14 @@ __device__ __forceinline__ float act_both(float z, int act, float& deriv) {
     deriv = fmaf(h, 1.f - sg, sg);
     return h;
 }
+__device__ __forceinline__ float swish_both(float z, float& deriv) {     // act_both's swish branch, branch-free
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    const float sg = fmaf(0.5f, t, 0.5f);
+    const float h = z * sg;
+    deriv = fmaf(h, 1.f - sg, sg);
+    return h;
+}
 __device__ __forceinline__ float fast_sqrt(float x) {
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -562,46 +570,75 @@ k_train_fused(const __grid_constant__ FusedArgs a) {
 
                 // The epilogue of a tile writes the produced operand to shared memory (next pass) AND to
                 // global memory in phase B's layout -- no separate copy pass.
+                // Every decision that is uniform over the warp (last layer / full tile / activation kind) is taken once
+                // per tile, and the bodies below are straight-line code: per-element branches on the activation kind
+                // and on the column bounds kept the compiler from scheduling across them (9 % of the step's stall
+                // samples were branch resolution) and made every epilogue a chain of tiny basic blocks.
                 auto epilogue_tile = [&](int tile, const float (&c)[4]) {
                     // accumulator fragment: rows lane/4 and lane/4+8, columns n0 + 2*(lane%4), +1
                     const int n = tile * 8 + 2 * (lane & 3);
+                    if (last_fwd) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int i = (lane >> 2) + 8 * h;
-                        float v0 = c[2 * h], v1 = c[2 * h + 1];
-                        if (last_fwd) {
-                            if (n < out_w) headbuf[i * a.head_stride + n] = v0;
-                            if (n + 1 < out_w) headbuf[i * a.head_stride + n + 1] = v1;
-                            continue;
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = (lane >> 2) + 8 * h;
+                            if (n < out_w) headbuf[i * a.head_stride + n] = c[2 * h];
+                            if (n + 1 < out_w) headbuf[i * a.head_stride + n + 1] = c[2 * h + 1];
                         }
-                        uint32_t hi, lo;
-                        if (fwd) {
-                            // the backward pass needs act'(z), not z: keep that (one sigmoid serves both)
-                            float d0 = 0.f, d1 = 0.f;
+                        return;
+                    }
+                    const bool full = tile * 8 + 8 <= out_w;
+                    float v[4];
+                    if (fwd) {
+                        // the backward pass needs act'(z), not z: keep that (one sigmoid serves both)
+                        float d[4];
 #ifdef MB_EXP_NOACT
-                            d0 = d1 = 1.f;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { v[q] = c[q]; d[q] = 1.f; }
 #else
-                            if (n < out_w) v0 = act_both(v0, act_kind, d0); else v0 = (n == out_w) ? 1.f : 0.f;
-                            if (n + 1 < out_w) v1 = act_both(v1, act_kind, d1); else v1 = (n + 1 == out_w) ? 1.f : 0.f;
+                        if (full && act_kind == MB_ACT_SWISH) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) v[q] = swish_both(c[q], d[q]);
+                        } else if (full) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) { d[q] = c[q] > 0.f ? 1.f : 0.f; v[q] = fmaxf(c[q], 0.f); }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int col = n + (q & 1);
+                                d[q] = 0.f;
+                                if (col < out_w) v[q] = act_both(c[q], act_kind, d[q]);
+                                else v[q] = col == out_w ? 1.f : 0.f;
+                            }
+                        }
 #endif
-                            *reinterpret_cast<float2*>(zrow + i * a.z_stride + n) = make_float2(d0, d1);
-                            split2(v0, v1, hi, lo);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = (lane >> 2) + 8 * h;
+                            uint32_t hi, lo;
+                            *reinterpret_cast<float2*>(zrow + i * a.z_stride + n) = make_float2(d[2 * h], d[2 * h + 1]);
+                            split2(v[2 * h], v[2 * h + 1], hi, lo);
 #ifndef MB_EXP_NOGSTORE
                             const int64_t o = grow[h] + (tile >> 1) * h_strip_stride + (((tile & 1) ^ gsw[h]) << 3);
                             *reinterpret_cast<uint32_t*>(hbuf + o) = hi;
                             *reinterpret_cast<uint32_t*>(hbuf + o + h_half) = lo;
 #endif
-                        } else {
+                            *reinterpret_cast<uint32_t*>(Dh + i * dstride + n) = hi;
+                            *reinterpret_cast<uint32_t*>(Dl + i * dstride + n) = lo;
+                        }
+                    } else {
+                        const float m0 = (full || n < out_w) ? 1.f : 0.f, m1 = (full || n + 1 < out_w) ? 1.f : 0.f;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = (lane >> 2) + 8 * h;
+                            uint32_t hi, lo;
                             const float2 d = *reinterpret_cast<const float2*>(zrow + i * a.z_stride + n);
-                            v0 = n < out_w ? v0 * d.x : 0.f;
-                            v1 = n + 1 < out_w ? v1 * d.y : 0.f;
-                            split2(v0, v1, hi, lo);
+                            split2(c[2 * h] * d.x * m0, c[2 * h + 1] * d.y * m1, hi, lo);
                             const int64_t o = grow[h] + tile * 8;
                             *reinterpret_cast<uint32_t*>(gbuf + o) = hi;
                             *reinterpret_cast<uint32_t*>(gbuf + o + (int64_t)kChunk * lo_.Ns) = lo;
+                            *reinterpret_cast<uint32_t*>(Dh + i * dstride + n) = hi;
+                            *reinterpret_cast<uint32_t*>(Dl + i * dstride + n) = lo;
                         }
-                        *reinterpret_cast<uint32_t*>(Dh + i * dstride + n) = hi;
-                        *reinterpret_cast<uint32_t*>(Dl + i * dstride + n) = lo;
                     }
                 };
 
