@@ -70,6 +70,37 @@ def test_fused_train_step_matches_oracle_ragged(B):
         assert norm_rel(msd["module.minlogstd_net%d" % e].cpu().numpy() / 0.1, g["min_logstd"][e].numpy()) < 1e-3
 
 
+@pytest.mark.parametrize("E,hidden,B", [(2, [200, 200, 200, 200], 256), (10, [200, 200, 200, 200], 256),
+                                        (20, [64, 48], 300), (3, [256, 256], 100)])
+def test_fused_train_step_ensemble_sizes_and_widths(E, hidden, B):
+    """The persistent kernel at other ensemble sizes and layer widths: 2 members (21 CTAs each, 5 of them without a
+    row block), 10 members (MOPO: 14 CTAs per member, two row blocks on some), 20 members (7 CTAs per member, three
+    row blocks each, narrow layers with partial tiles) and 256-wide layers (the 16 k-step instantiation): loss,
+    per-member loss and the first Adam moments against the oracle's analytic gradients."""
+    cfg = dict(E=E, elites=max(1, E - 1), hidden=hidden, act="swish")
+    m, p = make_pe_model(cfg, 23)
+    tr = _trainer(m)
+    assert tr.fused_steps_supported()
+    bt = _batch(950 + E, E, B)
+    diag = tr.train_from_torch_batch(bt)
+    g = po.model_loss_grads(to_torch(p), *[bt[k].cpu() for k in ("observations", "actions", "deltas", "rewards",
+                                                                 "terminals")],
+                            weight_decay=cases.WEIGHT_DECAY[:len(hidden) + 1])
+    assert_close(np.array(diag["train_loss"]), g["loss"].numpy(), what="loss")
+    assert_close(np.array([diag["mt/net_%d/train_loss" % i] for i in range(E)]), g["ensemble_loss"].numpy(),
+                 what="ensemble_loss")
+    msd = m.module.reference_state_dict("module.", flat=tr.exp_avg)
+    for l in range(len(hidden) + 1):
+        for e in range(E):
+            got = msd["module.net.%d.weight_net%d" % (2 * l, e)].cpu().numpy() / 0.1
+            assert norm_rel(got, g["W"][l][e].numpy()) < 1e-3, ("dW", l, e)
+            gb = msd["module.net.%d.bias_net%d" % (2 * l, e)].cpu().numpy() / 0.1
+            assert norm_rel(gb, g["b"][l][e].numpy()) < 1e-3, ("db", l, e)
+    for e in range(E):
+        assert norm_rel(msd["module.maxlogstd_net%d" % e].cpu().numpy() / 0.1, g["max_logstd"][e].numpy()) < 1e-3
+        assert norm_rel(msd["module.minlogstd_net%d" % e].cpu().numpy() / 0.1, g["min_logstd"][e].numpy()) < 1e-3
+
+
 def test_fused_train_100_steps_match_reference_adam():
     """A hundred fused steps against the reference's PEModelTrainer run (loss curve, parameter and
     moment checksums at step 100)."""
