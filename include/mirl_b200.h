@@ -317,6 +317,30 @@ int mb_policy_action(const mb_mlp_desc* d, const float* params, const float* obs
                      const float* eps, const mb_policy_cfg* cfg, float* action, float* log_prob, float* mean,
                      float* std, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- actor + entropy-coefficient update (second half): SACAgent.train_from_torch_batch's "update actor
+ * and alpha" block (sac_agent.py:170-195) --
+ *   new_action, info = policy.action(obs, reparameterize=True, return_log_prob=True)        (gaussian.py:55-97)
+ *   compute_alpha_loss (sac_agent.py:88-100) + alpha_optimizer.step()                       (Adam on log_alpha)
+ *   compute_policy_loss (sac_agent.py:102-118): alpha * log_prob.mean() - qf.value(obs, new_action, **v_pi).mean()
+ *   policy_optimizer.step()                                                                  (torch.optim.Adam)
+ * as a chain of launches (tcgen05 layer GEMMs forward and backward, hand-written heads); the critics are read, not
+ * updated.  policy: 1-member MLP obs -> 2 * act_dim; critic: the E-member ensemble on [obs | action] (outputs 1, or
+ * Q atoms for TQC).  reduce_mode MB_REDUCE_* over `members` (host array of n_members indices, NULL = all; the
+ * batch-wise draw of ensemble_value.py:84-86 -- per-row draws are not covered); with Q > 1 outputs the value is the mean
+ * of the listed members' atoms (distributional_value.py:51-55, number_drop 0) and reduce_mode must be MB_REDUCE_MEAN.
+ * noise[B][act_dim] = the rsample() draw.  log_alpha / its two Adam moments are device scalars (NULL = fixed
+ * alpha_fixed, use_automatic_entropy_tuning False); both optimisers take lr / betas / eps and have made
+ * adam_steps_done steps.  info (device float[8], may be NULL): [0] policy/loss [1] policy/q_pi [2] policy/entropy
+ * [3] alpha/value [4] alpha/loss [5] the alpha the policy loss used. */
+size_t mb_actor_workspace_bytes(const mb_mlp_desc* policy, const mb_mlp_desc* critic, int64_t B);
+int mb_actor_update(const mb_mlp_desc* policy, float* policy_params, float* exp_avg, float* exp_avg_sq,
+                    int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                    const mb_policy_cfg* cfg, const mb_mlp_desc* critic, const float* critic_params,
+                    int reduce_mode, const int32_t* members, int n_members,
+                    const float* obs, const float* noise, int obs_dim, int act_dim, int64_t B,
+                    float* log_alpha, float* alpha_exp_avg, float* alpha_exp_avg_sq, float target_entropy,
+                    float alpha_fixed, float* info, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- tcgen05 operand pack: bf16 hi/lo split of every member's weights in the UMMA
  * shared-memory layout the rollout kernel streams (rebuild after the weights change). */
 size_t mb_pe_tc_pack_bytes(const mb_pe_model* m);

@@ -14,6 +14,7 @@ B200TQCQValue         TQCQValue                                    mirl/values/d
 B200DevicePool        SimplePool (imagined-data pool, in HBM)      mirl/pools/simple_pool.py
 B200ExtraFieldPool    ExtraFieldPool (real-data pool, in HBM)      mirl/pools/extra_field_pool.py
 B200CriticTrainer     critic half of SACAgent.train_from_torch_batch  mirl/agents/sac_agent.py:160-166
+B200ActorTrainer      actor + alpha half of the same                  mirl/agents/sac_agent.py:170-195
 B200GaussianPolicy    GaussianPolicy (forward / sampling)           mirl/policies/gaussian_policy.py
 ====================  ===========================================  ============================
 
@@ -25,7 +26,8 @@ from .pe_model_trainer import B200PEModelTrainer       # noqa: F401
 from .values import B200CriticTrainer, B200EnsembleQValue, B200TQCQValue  # noqa: F401
 from .collectors import B200MBPOCollector, B200MOPOCollector  # noqa: F401
 from .pools import B200DevicePool, B200ExtraFieldPool  # noqa: F401
-from .policies import B200GaussianPolicy              # noqa: F401
+from .policies import B200ActorTrainer, B200GaussianPolicy  # noqa: F401
 
 __all__ = ["B200PEModel", "B200PEModelTrainer", "B200EnsembleQValue", "B200TQCQValue", "B200CriticTrainer",
-           "B200MBPOCollector", "B200MOPOCollector", "B200DevicePool", "B200ExtraFieldPool", "B200GaussianPolicy"]
+           "B200MBPOCollector", "B200MOPOCollector", "B200DevicePool", "B200ExtraFieldPool", "B200GaussianPolicy",
+           "B200ActorTrainer"]

@@ -88,6 +88,10 @@ SIGNATURES = {
                                   c_int, c_int, P, c_int, c_int64, P, c_float, P, P, P, c_size_t, P]),
     "mb_policy_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
     "mb_policy_action": (c_int, [POINTER(MlpDesc), P, P, c_int, c_int64, P, POINTER(PolicyCfg), P, P, P, P, P, c_size_t, P]),
+    "mb_actor_workspace_bytes": (c_size_t, [POINTER(MlpDesc), POINTER(MlpDesc), c_int64]),
+    "mb_actor_update": (c_int, [POINTER(MlpDesc), P, P, P, c_int64, c_float, c_float, c_float, c_float, POINTER(PolicyCfg),
+                                POINTER(MlpDesc), P, c_int, POINTER(c_int32), c_int, P, P, c_int, c_int, c_int64,
+                                P, P, P, c_float, c_float, P, P, c_size_t, P]),
     "mb_critic_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64]),
     "mb_critic_forward": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64, P, P, c_size_t, P]),
     "mb_critic_redq_target": (c_int, [POINTER(MlpDesc), P, P, P, c_int, c_int, c_int64,

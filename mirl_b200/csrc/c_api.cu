@@ -541,6 +541,48 @@ int mb_policy_action(const mb_mlp_desc* d, const float* params, const float* obs
                                 workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t mb_actor_workspace_bytes(const mb_mlp_desc* policy, const mb_mlp_desc* critic, int64_t B) {
+    if (!policy || !critic || validate_desc(policy, "mb_actor_workspace_bytes") || validate_desc(critic, "mb_actor_workspace_bytes"))
+        return 0;
+    return actor_workspace_bytes(*policy, *critic, B < 1 ? 1 : B);
+}
+
+int mb_actor_update(const mb_mlp_desc* policy, float* policy_params, float* exp_avg, float* exp_avg_sq,
+                    int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                    const mb_policy_cfg* cfg, const mb_mlp_desc* critic, const float* critic_params,
+                    int reduce_mode, const int32_t* members, int n_members,
+                    const float* obs, const float* noise, int obs_dim, int act_dim, int64_t B,
+                    float* log_alpha, float* alpha_exp_avg, float* alpha_exp_avg_sq, float target_entropy,
+                    float alpha_fixed, float* info, void* workspace, size_t workspace_bytes, void* stream) {
+    const char* who = "mb_actor_update";
+    int rc = validate_desc(policy, who);
+    if (rc) return rc;
+    rc = validate_desc(critic, who);
+    if (rc) return rc;
+    MB_CHECK_ARG(cfg != nullptr, "%s: null policy cfg", who);
+    MB_CHECK_ARG(policy->ensemble_size == 1, "%s: the policy is a 1-member MLP", who);
+    MB_CHECK_ARG(obs_dim >= 1 && act_dim >= 1 && policy->sizes[0] == obs_dim &&
+                 policy->sizes[policy->num_layers] == 2 * act_dim, "%s: policy maps %d -> %d, expected %d -> %d", who,
+                 policy->sizes[0], policy->sizes[policy->num_layers], obs_dim, 2 * act_dim);
+    MB_CHECK_ARG(critic->sizes[0] == obs_dim + act_dim, "%s: critic input %d != obs+act %d", who, critic->sizes[0],
+                 obs_dim + act_dim);
+    MB_CHECK_ARG(B >= 1 && B < (int64_t)1 << 20, "%s: B out of range", who);
+    MB_CHECK_ARG(policy_params && exp_avg && exp_avg_sq && critic_params && obs && noise, "%s: null tensor", who);
+    MB_CHECK_ARG(log_alpha == nullptr || (alpha_exp_avg && alpha_exp_avg_sq), "%s: log_alpha without its Adam moments", who);
+    MB_CHECK_ARG(adam_steps_done >= 0, "%s: adam_steps_done < 0", who);
+    MB_CHECK_ARG(reduce_mode >= MB_REDUCE_MIN && reduce_mode <= MB_REDUCE_MAX, "%s: reduce_mode %d", who, reduce_mode);
+    const int Q = critic->sizes[critic->num_layers];
+    MB_CHECK_ARG(Q == 1 || reduce_mode == MB_REDUCE_MEAN, "%s: critics with %d outputs reduce by the mean of their atoms", who, Q);
+    MB_CHECK_ARG(members == nullptr || (n_members >= 1 && n_members <= critic->ensemble_size), "%s: n_members %d", who, n_members);
+    for (int i = 0; members && i < n_members; ++i)
+        MB_CHECK_ARG(members[i] >= 0 && members[i] < critic->ensemble_size, "%s: member %d out of range", who, members[i]);
+    MB_CHECK_ARG(workspace && workspace_bytes >= actor_workspace_bytes(*policy, *critic, B), "%s: workspace too small", who);
+    return launch_actor_update(*policy, policy_params, exp_avg, exp_avg_sq, adam_steps_done, lr, beta1, beta2, eps, *cfg,
+                               *critic, critic_params, reduce_mode, members, n_members, obs, noise, obs_dim, act_dim, B,
+                               log_alpha, alpha_exp_avg, alpha_exp_avg_sq, target_entropy, alpha_fixed, info, workspace,
+                               (cudaStream_t)stream);
+}
+
 static int check_critic(const char* who, const mb_mlp_desc* d, const float* params, const float* obs,
                         const float* act, int O, int A, int64_t B) {
     int rc = validate_desc(d, who);

@@ -167,6 +167,15 @@ int launch_critic_train_chain(const mb_mlp_desc& d, int head_kind, float* params
                               int64_t B, float clip_error, float* target_params, float tau, float* ensemble_loss,
                               float* loss_terms, void* ws, cudaStream_t s);
 
+// actor + entropy-coefficient update (sac_agent.py:88-118,170-195) as a chain of launches
+size_t actor_workspace_bytes(const mb_mlp_desc& pd, const mb_mlp_desc& cd, int64_t B);
+int launch_actor_update(const mb_mlp_desc& pd, float* pparams, float* exp_avg, float* exp_avg_sq,
+                        int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                        const mb_policy_cfg& cfg, const mb_mlp_desc& cd, const float* cparams, int reduce_mode,
+                        const int32_t* members, int n_members, const float* obs, const float* noise, int O, int A,
+                        int64_t B, float* log_alpha, float* la_m1, float* la_m2, float target_entropy,
+                        float alpha_fixed, float* info, void* ws, cudaStream_t s);
+
 // ---- critic targets (critic.cu)
 size_t critic_workspace_bytes(const mb_mlp_desc& d, int64_t B);
 int launch_critic_forward(const mb_mlp_desc& d, const float* params, const float* obs,

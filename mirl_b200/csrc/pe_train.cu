@@ -896,4 +896,327 @@ int launch_critic_train_chain(const mb_mlp_desc& d, int head_kind, float* params
     return MB_OK;
 }
 
+// ---- actor + entropy-coefficient update as a chain of launches -------------------------
+// SACAgent.train_from_torch_batch, "update actor and alpha" (sac_agent.py:170-195):
+//   new_action, info = policy.action(obs, reparameterize=True, return_log_prob=True)   (gaussian.py:55-97)
+//   alpha:  res = log_prob.mean() + target_entropy;  loss = -res * exp(log_alpha);  Adam    (sac_agent.py:88-100)
+//   policy: loss = alpha * log_prob.mean() - qf.value(obs, new_action, **current_v_pi_kwargs).mean()   (:102-118)
+// written out by hand: policy forward (tensor-core layer GEMMs, pre-activations kept), sample + log-prob head,
+// alpha step, critic forward on [obs | action], d loss / d q through the member reduction, the critic's dX chain
+// down to its INPUT (no critic weight gradients), d loss / d (mean, log-std) through tanh and the log-prob, the
+// policy's dW / dX chain and Adam.  With pre = mean + std * eps fixed by the noise draw:
+//   d log_prob / d pre = 2 tanh(pre) (squash correction; the Normal term's pre and mean paths cancel),
+//   d log_prob / d std = -1 / std.
+struct ActorWs {
+    float* pz[MB_MAX_LAYERS];      // policy pre-activations [B][w], l < Lp-1
+    float* pout;                   // [B][2A]
+    float* action;                 // [B][A]
+    float* pg[MB_MAX_LAYERS];      // dL/d(output of policy layer l) [B][w_{l+1}]
+    float* pgrads;                 // policy gradient blob
+    float* x0;                     // [B][O+A]
+    float* cz[MB_MAX_LAYERS];      // critic pre-activations [E][B][w], l < Lc-1
+    float* cout;                   // [E][B][Q]
+    float* cg[MB_MAX_LAYERS];      // dL/d(output of critic layer l) [E][B][w_{l+1}]
+    float* gx0;                    // [E][B][O+A]
+    float* scal;                   // [0] sum log_prob  [1] sum q  [2] alpha of the policy loss  [3] alpha before its step  [4] alpha loss
+};
+
+static ActorWs actor_carve(const mb_mlp_desc& pd, const mb_mlp_desc& cd, int64_t B, void* ws, size_t* bytes) {
+    ActorWs w{};
+    const int Lp = pd.num_layers, Lc = cd.num_layers;
+    const int64_t E = cd.ensemble_size;
+    float* p = reinterpret_cast<float*>(ws);
+    float* const p0 = p;
+    auto take = [&](int64_t n) { float* t = p; p += round_up4(n); return t; };
+    w.scal = take(16);
+    for (int l = 0; l + 1 < Lp; ++l) w.pz[l] = take(B * pd.sizes[l + 1]);
+    w.pout = take(B * pd.sizes[Lp]);
+    w.action = take(B * (pd.sizes[Lp] / 2));
+    for (int l = 0; l < Lp; ++l) w.pg[l] = take(B * pd.sizes[l + 1]);
+    w.pgrads = take(param_count(pd, false));
+    w.x0 = take(B * cd.sizes[0]);
+    for (int l = 0; l + 1 < Lc; ++l) w.cz[l] = take(E * B * cd.sizes[l + 1]);
+    w.cout = take(E * B * cd.sizes[Lc]);
+    for (int l = 0; l < Lc; ++l) w.cg[l] = take(E * B * cd.sizes[l + 1]);
+    w.gx0 = take(E * B * cd.sizes[0]);
+    if (bytes) *bytes = (size_t)(p - p0) * sizeof(float) + 256;
+    return w;
+}
+
+size_t actor_workspace_bytes(const mb_mlp_desc& pd, const mb_mlp_desc& cd, int64_t B) {
+    size_t n = 0;
+    actor_carve(pd, cd, B, nullptr, &n);
+    return n;
+}
+
+__device__ __forceinline__ float bounded_logstd(float raw, int mode, float& dls_draw) {
+    if (mode == MB_LOGSTD_TANH) {            // (tanh + 1) * (max - min) / 2 + min, gaussian.py:17-30
+        const float th = tanhf(raw);
+        dls_draw = 6.f * (1.f - th * th);
+        return (th + 1.f) * 6.f - 10.f;
+    }
+    if (mode == MB_LOGSTD_CLAMP) {
+        dls_draw = (raw >= -10.f && raw <= 2.f) ? 1.f : 0.f;
+        return fminf(fmaxf(raw, -10.f), 2.f);
+    }
+    dls_draw = 1.f;
+    return raw;
+}
+
+// sample + log-prob (k_policy_head's arithmetic); the log-probs are summed over the batch into scal[0]
+__global__ void k_actor_head_fwd(const float* __restrict__ out, const float* __restrict__ eps, int64_t B, int A,
+                                 mb_policy_cfg cfg, float* __restrict__ action, float* __restrict__ scal) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float lp = 0.f;
+    if (t < B * A) {
+        const int64_t b = t / A;
+        const int j = (int)(t - b * A);
+        float dd;
+        const float mean = out[b * 2 * A + j] * cfg.mean_scale;
+        const float ls = bounded_logstd(out[b * 2 * A + A + j] + cfg.logstd_extra_bias, cfg.bound_mode, dd);
+        const float sd = expf(ls) * cfg.std_scale + cfg.min_std;
+        const float e = eps[t];
+        const float pre = mean + sd * e;
+        action[t] = cfg.squashed ? tanhf(pre) : pre;
+        lp = -0.5f * e * e - logf(sd) - 0.91893853320467274178f;
+        if (cfg.squashed) lp -= 2.f * 0.69314718055994530942f - softplusf_(2.f * pre) - softplusf_(-2.f * pre);
+    }
+    for (int o = 16; o; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(scal, lp);
+}
+
+// entropy coefficient: compute_alpha_loss + alpha_optimizer.step (torch.optim.Adam on the scalar log_alpha)
+__global__ void k_alpha_update(float* __restrict__ scal, int64_t B, float target_entropy, float alpha_fixed,
+                               float* log_alpha, float* m1, float* m2, int64_t steps_done, float lr, float beta1,
+                               float beta2, float eps) {
+    pdl_trigger();
+    pdl_wait();
+    if (log_alpha == nullptr) { scal[2] = alpha_fixed; scal[3] = alpha_fixed; scal[4] = 0.f; return; }
+    const float la = *log_alpha, alpha = expf(la);
+    const float res = scal[0] / (float)B + target_entropy;
+    const float g = -res * alpha;
+    scal[3] = alpha;
+    scal[4] = g;                                     // alpha_loss = (-res) * alpha, numerically its own gradient
+    const double t = (double)(steps_done + 1);
+    const float a = *m1 * beta1 + g * (1.f - beta1), v = *m2 * beta2 + g * g * (1.f - beta2);
+    *m1 = a;
+    *m2 = v;
+    const float step_size = (float)((double)lr / (1.0 - pow((double)beta1, t)));
+    const float denom = sqrtf(v) / (float)sqrt(1.0 - pow((double)beta2, t)) + eps;
+    const float nla = la - step_size * (a / denom);
+    *log_alpha = nla;
+    scal[2] = expf(nla);                              // _get_alpha() after the step (sac_agent.py:66-72,177-188)
+}
+
+struct ActorMembers { int n; int idx[32]; };
+
+// q_pi of a row = reduction of the listed members' outputs (ensemble_value.py:91-96; TQC: the mean of all atoms,
+// distributional_value.py:51-55), summed into scal[1]; seed of the backward pass: d(-mean_b q_pi) / d q[e][b][o]
+__global__ void k_actor_seed(const float* __restrict__ cout, int E, int64_t B, int Q, int mode, ActorMembers mem,
+                             float* __restrict__ g, float* __restrict__ scal) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float q = 0.f;
+    if (b < B) {
+        for (int e = 0; e < E; ++e)
+            for (int o = 0; o < Q; ++o) g[((int64_t)e * B + b) * Q + o] = 0.f;
+        const float invB = 1.f / (float)B;
+        if (mode == MB_REDUCE_MEAN) {
+            const float wgt = 1.f / (float)(mem.n * Q);
+            for (int i = 0; i < mem.n; ++i)
+                for (int o = 0; o < Q; ++o) {
+                    const int64_t k = ((int64_t)mem.idx[i] * B + b) * Q + o;
+                    q += cout[k] * wgt;
+                    g[k] = -invB * wgt;
+                }
+        } else {
+            int best = mem.idx[0];
+            q = cout[((int64_t)best * B + b) * Q];
+            for (int i = 1; i < mem.n; ++i) {
+                const float v = cout[((int64_t)mem.idx[i] * B + b) * Q];
+                if (mode == MB_REDUCE_MIN ? v < q : v > q) { q = v; best = mem.idx[i]; }
+            }
+            g[((int64_t)best * B + b) * Q] = -invB;
+        }
+    }
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(scal + 1, q);
+}
+
+// d loss / d (policy output): the members' input gradients are summed over e, the action columns go through the
+// squash and the reparameterisation, the log-prob terms are added
+__global__ void k_actor_head_bwd(const float* __restrict__ gx0, int E, int64_t B, int IN, int O, int A,
+                                 const float* __restrict__ out, const float* __restrict__ eps, mb_policy_cfg cfg,
+                                 const float* __restrict__ scal, float* __restrict__ gout) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * A) return;
+    const int64_t b = t / A;
+    const int j = (int)(t - b * A);
+    float ga = 0.f;
+    for (int e = 0; e < E; ++e) ga += gx0[((int64_t)e * B + b) * IN + O + j];
+    const float alpha_b = scal[2] / (float)B;
+    float dls_draw;
+    const float mean = out[b * 2 * A + j] * cfg.mean_scale;
+    const float ls = bounded_logstd(out[b * 2 * A + A + j] + cfg.logstd_extra_bias, cfg.bound_mode, dls_draw);
+    const float ex = expf(ls), sd = ex * cfg.std_scale + cfg.min_std;
+    const float e = eps[t];
+    const float pre = mean + sd * e;
+    float dpre = ga;
+    if (cfg.squashed) {
+        const float a = tanhf(pre);
+        dpre = ga * (1.f - a * a) + alpha_b * 2.f * a;
+    }
+    const float dsd = dpre * e - alpha_b / sd;
+    gout[b * 2 * A + j] = dpre * cfg.mean_scale;
+    gout[b * 2 * A + A + j] = dsd * cfg.std_scale * ex * dls_draw;
+}
+
+// info[0] policy loss, [1] q_pi mean, [2] entropy, [3] alpha before its step, [4] alpha loss, [5] alpha of the policy loss
+__global__ void k_actor_info(const float* __restrict__ scal, int64_t B, float* __restrict__ info) {
+    pdl_trigger();
+    pdl_wait();
+    const float lp = scal[0] / (float)B, q = scal[1] / (float)B;
+    info[0] = scal[2] * lp - q;
+    info[1] = q;
+    info[2] = -lp;
+    info[3] = scal[3];
+    info[4] = scal[4];
+    info[5] = scal[2];
+}
+
+int launch_actor_update(const mb_mlp_desc& pd, float* pparams, float* exp_avg, float* exp_avg_sq,
+                        int64_t adam_steps_done, float lr, float beta1, float beta2, float eps,
+                        const mb_policy_cfg& cfg, const mb_mlp_desc& cd, const float* cparams, int reduce_mode,
+                        const int32_t* members, int n_members, const float* obs, const float* noise, int O, int A,
+                        int64_t B, float* log_alpha, float* la_m1, float* la_m2, float target_entropy,
+                        float alpha_fixed, float* info, void* ws, cudaStream_t s) {
+    const int Lp = pd.num_layers, Lc = cd.num_layers, E = cd.ensemble_size, Q = cd.sizes[Lc], IN = O + A;
+    if (E > 32) { set_error("actor update: ensemble_size %d > 32", E); return MB_EUNSUPPORTED; }
+    ActorWs w = actor_carve(pd, cd, B, ws, nullptr);
+    ActorMembers mem{};
+    mem.n = members ? n_members : E;
+    for (int i = 0; i < mem.n; ++i) mem.idx[i] = members ? members[i] : i;
+    cudaMemsetAsync(w.scal, 0, 16 * sizeof(float), s);
+    const unsigned gBA = (unsigned)((B * A + 255) / 256);
+    // ---- policy forward, pre-activations kept
+    for (int l = 0; l < Lp; ++l) {
+        TgBatch tb = tg_members(0, 1);
+        tb.nops = 1;
+        TgOp& o = tb.op[0];
+        o.mode = TG_FWD;
+        o.M = (int)B; o.N = pd.sizes[l + 1]; o.R = pd.sizes[l];
+        o.a = l == 0 ? obs : w.pz[l - 1]; o.lda = o.R; o.a_ss = 0;
+        o.a_act = l == 0 ? -1 : pd.activation;
+        o.b = pparams + w_offset(pd, l); o.ldb = o.N; o.b_ms = (int64_t)o.R * o.N;
+        o.bias = pparams + b_offset(pd, l); o.bias_ms = o.N;
+        o.out = l + 1 < Lp ? w.pz[l] : w.pout; o.ldo = o.N; o.out_ss = (int64_t)B * o.N;
+        int rc = launch_tc_gemm(tb, s);
+        if (rc) return rc;
+    }
+    launch_pdl(k_actor_head_fwd, dim3(gBA), dim3(256), 0, s, (const float*)w.pout, noise, B, A, cfg, w.action, w.scal);
+    MB_CUDA_LAUNCH_CHECK("k_actor_head_fwd");
+    launch_pdl(k_alpha_update, dim3(1), dim3(1), 0, s, w.scal, B, target_entropy, alpha_fixed, log_alpha, la_m1, la_m2,
+               adam_steps_done, lr, beta1, beta2, eps);
+    MB_CUDA_LAUNCH_CHECK("k_alpha_update");
+    // ---- critics on [obs | new action]
+    {
+        const int64_t total = B * IN;
+        launch_pdl(k_critic_prep, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, obs, (const float*)w.action, O, A,
+                   B, w.x0, w.scal + 8, 0, w.scal + 8);
+        MB_CUDA_LAUNCH_CHECK("k_critic_prep");
+    }
+    for (int l = 0; l < Lc; ++l) {
+        TgBatch tb = tg_members(0, E);
+        tb.nops = 1;
+        TgOp& o = tb.op[0];
+        o.mode = TG_FWD;
+        o.M = (int)B; o.N = cd.sizes[l + 1]; o.R = cd.sizes[l];
+        o.a = l == 0 ? w.x0 : w.cz[l - 1]; o.lda = o.R; o.a_ss = l == 0 ? 0 : (int64_t)B * o.R;
+        o.a_act = l == 0 ? -1 : cd.activation;
+        o.b = cparams + w_offset(cd, l); o.ldb = o.N; o.b_ms = (int64_t)o.R * o.N;
+        o.bias = cparams + b_offset(cd, l); o.bias_ms = o.N;
+        o.out = l + 1 < Lc ? w.cz[l] : w.cout; o.ldo = o.N; o.out_ss = (int64_t)B * o.N;
+        int rc = launch_tc_gemm(tb, s);
+        if (rc) return rc;
+    }
+    launch_pdl(k_actor_seed, dim3((unsigned)((B + 255) / 256)), dim3(256), 0, s, (const float*)w.cout, E, B, Q, reduce_mode,
+               mem, w.cg[Lc - 1], w.scal);
+    MB_CUDA_LAUNCH_CHECK("k_actor_seed");
+    // ---- critic dX chain down to the input (no weight gradients: the critics are not updated here)
+    for (int l = Lc - 1; l >= 0; --l) {
+        const int K = cd.sizes[l], N = cd.sizes[l + 1];
+        TgBatch xb = tg_members(0, E);
+        xb.nops = 1;
+        TgOp& x = xb.op[0];
+        x.mode = TG_DX;
+        x.M = (int)B; x.N = K; x.R = N;
+        x.a = w.cg[l]; x.lda = N; x.a_ss = (int64_t)B * N;
+        x.b = cparams + w_offset(cd, l); x.ldb = N; x.b_ms = (int64_t)K * N; x.b_trans = 1;
+        if (l > 0) { x.z = w.cz[l - 1]; x.ldz = K; x.z_ss = (int64_t)B * K; x.z_act = cd.activation; }
+        x.out = l > 0 ? w.cg[l - 1] : w.gx0; x.ldo = K; x.out_ss = (int64_t)B * K;
+        int rc = launch_tc_gemm(xb, s);
+        if (rc) return rc;
+    }
+    launch_pdl(k_actor_head_bwd, dim3(gBA), dim3(256), 0, s, (const float*)w.gx0, E, B, IN, O, A, (const float*)w.pout, noise,
+               cfg, (const float*)w.scal, w.pg[Lp - 1]);
+    MB_CUDA_LAUNCH_CHECK("k_actor_head_bwd");
+    // ---- policy backward + Adam
+    TgBatch dwb = tg_members(0, 1);
+    for (int l = Lp - 1; l >= 0; --l) {
+        const int K = pd.sizes[l], N = pd.sizes[l + 1];
+        TgOp& o = dwb.op[dwb.nops++];
+        o.mode = TG_DW;
+        o.M = K + 1; o.N = N; o.R = (int)B;
+        o.a = l == 0 ? obs : w.pz[l - 1]; o.lda = K; o.a_ss = 0; o.a_trans = 1;
+        o.a_act = l == 0 ? -1 : pd.activation;
+        o.a_ones_row = K;
+        o.b = w.pg[l]; o.ldb = N; o.b_ss = (int64_t)B * N;
+        o.w = pparams + w_offset(pd, l); o.w_ms = (int64_t)K * N; o.wd = 0.f;
+        o.out = w.pgrads + w_offset(pd, l); o.ldo = N; o.out_ms = (int64_t)K * N;
+        o.out_ones = w.pgrads + b_offset(pd, l); o.out_ones_ms = N;
+        o.l2_acc = nullptr;
+        if (l > 0) {
+            TgBatch xb = tg_members(0, 1);
+            xb.nops = 1;
+            TgOp& x = xb.op[0];
+            x.mode = TG_DX;
+            x.M = (int)B; x.N = K; x.R = N;
+            x.a = w.pg[l]; x.lda = N; x.a_ss = (int64_t)B * N;
+            x.b = pparams + w_offset(pd, l); x.ldb = N; x.b_ms = (int64_t)K * N; x.b_trans = 1;
+            x.z = w.pz[l - 1]; x.ldz = K; x.z_ss = (int64_t)B * K; x.z_act = pd.activation;
+            x.out = w.pg[l - 1]; x.ldo = K; x.out_ss = (int64_t)B * K;
+            int rc = launch_tc_gemm(xb, s);
+            if (rc) return rc;
+        }
+    }
+    int rc = launch_tc_gemm(dwb, s);
+    if (rc) return rc;
+    AdamSegs segs;
+    segs.n = 0;
+    int64_t maxlen = 0;
+    for (int l = 0; l < Lp; ++l) {
+        const int64_t wn = (int64_t)pd.sizes[l] * pd.sizes[l + 1], bn = pd.sizes[l + 1];
+        segs.off[segs.n] = w_offset(pd, l); segs.len[segs.n++] = wn;
+        segs.off[segs.n] = b_offset(pd, l); segs.len[segs.n++] = bn;
+        maxlen = wn > maxlen ? wn : maxlen;
+    }
+    const double hstep = (double)(adam_steps_done + 1);
+    const double bc1 = 1.0 - pow((double)beta1, hstep), bc2 = 1.0 - pow((double)beta2, hstep);
+    const int64_t nb = (maxlen + 255) / 256;
+    launch_pdl(k_adam, dim3((unsigned)(nb < 1184 ? nb : 1184), (unsigned)segs.n), dim3(256), 0, s, segs, pparams, exp_avg,
+               exp_avg_sq, (const float*)w.pgrads, beta1, beta2, eps, (float)(lr / bc1), (float)sqrt(bc2),
+               (const float*)nullptr);
+    MB_CUDA_LAUNCH_CHECK("k_adam");
+    if (info != nullptr) {
+        launch_pdl(k_actor_info, dim3(1), dim3(1), 0, s, (const float*)w.scal, B, info);
+        MB_CUDA_LAUNCH_CHECK("k_actor_info");
+    }
+    return MB_OK;
+}
+
 }  // namespace mb

@@ -266,7 +266,7 @@ k_tc_gemm(TgBatch gb, int nt_max) {
         else { x.x = __ldg(p); if (nb + 1 < Nn) x.y = __ldg(p + 1); if (nb + 2 < Nn) x.z = __ldg(p + 2); if (nb + 3 < Nn) x.w = __ldg(p + 3); }
         return x;
     };
-    const float* zb = mode == TG_DX ? op.z + (int64_t)slot * op.z_ss : nullptr;
+    const float* zb = (mode == TG_DX && op.z != nullptr) ? op.z + (int64_t)slot * op.z_ss : nullptr;   // no z: plain A B^T
     const bool z_relu = op.z_act == MB_ACT_RELU;
     const float* wb = mode == TG_DW ? op.w + (int64_t)e * op.w_ms : nullptr;
     float* ob = op.out + (int64_t)slot * op.out_ss + (int64_t)e * op.out_ms;
@@ -283,7 +283,7 @@ k_tc_gemm(TgBatch gb, int nt_max) {
             c[u] = cb4;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!live[u]) continue;
-            if (mode == TG_DX) c[u] = ld4(zb + (int64_t)m * ldz + nb);
+            if (mode == TG_DX) { if (zb != nullptr) c[u] = ld4(zb + (int64_t)m * ldz + nb); }
             else if (mode == TG_DW && !plain[u]) c[u] = ld4(wb + (int64_t)m * Nn + nb);
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
                          : "r"(tile + (uint32_t)(r * LDT + col) * 4u));
@@ -303,6 +303,7 @@ k_tc_gemm(TgBatch gb, int nt_max) {
             } else if (mode == TG_DX) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    if (zb == nullptr) continue;
                     if (z_relu) { vv[i] = cc[i] > 0.f ? vv[i] : 0.f; continue; }
                     const float sg = rcp_ftz(1.0f + ex2_ftz(cc[i] * -1.4426950408889634f));
                     vv[i] *= sg * (1.f + cc[i] * (1.f - sg));

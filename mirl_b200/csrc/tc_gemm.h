@@ -26,7 +26,7 @@ struct TgOp {
     const float* bias;     // FWD: [N] per member
     int64_t bias_ms;
     int out_act;           // FWD (-1 none)
-    const float* z;        // DX: out *= act'(z[m*ldz + n])
+    const float* z;        // DX: out *= act'(z[m*ldz + n]); nullptr: no factor (gradient with respect to a network input)
     int64_t ldz, z_ss;
     int z_act;             // DX: MB_ACT_SWISH (0, the default) or MB_ACT_RELU
     const float* w;        // DW: out += wd * w[m*N + n]

@@ -9,8 +9,8 @@ reparameterised sample from a caller-visible noise tensor, tanh squashing and th
 
 Same constructor arguments, ``action()`` keywords, return values and state-dict keys
 (``module.net.{2l}.weight`` ``[in,out]``, ``module.net.{2l}.bias`` ``[1,out]``) as the reference, so reference
-checkpoints load unchanged.  Forward-only (the SAC actor update differentiates through the reference policy;
-this class serves the no-grad uses: model rollouts, exploration, target actions).  The noise is drawn like the
+checkpoints load unchanged.  ``action()`` is forward-only (model rollouts, exploration, target actions); the SAC actor
+update -- which differentiates through this policy and the critics -- is ``B200ActorTrainer`` below.  The noise is drawn like the
 reference's ``dist.rsample()`` / ``dist.sample()``: one standard-normal ``[B, A]`` tensor from the default
 generator of the observation's device; ``noise=`` replays a recorded draw.
 """
@@ -129,3 +129,120 @@ class B200GaussianPolicy(nn.Module, Policy):
     def action_np(self, obs, **kwargs):
         a, info = self.action(torch.as_tensor(obs, device=self.device).float(), **kwargs)
         return a.cpu().numpy(), {k: v.cpu().numpy() for k, v in info.items()}
+
+
+class B200ActorTrainer(object):
+    """Actor half of ``SACAgent.train_from_torch_batch`` (mirl/agents/sac_agent.py:170-195) on the device:
+    ``policy.action(obs, reparameterize=True, return_log_prob=True)``, ``compute_alpha_loss`` + the Adam step on
+    ``log_alpha`` (:88-100), ``compute_policy_loss`` (:102-118: ``alpha * log_prob.mean() - qf.value(obs, new_action,
+    **current_v_pi_kwargs).mean()`` with the alpha AFTER its step) and the Adam step on the policy, as one chain of
+    launches (``mb_actor_update``): tensor-core layer GEMMs forward and backward through the policy and (input
+    gradients only) through the critics, hand-written sample / log-prob / reduction kernels.  The critics are read,
+    not updated.
+
+    ``policy`` is a ``B200GaussianPolicy``, ``qf`` a ``B200EnsembleQValue`` or ``B200TQCQValue``; the other
+    arguments are the ``SACAgent`` ones (sac_agent.py:17-37).  ``current_v_pi_kwargs``: ``mode`` min / mean / max,
+    ``sample_number`` (None = all members; fewer: the batch-wise draw of ensemble_value.py:84-86 -- the per-row draw
+    is not covered); for TQC ``number_drop`` must be 0 (tqc_agent.py:26-28)."""
+
+    def __init__(self, policy, qf, policy_lr=3e-4, alpha_if_not_automatic=1e-2, use_automatic_entropy_tuning=True,
+                 init_log_alpha=0, target_entropy=None, current_v_pi_kwargs=None, optimizer_class="Adam",
+                 optimizer_kwargs={}):
+        import numpy as np
+        if optimizer_class not in ("Adam", torch.optim.Adam):
+            raise NotImplementedError("the actor update implements torch.optim.Adam only")
+        extra = set(optimizer_kwargs) - {"betas", "eps"}
+        if extra:
+            raise NotImplementedError("Adam options %s" % sorted(extra))
+        self.policy, self.qf = policy, qf
+        self.policy_lr = policy_lr
+        self.betas = tuple(optimizer_kwargs.get("betas", (0.9, 0.999)))
+        self.eps = optimizer_kwargs.get("eps", 1e-8)
+        self.use_automatic_entropy_tuning = use_automatic_entropy_tuning
+        self.alpha_if_not_automatic = alpha_if_not_automatic
+        self.target_entropy = (-float(np.prod(policy.action_shape)) if target_entropy is None else float(target_entropy))
+        self.current_v_pi_kwargs = dict(current_v_pi_kwargs or {})
+        dev = policy.device
+        self.exp_avg = torch.zeros_like(policy.net.flat.data)
+        self.exp_avg_sq = torch.zeros_like(policy.net.flat.data)
+        # [log_alpha, exp_avg, exp_avg_sq]
+        self.alpha_state = torch.tensor([float(init_log_alpha), 0.0, 0.0], device=dev)
+        self.num_updates = 0
+        self._ws = None
+
+    @property
+    def log_alpha(self):
+        return self.alpha_state[0:1]
+
+    def get_alpha(self):
+        """``SACAgent._get_alpha`` (sac_agent.py:66-72)."""
+        if self.use_automatic_entropy_tuning:
+            return float(self.alpha_state[0].exp().item())
+        return self.alpha_if_not_automatic
+
+    def _reduction(self):
+        import numpy as np
+        from .values import B200TQCQValue
+        kw, E = self.current_v_pi_kwargs, self.qf.ensemble_size
+        if isinstance(self.qf, B200TQCQValue):
+            if kw.get("number_drop", 0) not in (0, None) or kw.get("percentage_drop") not in (0, None):
+                raise NotImplementedError("the actor update pools all atoms (number_drop 0, tqc_agent.py:26-28)")
+            return _lib.REDUCE["mean"], None
+        mode = kw.get("mode", "min")
+        if mode not in _lib.REDUCE:
+            raise NotImplementedError("mode %r" % (mode,))
+        n = kw.get("sample_number", 2)
+        n = E if n is None else n
+        members = None
+        if n != E:
+            if not kw.get("batchwise_sample", False):
+                raise NotImplementedError("per-row member draws (sample_from_ensemble) inside the actor update")
+            members = np.random.choice(E, n, replace=False).astype(np.int32)       # ensemble_value.py:85
+        return _lib.REDUCE[mode], members
+
+    def update_async(self, obs, noise=None):
+        """One actor (+ alpha) update; returns the device tensor ``info [8]`` (see ``mb_actor_update``) without
+        synchronising.  ``noise [B, A]`` replays a recorded ``rsample()`` draw."""
+        pol, qf, L = self.policy, self.qf, _lib.lib()
+        dev = pol.device
+        obs = _lib.f32(obs, dev)
+        assert obs.dim() == 2
+        B, O, A = obs.shape[0], pol.observation_shape[0], pol.action_shape[0]
+        noise = torch.randn(B, A, device=dev) if noise is None else _lib.f32(noise, dev)
+        assert noise.shape == (B, A)
+        for name in ("exp_avg", "exp_avg_sq", "alpha_state"):
+            if getattr(self, name).device != dev:
+                setattr(self, name, getattr(self, name).to(dev))
+        pd, cd = ctypes.byref(pol.net.desc), ctypes.byref(qf.module.desc)
+        need = L.mb_actor_workspace_bytes(pd, cd, B)
+        if need == 0:
+            raise NotImplementedError("actor update: %s" % L.mb_last_error().decode())
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        mode, members = self._reduction()
+        marr = None if members is None else (ctypes.c_int32 * len(members))(*[int(m) for m in members])
+        cfg = _lib.PolicyCfg(float(pol.mean_scale), float(pol.std_scale), float(pol.min_std),
+                             float(pol.logstd_extra_bias), _lib.LOGSTD_BOUND[pol.bound_mode], int(bool(pol.squashed)))
+        info = torch.zeros(8, device=dev)
+        auto = self.use_automatic_entropy_tuning
+        st = self.alpha_state
+        with torch.cuda.device(dev):
+            _lib.check(L.mb_actor_update(
+                pd, _lib.ptr(pol.net.flat.data), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.num_updates,
+                float(self.policy_lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), ctypes.byref(cfg),
+                cd, _lib.ptr(qf.module.flat.data), mode, marr, 0 if members is None else len(members),
+                _lib.ptr(obs), _lib.ptr(noise), O, A, B,
+                _lib.ptr(st[0:1]) if auto else None, _lib.ptr(st[1:2]) if auto else None, _lib.ptr(st[2:3]) if auto else None,
+                float(self.target_entropy), float(self.alpha_if_not_automatic), _lib.ptr(info), _lib.ptr(self._ws),
+                self._ws.numel(), _lib.stream(dev)))
+        self.num_updates += 1
+        pol.net.mark_weights_changed()
+        return info
+
+    def update(self, obs, noise=None):
+        """-> the ``train_info`` entries of the reference (sac_agent.py:97-99,147-149), synchronising like it."""
+        v = self.update_async(obs, noise).tolist()
+        out = {"policy/loss": v[0], "policy/q_pi": v[1], "policy/entropy": v[2]}
+        if self.use_automatic_entropy_tuning:
+            out.update({"alpha/value": v[3], "alpha/loss": v[4]})
+        return out

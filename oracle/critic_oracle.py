@@ -149,3 +149,46 @@ def policy_action(W, b, obs, eps=None, squashed=True, min_std=1e-4, mean_scale=1
     if squashed:
         lp = lp - (2 * np.log(2) - torch.nn.functional.softplus(2 * pre) - torch.nn.functional.softplus(-2 * pre))
     return (torch.tanh(pre) if squashed else pre), lp.sum(-1, keepdim=True), mean, std
+
+
+def actor_update(pW, pb, popt, log_alpha, aopt, cW, cb, obs, eps, lr=3e-4, target_entropy=-1.0, mode="mean",
+                 member_idx=None, alpha_fixed=None, squashed=True, activation="relu"):
+    """Actor half of SACAgent.train_from_torch_batch (mirl/agents/sac_agent.py:170-195): policy.action with
+    ``reparameterize=True, return_log_prob=True`` (gaussian.py:55-97; ``eps`` is the rsample draw),
+    compute_alpha_loss (:88-100) + Adam on ``log_alpha``, compute_policy_loss (:102-118) with the alpha AFTER its
+    step, ``qf.value(obs, new_action, mode=..., sample_number/batchwise index=member_idx)`` (ensemble_value.py:65-107;
+    several outputs per member: TQCQValue.value with number_drop 0 = mean of all atoms, distributional_value.py:51-55),
+    Adam on the policy.  Gradients by torch autograd on this restatement.  Mutates ``pW, pb, popt`` (policy
+    parameters ``[1,in,out]`` / ``[1,1,out]`` and ``{"step","m","v"}``) and ``log_alpha`` / ``aopt`` (a 1-element
+    tensor and its state; ``log_alpha=None``: fixed ``alpha_fixed``).  Returns the info dict of the reference
+    (policy/loss, policy/q_pi, policy/entropy, alpha/value, alpha/loss)."""
+    from oracle.pe_oracle import adam_update
+    leaves = [t.clone().requires_grad_(True) for t in list(pW) + list(pb)]
+    n = len(pW)
+    action, lp, _, _ = policy_action(leaves[:n], leaves[n:], obs, eps, squashed=squashed, activation=activation)
+    info = {}
+    if log_alpha is not None:
+        res = float(lp.detach().mean()) + target_entropy
+        alpha = float(log_alpha.exp())
+        info["alpha/value"], info["alpha/loss"] = alpha, -res * alpha
+        aopt["step"] += 1
+        adam_update(log_alpha, torch.tensor([-res * alpha]), aopt["m"][0], aopt["v"][0], aopt["step"], lr=lr)
+        alpha = float(log_alpha.exp())
+    else:
+        alpha = alpha_fixed
+    q = mlp_forward(cW, cb, torch.cat([obs, action], dim=-1), activation)           # [E,B,Q]
+    if member_idx is not None:
+        q = q[torch.as_tensor(np.asarray(member_idx), dtype=torch.long)]
+    if q.shape[-1] > 1:                                                           # TQC: pooled atoms, no drop
+        value = q.transpose(0, 1).reshape(q.shape[1], -1).mean(-1, keepdim=True)
+    else:
+        value = reduce_members(q, mode)
+    entropy, q_pi = -lp.mean(), value.mean()
+    loss = -alpha * entropy - q_pi
+    grads = torch.autograd.grad(loss, leaves)
+    popt["step"] += 1
+    for t, g, m, v in zip(list(pW) + list(pb), grads, popt["m"], popt["v"]):
+        adam_update(t, g, m, v, popt["step"], lr=lr)
+    info.update({"policy/loss": float(loss.detach()), "policy/q_pi": float(q_pi.detach()),
+                 "policy/entropy": float(entropy.detach())})
+    return info

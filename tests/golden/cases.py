@@ -209,6 +209,14 @@ def tqc_atoms_target(x, seed, n_target=115):
     return (x["rewards"] + 0.5 * x["log_prob"] + 1.5 * spread).astype(np.float32)
 
 
+def actor_noise(step, B=256, act=ACT):
+    """The standard-normal draw ``policy.action`` consumed in gen_golden.gen_actor_update: ``dist.rsample()`` after
+    ``torch.manual_seed(980 + step)`` is ``mean + std * torch.randn(B, A)`` of the same generator state."""
+    import torch
+    torch.manual_seed(980 + step)
+    return torch.randn(B, act).numpy()
+
+
 def policy_state_dict(W, b):
     """Reference ``GaussianPolicy.state_dict()`` keys (a plain MLP: ``module.net.{2l}.weight`` / ``.bias``)."""
     sd = {}

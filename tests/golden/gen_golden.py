@@ -546,6 +546,61 @@ def gen_tqc_update():
     print("tqc_update", out["loss"])
 
 
+def gen_actor_update():
+    """Actor half of SACAgent.train_from_torch_batch (sac_agent.py:170-195) on the reference classes: GaussianPolicy
+    (17 -> 256 -> 256 -> 12 relu, tanh-squashed) and EnsembleQValue (REDQ: 10 critics, 2x256 relu; value = mean over
+    all members, configs/redq.json:96-99): policy.action(reparameterize=True, return_log_prob=True),
+    SACAgent.compute_alpha_loss + Adam(log_alpha), SACAgent.compute_policy_loss + Adam(policy), lr 3e-4,
+    target_entropy -1 (redq.json:95); four updates on batch 256.  The second fixture uses a 2-member critic with
+    mode 'min' (SAC's default current_v_pi_kwargs)."""
+    import types
+    from mirl.agents.sac_agent import SACAgent
+    from mirl.policies.gaussian_policy import GaussianPolicy
+    from mirl.values.ensemble_value import EnsembleQValue
+    env = ref_shim.FakeEnv()
+    for tag, E, v_pi in (("redq", 10, {"sample_number": None, "mode": "mean"}), ("sacmin", 2, {"sample_number": None, "mode": "min"})):
+        pol = GaussianPolicy(env, hidden_layers=[256, 256], activation="relu")
+        W, b = cases.mlp_params(95, 1, [cases.OBS, 256, 256, 2 * cases.ACT])
+        pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(W, b).items()})
+        qf = EnsembleQValue(env, ensemble_size=E, hidden_layers=[256, 256], activation="relu")
+        cW, cb = cases.mlp_params(96, E, [cases.OBS + cases.ACT, 256, 256, 1])
+        qf.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(cW, cb).items()})
+        log_alpha = torch.zeros(1, requires_grad=True)
+        stub = types.SimpleNamespace(qf=qf, log_alpha=log_alpha, use_automatic_entropy_tuning=True, target_entropy=-1.0,
+                                     _log_policy_info=lambda *a: {})
+        stub._get_alpha = lambda: log_alpha.exp().detach()
+        popt = torch.optim.Adam(pol.parameters(), lr=3e-4)
+        aopt = torch.optim.Adam([log_alpha], lr=3e-4)
+        out = {k: [] for k in ("policy_loss", "q_pi", "entropy", "alpha_value", "alpha_loss", "log_alpha")}
+        steps = 4
+        for s_ in range(steps):
+            o, _ = cases.rollout_inputs(970 + s_, 256)
+            torch.manual_seed(980 + s_)
+            new_action, info = pol.action(T(o), reparameterize=True, return_log_prob=True)
+            alpha_loss, ainfo = SACAgent.compute_alpha_loss(stub, info)
+            aopt.zero_grad()
+            alpha_loss.backward()
+            aopt.step()
+            policy_loss, _ = SACAgent.compute_policy_loss(stub, T(o), new_action, info, v_pi)
+            popt.zero_grad()
+            policy_loss.backward()
+            popt.step()
+            with torch.no_grad():
+                qv, _ = qf.value(T(o), new_action, **v_pi)
+            out["policy_loss"].append(float(policy_loss)); out["q_pi"].append(float(qv.mean()))
+            out["entropy"].append(float(-info["log_prob"].mean()))
+            out["alpha_value"].append(ainfo["alpha/value"]); out["alpha_loss"].append(ainfo["alpha/loss"])
+            out["log_alpha"].append(float(log_alpha))
+            if s_ + 1 in (1, steps):
+                out["param_proj_%d" % (s_ + 1)] = np.stack([proj(p, 8000 + i) for i, p in enumerate(pol.parameters())])
+                out["m_proj_%d" % (s_ + 1)] = np.stack([proj(popt.state[p]["exp_avg"], 8100 + i)
+                                                         for i, p in enumerate(pol.parameters())])
+        out = {k: (np.array(v, dtype=np.float64) if isinstance(v, list) else v) for k, v in out.items()}
+        out["names"] = np.array([n for n, _ in pol.named_parameters()])
+        np.savez(os.path.join(HERE, "actor_update_%s.npz" % tag), **out)
+        print(tag, out["policy_loss"], out["log_alpha"])
+
+
 def gen_policy():
     """GaussianPolicy.action (gaussian_policy.py:35-47 -> gaussian.py:55-97,199-204), 17 -> 256 -> 256 -> 12 relu,
     tanh-squashed: reparameterised and plain samples with log-prob / mean / std, and the deterministic action.
@@ -582,7 +637,7 @@ def main():
         globals()["gen_" + only]()
     else:
         gen_forward(); gen_step(); gen_dist(); gen_loss(); gen_train(); gen_critics(); gen_keys(); gen_pool()
-        gen_trainloop(); gen_collect(); gen_extrapool(); gen_critic_update(); gen_tqc_update(); gen_policy()
+        gen_trainloop(); gen_collect(); gen_extrapool(); gen_critic_update(); gen_tqc_update(); gen_actor_update(); gen_policy()
     for f in sorted(os.listdir(HERE)):
         if f.endswith((".npz", ".json")):
             print("%8d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))

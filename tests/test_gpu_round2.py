@@ -523,6 +523,54 @@ def test_wide_critic_update_chain_matches_oracle():
                 assert_close(tsd[name].cpu(), ot_, what="target " + name)
 
 
+@pytest.mark.parametrize("tag,E,mode", [("redq", 10, "mean"), ("sacmin", 2, "min")])
+def test_actor_update_matches_reference(tag, E, mode):
+    """B200ActorTrainer against the reference's actor half of SACAgent.train_from_torch_batch (policy.action with the
+    recorded rsample draw, compute_alpha_loss + Adam(log_alpha), compute_policy_loss + Adam(policy); REDQ: mean over
+    10 critics, SAC default: min over 2): policy loss, q_pi, entropy, alpha trajectory, policy parameters and first
+    moments after 1 and 4 updates."""
+    import mirl_b200
+    g = golden("actor_update_%s.npz" % tag)
+    pol = mirl_b200.B200GaussianPolicy(FakeEnv(), hidden_layers=[256, 256], activation="relu")
+    W, b = cases.mlp_params(95, 1, [cases.OBS, 256, 256, 2 * cases.ACT])
+    pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(W, b).items()})
+    pol = pol.to("cuda")
+    qf = mirl_b200.B200EnsembleQValue(FakeEnv(), ensemble_size=E, hidden_layers=[256, 256], activation="relu")
+    cW, cb = cases.mlp_params(96, E, [cases.OBS + cases.ACT, 256, 256, 1])
+    qf.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(cW, cb).items()})
+    qf = qf.to("cuda")
+    before = qf.module.flat.data.clone()
+    tr = mirl_b200.B200ActorTrainer(pol, qf, policy_lr=3e-4, target_entropy=-1.0,
+                                    current_v_pi_kwargs={"sample_number": None, "mode": mode})
+    steps = len(g["policy_loss"])
+    for s_ in range(steps):
+        o, _ = cases.rollout_inputs(970 + s_, 256)
+        info = tr.update(T(o, "cuda"), noise=T(cases.actor_noise(s_), "cuda"))
+        for key, name in (("policy/loss", "policy_loss"), ("policy/q_pi", "q_pi"), ("policy/entropy", "entropy"),
+                          ("alpha/value", "alpha_value"), ("alpha/loss", "alpha_loss")):
+            assert abs(info[key] - g[name][s_]) <= 1e-3 * abs(g[name][s_]) + 1e-5, (s_, key, info[key], g[name][s_])
+        assert abs(float(tr.log_alpha.item()) - g["log_alpha"][s_]) <= 2e-6, (s_, float(tr.log_alpha.item()))
+        if s_ + 1 in (1, steps):
+            sd = pol.state_dict()
+            msd = dict(zip([k for k, _ in pol._reference_items()],
+                           [v for _, v in _policy_views(pol, tr.exp_avg)]))
+            for i, name in enumerate(g["names"]):
+                name = str(name)
+                got, ref = proj(sd[name], 8000 + i), g["param_proj_%d" % (s_ + 1)][i]
+                assert abs(got[0] - ref[0]) <= 3e-4 * (s_ + 1) * 0.05 * np.sqrt(sd[name].numel()) + 1e-4 * ref[0], (name, got, ref)
+                gm, rm = proj(msd[name], 8100 + i), g["m_proj_%d" % (s_ + 1)][i]
+                assert abs(gm[0] - rm[0]) <= 3e-3 * rm[0] + 2e-5, ("exp_avg", name, gm, rm)
+    assert torch.equal(qf.module.flat.data, before)               # the critics are read, not updated
+
+
+def _policy_views(pol, flat):
+    """Per-tensor views of a blob laid out like the policy's parameters, in the reference's key order."""
+    net = pol.net
+    for l in range(net.num_fc):
+        yield "w", net.weight(l, flat=flat)[0]
+        yield "b", net.bias(l, flat=flat)[0].view(1, -1)
+
+
 # ---- N1: policy action -------------------------------------------------------------------------------
 def test_gaussian_policy_action_matches_reference():
     """B200GaussianPolicy.action against the reference GaussianPolicy (17 -> 256 -> 256 -> 12 relu, tanh-squashed):
