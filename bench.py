@@ -339,6 +339,18 @@ def secondary_metrics(dev, world, rank, timed):
                          "unit": "TFLOP/s", "frac": tf / pk["tensor"], "bound": "latency (11 launches)",
                          "config": "TQC: 5 critics 3x512 relu x 25 quantiles, batch 256, 115 target atoms: tcgen05 layer "
                                    "GEMM chain + quantile-Huber head + Adam + soft target update"}
+    # actor + alpha update (N3, second half): REDQ's policy against the mean of its 10 critics
+    pol = mirl_b200.B200GaussianPolicy(FakeEnv(), hidden_layers=[256, 256], activation="relu").to(dev)
+    at = mirl_b200.B200ActorTrainer(pol, q, target_entropy=-1.0, current_v_pi_kwargs={"sample_number": None, "mode": "mean"})
+    eps_a = torch.randn(B, 6, device=dev)
+    ms = timed(lambda: at.update_async(o, eps_a), 100, 10) / 100
+    pm = 17 * 256 + 256 * 256 + 256 * 12
+    tf = (2 * pm * 3 + 10 * 2 * cm * 2) * B / (ms * 1e-3) / 1e12
+    out["actor_update"] = {"updates_per_s": 1e3 / ms, "kernel_ms": ms, "achieved": tf, "peak": pk["tensor"],
+                           "unit": "TFLOP/s", "frac": tf / pk["tensor"], "bound": "latency (17 launches)",
+                           "config": "REDQ: policy 17-256-256-12 relu through the mean of 10 critics 2x256, batch 256: policy "
+                                     "forward + sample + alpha step + critics forward + input-gradient chain + policy "
+                                     "backward + Adam"}
     ms = timed(lambda: q.q_target(o, a, r, d, lp, alpha=0.2, sample_number=2, batchwise_sample=True), 200, 20) / 200
     tf = 2 * 2 * cm * B / (ms * 1e-3) / 1e12                                             # 2 drawn members
     out["redq_target"] = {"targets_per_s": world * B / (ms * 1e-3), "kernel_ms": ms, "achieved": tf, "peak": pk["tensor"],

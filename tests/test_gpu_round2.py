@@ -563,6 +563,50 @@ def test_actor_update_matches_reference(tag, E, mode):
     assert torch.equal(qf.module.flat.data, before)               # the critics are read, not updated
 
 
+@pytest.mark.parametrize("kind", ["tqc", "subset", "fixed_alpha"])
+def test_actor_update_variants_match_oracle(kind, monkeypatch):
+    """The other reductions of the actor update against critic_oracle.actor_update (pinned to the reference by the
+    actor_update fixtures): TQC critics (3x512, 25 quantiles: q_pi = mean of all 125 atoms), a batch-wise drawn
+    subset (3 of 10 members, max), and a fixed entropy coefficient (use_automatic_entropy_tuning False)."""
+    import mirl_b200
+    from oracle import critic_oracle as co
+    from tests.helpers_gpu import make_critic
+    pol = mirl_b200.B200GaussianPolicy(FakeEnv(), hidden_layers=[256, 256], activation="relu")
+    W, b = cases.mlp_params(97, 1, [cases.OBS, 256, 256, 2 * cases.ACT])
+    pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(W, b).items()})
+    pol = pol.to("cuda")
+    qf, (cW, cb) = make_critic("tqc" if kind == "tqc" else "redq", 98)
+    kw = {"tqc": {"number_drop": 0}, "subset": {"sample_number": 3, "batchwise_sample": True, "mode": "max"},
+          "fixed_alpha": {"sample_number": None, "mode": "min"}}[kind]
+    auto = kind != "fixed_alpha"
+    tr = mirl_b200.B200ActorTrainer(pol, qf, policy_lr=1e-3, target_entropy=-3.0, current_v_pi_kwargs=kw,
+                                    use_automatic_entropy_tuning=auto, alpha_if_not_automatic=0.05)
+    pW, pb = [T(a.copy()) for a in W], [T(a.copy()) for a in b]
+    popt = {"step": 0, "m": [torch.zeros_like(t) for t in pW + pb], "v": [torch.zeros_like(t) for t in pW + pb]}
+    log_alpha = torch.zeros(1) if auto else None
+    aopt = {"step": 0, "m": [torch.zeros(1)], "v": [torch.zeros(1)]}
+    rs = np.random.RandomState(12)
+    for s_ in range(3):
+        o, _ = cases.rollout_inputs(990 + s_, 200)
+        eps = rs.standard_normal((200, cases.ACT)).astype(np.float32)
+        members = None
+        if kind == "subset":
+            np.random.seed(40 + s_)
+            members = np.random.choice(10, 3, replace=False)           # the draw the trainer makes (ensemble_value.py:85)
+            np.random.seed(40 + s_)
+        want = co.actor_update(pW, pb, popt, log_alpha, aopt, [T(a) for a in cW], [T(a) for a in cb], T(o), T(eps),
+                               lr=1e-3, target_entropy=-3.0, mode=kw.get("mode", "mean"), member_idx=members,
+                               alpha_fixed=0.05)
+        info = tr.update(T(o, "cuda"), noise=T(eps, "cuda"))
+        for key, v in want.items():
+            assert abs(info[key] - v) <= 1e-3 * abs(v) + 1e-5, (s_, key, info[key], v)
+    sd = pol.state_dict()
+    for l in range(3):
+        # Adam moves every weight by about lr per step whatever the gradient's size: compare on that scale
+        assert (sd["module.net.%d.weight" % (2 * l)].cpu() - pW[l][0]).abs().max() <= 0.15 * 3 * 1e-3
+        assert (sd["module.net.%d.bias" % (2 * l)].cpu() - pb[l][0]).abs().max() <= 0.15 * 3 * 1e-3
+
+
 def _policy_views(pol, flat):
     """Per-tensor views of a blob laid out like the policy's parameters, in the reference's key order."""
     net = pol.net
