@@ -15,6 +15,7 @@ B200DevicePool        SimplePool (imagined-data pool, in HBM)      mirl/pools/si
 B200ExtraFieldPool    ExtraFieldPool (real-data pool, in HBM)      mirl/pools/extra_field_pool.py
 B200CriticTrainer     critic half of SACAgent.train_from_torch_batch  mirl/agents/sac_agent.py:160-166
 B200ActorTrainer      actor + alpha half of the same                  mirl/agents/sac_agent.py:170-195
+B200SACUpdater        SACAgent.train_from_torch_batch                 mirl/agents/sac_agent.py:152-204
 B200GaussianPolicy    GaussianPolicy (forward / sampling)           mirl/policies/gaussian_policy.py
 ====================  ===========================================  ============================
 
@@ -27,7 +28,8 @@ from .values import B200CriticTrainer, B200EnsembleQValue, B200TQCQValue  # noqa
 from .collectors import B200MBPOCollector, B200MOPOCollector  # noqa: F401
 from .pools import B200DevicePool, B200ExtraFieldPool  # noqa: F401
 from .policies import B200ActorTrainer, B200GaussianPolicy  # noqa: F401
+from .agents import B200SACUpdater                    # noqa: F401
 
 __all__ = ["B200PEModel", "B200PEModelTrainer", "B200EnsembleQValue", "B200TQCQValue", "B200CriticTrainer",
            "B200MBPOCollector", "B200MOPOCollector", "B200DevicePool", "B200ExtraFieldPool", "B200GaussianPolicy",
-           "B200ActorTrainer"]
+           "B200ActorTrainer", "B200SACUpdater"]

@@ -192,3 +192,30 @@ def actor_update(pW, pb, popt, log_alpha, aopt, cW, cb, obs, eps, lr=3e-4, targe
     info.update({"policy/loss": float(loss.detach()), "policy/q_pi": float(q_pi.detach()),
                  "policy/entropy": float(entropy.detach())})
     return info
+
+
+def sac_train_step(state, batch, step, noise_fn, discount=0.99, lr=3e-4, tau=5e-3, target_entropy=-1.0,
+                   policy_update_freq=20, next_sample_number=2, current_mode="mean"):
+    """SACAgent.train_from_torch_batch (mirl/agents/sac_agent.py:152-204) with REDQ's settings, composed from the
+    functions above, consuming NumPy's global generator exactly like the reference: the batch-wise member pair of
+    the TD target (ensemble_value.py:84-86) and the per-row sample that ``compute_qf_loss`` draws and discards
+    (``qf.value(..., return_ensemble=True)`` with the default sample_number 2, ddpg_agent.py:139 ->
+    ensemble_value.py:87-88).  ``state``: dict with pW, pb, popt, cW, cb, copt, tW, tb, log_alpha, aopt;
+    ``noise_fn(B, A)`` = the policy's standard-normal draw.  Returns the reference's train_info entries."""
+    pW, pb, cW, cb, tW, tb = (state[k] for k in ("pW", "pb", "cW", "cb", "tW", "tb"))
+    B, A = batch["actions"].shape
+    E = cW[0].shape[0]
+    alpha = float(state["log_alpha"].exp())
+    next_action, lp, _, _ = policy_action(pW, pb, batch["next_observations"], noise_fn(B, A))
+    idx = subset_indices_batchwise(E, next_sample_number)
+    v = redq_value(tW, tb, batch["next_observations"], next_action, member_idx=idx, mode="min")
+    q_target = td_target(v, batch["rewards"], batch["terminals"], lp, alpha, discount)
+    if E != 2:
+        subset_indices_rowwise(E, B, 2)                       # drawn and discarded by compute_qf_loss
+    info = {"qf/loss": float(critic_update(cW, cb, state["copt"], tW, tb, batch["observations"], batch["actions"],
+                                           q_target, lr=lr, tau=tau))}
+    if step % policy_update_freq == 0:
+        info.update(actor_update(pW, pb, state["popt"], state["log_alpha"], state["aopt"], cW, cb,
+                                 batch["observations"], noise_fn(B, A), lr=lr, target_entropy=target_entropy,
+                                 mode=current_mode))
+    return info

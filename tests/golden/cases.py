@@ -209,6 +209,18 @@ def tqc_atoms_target(x, seed, n_target=115):
     return (x["rewards"] + 0.5 * x["log_prob"] + 1.5 * spread).astype(np.float32)
 
 
+def sac_batch(seed, B, obs=OBS, act=ACT):
+    """A replay batch with the keys SACAgent.train_from_torch_batch reads (sac_agent.py:153-157)."""
+    rs = np.random.RandomState(seed)
+    return {
+        "observations": rs.standard_normal((B, obs)).astype(np.float32),
+        "actions": rs.uniform(-1, 1, (B, act)).astype(np.float32),
+        "rewards": rs.standard_normal((B, 1)).astype(np.float32),
+        "terminals": (rs.uniform(size=(B, 1)) < 0.1).astype(np.float32),
+        "next_observations": rs.standard_normal((B, obs)).astype(np.float32),
+    }
+
+
 def actor_noise(step, B=256, act=ACT):
     """The standard-normal draw ``policy.action`` consumed in gen_golden.gen_actor_update: ``dist.rsample()`` after
     ``torch.manual_seed(980 + step)`` is ``mean + std * torch.randn(B, A)`` of the same generator state."""
