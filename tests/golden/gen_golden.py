@@ -603,58 +603,73 @@ def gen_actor_update():
 
 
 def gen_sac_update():
-    """The UNMODIFIED reference agent end to end: SACAgent.train_from_torch_batch (sac_agent.py:152-204) with the
-    REDQ settings of configs/redq.json (10 critics 2x256 relu, q_target = min over a batch-wise random pair,
-    policy through the mean of all ten, policy_update_freq 20, target_entropy -1, lr 3e-4, tau 5e-3), 24 updates on
-    batch 256: critic loss of every update, the actor / alpha statistics of updates 0 and 20, parameter checksums of
-    qf, qf_target, policy and log_alpha at the end.  RNG: np.random.seed(31) (member pairs), torch.manual_seed(32)
-    (one [256, 6] standard-normal draw per policy.action call, in call order)."""
+    """The UNMODIFIED reference agents end to end.
+    redq: SACAgent.train_from_torch_batch (sac_agent.py:152-204) with the settings of configs/redq.json (10 critics
+    2x256 relu, q_target = min over a batch-wise random pair, policy through the mean of all ten,
+    policy_update_freq 20, target_entropy -1, lr 3e-4, tau 5e-3), 24 updates on batch 256.
+    tqc: TQCAgent (tqc_agent.py:16-66) with configs/tqc.json (5 critics 3x512 relu x 25 quantiles, 8 % of the pooled
+    target atoms dropped, quantile-Huber critic loss, policy through the mean of all atoms, every update), 6 updates.
+    Recorded: critic loss of every update, the actor / alpha statistics of the updates that have them, parameter
+    checksums of qf, qf_target, policy and log_alpha at the end.  RNG: np.random.seed(31) (member pairs),
+    torch.manual_seed(32) (one [256, 6] standard-normal draw per policy.action call, in call order)."""
     import contextlib
     import tempfile
     from mirl.agents.sac_agent import SACAgent
+    from mirl.agents.tqc_agent import TQCAgent
     from mirl.policies.gaussian_policy import GaussianPolicy
     from mirl.utils.logger import logger
+    from mirl.values.distributional_value import TQCQValue
     from mirl.values.ensemble_value import EnsembleQValue
     with contextlib.redirect_stdout(sys.stderr):
         logger.set_snapshot_dir(tempfile.mkdtemp())
     env = ref_shim.FakeEnv()
-    c = cases.REDQ
-    pol = GaussianPolicy(env, hidden_layers=[256, 256], activation="relu")
-    W, b = cases.mlp_params(95, 1, [cases.OBS, 256, 256, 2 * cases.ACT])
-    pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(W, b).items()})
-    sizes = [cases.OBS + cases.ACT] + c["hidden"] + [c["out"]]
+    for tag in ("redq", "tqc"):
+        c = cases.REDQ if tag == "redq" else cases.TQC
+        pol = GaussianPolicy(env, hidden_layers=[256, 256], activation="relu")
+        W, b = cases.mlp_params(95, 1, [cases.OBS, 256, 256, 2 * cases.ACT])
+        pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(W, b).items()})
+        sizes = [cases.OBS + cases.ACT] + c["hidden"] + [c["out"]]
 
-    def build(seed):
-        q = EnsembleQValue(env, ensemble_size=c["E"], hidden_layers=list(c["hidden"]), activation=c["act"])
-        cW, cb = cases.mlp_params(seed, c["E"], sizes)
-        q.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(cW, cb).items()})
-        return q
-    qf, qt = build(71), build(171)                    # DDPGAgent.__init__ copies qf into qf_target (ddpg_agent.py:68)
-    agent = SACAgent(env, pol, qf, qt, policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3,
-                     use_automatic_entropy_tuning=True, alpha_if_not_automatic=0, policy_update_freq=20,
-                     target_entropy=-1, current_v_pi_kwargs={"sample_number": None, "mode": "mean"},
-                     next_v_pi_kwargs={"batchwise_sample": True}, tb_log_freq=-1)
-    np.random.seed(31)
-    torch.manual_seed(32)
-    steps = 24
-    out = {"qf_loss": [], "actor_steps": []}
-    for k in ("policy/loss", "policy/q_pi", "policy/entropy", "alpha/value", "alpha/loss"):
-        out[k.replace("/", "_")] = []
-    for s_ in range(steps):
-        x = cases.sac_batch(1200 + s_, 256)
-        info = agent.train_from_torch_batch({k: T(v) for k, v in x.items()})
-        out["qf_loss"].append(float(info["qf/loss"]))
-        if s_ % 20 == 0:
-            out["actor_steps"].append(s_)
-            for k in ("policy/loss", "policy/q_pi", "policy/entropy", "alpha/value", "alpha/loss"):
-                out[k.replace("/", "_")].append(float(info[k]))
-    out = {k: np.array(v, dtype=np.float64) for k, v in out.items()}
-    out["log_alpha"] = np.array(float(agent.log_alpha))
-    out["qf_proj"] = np.stack([proj(p, 9000 + i) for i, p in enumerate(qf.parameters())])
-    out["qt_proj"] = np.stack([proj(p, 9100 + i) for i, p in enumerate(qt.parameters())])
-    out["pol_proj"] = np.stack([proj(p, 9200 + i) for i, p in enumerate(pol.parameters())])
-    np.savez(os.path.join(HERE, "sac_update_redq.npz"), **out)
-    print("sac_update", out["qf_loss"][:3], out["qf_loss"][-3:], out["policy_loss"], out["log_alpha"])
+        def build(seed):
+            if tag == "redq":
+                q = EnsembleQValue(env, ensemble_size=c["E"], hidden_layers=list(c["hidden"]), activation=c["act"])
+            else:
+                q = TQCQValue(env, ensemble_size=c["E"], number_head=c["out"], hidden_layers=list(c["hidden"]),
+                              activation=c["act"])
+            cW, cb = cases.mlp_params(seed, c["E"], sizes)
+            q.load_state_dict({k: T(v) for k, v in cases.mlp_state_dict(cW, cb).items()})
+            return q
+        qf, qt = build(71), build(171)                # DDPGAgent.__init__ copies qf into qf_target (ddpg_agent.py:68)
+        if tag == "redq":
+            agent = SACAgent(env, pol, qf, qt, policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3,
+                             use_automatic_entropy_tuning=True, alpha_if_not_automatic=0, policy_update_freq=20,
+                             target_entropy=-1, current_v_pi_kwargs={"sample_number": None, "mode": "mean"},
+                             next_v_pi_kwargs={"batchwise_sample": True}, tb_log_freq=-1)
+            steps, freq = 24, 20
+        else:
+            agent = TQCAgent(env, pol, qf, qt, policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3,
+                             use_automatic_entropy_tuning=True, alpha_if_not_automatic=0, tb_log_freq=-1)
+            steps, freq = 6, 1
+        np.random.seed(31)
+        torch.manual_seed(32)
+        out = {"qf_loss": [], "actor_steps": []}
+        for k in ("policy/loss", "policy/q_pi", "policy/entropy", "alpha/value", "alpha/loss"):
+            out[k.replace("/", "_")] = []
+        for s_ in range(steps):
+            x = cases.sac_batch(1200 + s_, 256)
+            info = agent.train_from_torch_batch({k: T(v) for k, v in x.items()})
+            out["qf_loss"].append(float(info["qf/loss"]))
+            if s_ % freq == 0:
+                out["actor_steps"].append(s_)
+                for k in ("policy/loss", "policy/q_pi", "policy/entropy", "alpha/value", "alpha/loss"):
+                    out[k.replace("/", "_")].append(float(info[k]))
+        out = {k: np.array(v, dtype=np.float64) for k, v in out.items()}
+        out["log_alpha"] = np.array(float(agent.log_alpha))
+        out["qf_proj"] = np.stack([proj(p, 9000 + i) for i, p in enumerate(qf.parameters())])
+        out["qt_proj"] = np.stack([proj(p, 9100 + i) for i, p in enumerate(qt.parameters())])
+        out["pol_proj"] = np.stack([proj(p, 9200 + i) for i, p in enumerate(pol.parameters())])
+        np.savez(os.path.join(HERE, "sac_update_%s.npz" % tag), **out)
+        print("sac_update", tag, out["qf_loss"][:3], out["qf_loss"][-3:], out["policy_loss"], out["log_alpha"])
 
 
 def gen_policy():
