@@ -70,8 +70,16 @@ class B200MBPOCollector(Component):
                         if self.rollout_terminal_state:
                             o, stop = next_o, d
                         else:
-                            ind = self._get_live_ind(d)
-                            o, stop = next_o[ind], d[ind]
+                            # one host read decides everything: with no terminated row (the common case) the next
+                            # batch IS next_o -- no mask, no gather; the survivors of a compaction all have stop == 0,
+                            # so the loop ends exactly when no row is left (mbpo_collector.py:50-53,85-97)
+                            if float(d.sum().item()) != 0.0:
+                                ind = self._get_live_ind(d)
+                                next_o, d = next_o[ind], d[ind]
+                            o, stop = next_o, d
+                            if o.shape[0] == 0:
+                                break
+                            continue
                     else:
                         next_o, r, d, info = self.model.step(o, a, **self.step_kwargs)
                         d = stop + d - stop * d                       # stop or d
