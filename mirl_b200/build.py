@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmirl_b200.so")
 STAMP = os.path.join(HERE, "_build", "stamp")
-SOURCES = ["c_api.cu", "pe_simt.cu", "pe_tc.cu", "pe_train.cu", "critic.cu", "member_draw.cu", "tc_gemm.cu", "train_fused.cu"]
+SOURCES = ["c_api.cu", "pe_simt.cu", "pe_tc.cu", "pe_train.cu", "critic.cu", "member_draw.cu", "tc_gemm.cu", "train_fused.cu", "mlp_rows.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

@@ -516,7 +516,8 @@ int mb_tqc_train_step(const mb_mlp_desc* d, float* params, float* exp_avg, float
 size_t mb_policy_workspace_bytes(const mb_mlp_desc* d, int64_t B) {
     if (!d) return 0;
     if (B < 1) B = 1;
-    return (((size_t)B * d->sizes[d->num_layers] * sizeof(float) + 255) & ~size_t(255)) + critic_workspace_bytes(*d, B) + 256;
+    const size_t fwd = critic_workspace_bytes(*d, B), pack = mlp_rows_pack_bytes(*d);
+    return (((size_t)B * d->sizes[d->num_layers] * sizeof(float) + 255) & ~size_t(255)) + (fwd > pack ? fwd : pack) + 256;
 }
 
 int mb_policy_action(const mb_mlp_desc* d, const float* params, const float* obs, int obs_dim, int64_t B,

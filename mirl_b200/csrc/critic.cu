@@ -512,6 +512,8 @@ int launch_critic_tqc(const mb_mlp_desc& d, const float* params, const float* ob
 // softplus(-2 pre)) ].  One thread per (row, action dim); a row's A lanes reduce the log-prob by shuffle.
 namespace mb {
 
+constexpr int64_t kPolicyRowsMin = 4096;     // rows from which the one-launch forward (mlp_rows.cu) is used
+
 __global__ void k_policy_head(const float* __restrict__ out, const float* __restrict__ eps, int64_t B, int A,
                               mb_policy_cfg cfg, float* __restrict__ action, float* __restrict__ log_prob,
                               float* __restrict__ mean_out, float* __restrict__ std_out) {
@@ -554,7 +556,20 @@ int launch_policy_action(const mb_mlp_desc& d, const float* params, const float*
     float* out = reinterpret_cast<float*>(ws);
     const size_t out_bytes = ((size_t)B * 2 * A * sizeof(float) + 255) & ~size_t(255);
     void* cws = ws_bytes > out_bytes + critic_workspace_bytes(d, B) ? (void*)((char*)ws + out_bytes) : nullptr;
-    int rc = launch_critic_forward(d, params, obs, obs, O, 0, B, out, cws, s);
+    // rollout batch sizes: the whole network in one launch with the activations resident in shared memory
+    // (mlp_rows.cu); small batches keep the per-layer kernels (a handful of 64-row blocks would leave the GPU idle)
+    static int rows_on = -1;
+    if (rows_on < 0) {
+        const char* e = getenv("MB_POLICY_ROWS");
+        rows_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    int rc;
+    if (rows_on && B >= kPolicyRowsMin && d.ensemble_size == 1 && mlp_rows_supported(d) &&
+        ws_bytes >= out_bytes + mlp_rows_pack_bytes(d)) {
+        rc = launch_mlp_rows_forward(d, params, 0, obs, B, out, (char*)ws + out_bytes, s);
+    } else {
+        rc = launch_critic_forward(d, params, obs, obs, O, 0, B, out, cws, s);
+    }
     if (rc) return rc;
     if (log_prob && (32 % A) != 0) cudaMemsetAsync(log_prob, 0, sizeof(float) * B, s);
     const int64_t total = B * A;

@@ -176,6 +176,12 @@ int launch_actor_update(const mb_mlp_desc& pd, float* pparams, float* exp_avg, f
                         int64_t B, float* log_alpha, float* la_m1, float* la_m2, float target_entropy,
                         float alpha_fixed, float* info, void* ws, cudaStream_t s);
 
+// ---- row-parallel forward of one small MLP, the whole network in one launch (mlp_rows.cu): the policy at rollout batch sizes
+bool mlp_rows_supported(const mb_mlp_desc& d);
+size_t mlp_rows_pack_bytes(const mb_mlp_desc& d);
+int launch_mlp_rows_forward(const mb_mlp_desc& d, const float* params, int member, const float* x, int64_t B,
+                            float* out, void* pack, cudaStream_t s);
+
 // ---- critic targets (critic.cu)
 size_t critic_workspace_bytes(const mb_mlp_desc& d, int64_t B);
 int launch_critic_forward(const mb_mlp_desc& d, const float* params, const float* obs,

@@ -666,6 +666,31 @@ def _policy_views(pol, flat):
         yield "b", net.bias(l, flat=flat)[0].view(1, -1)
 
 
+@pytest.mark.parametrize("B,act_fn,hidden", [(4096, "relu", [256, 256]), (10_037, "relu", [256, 256]),
+                                           (6000, "swish", [64, 200, 32])])
+def test_policy_one_launch_forward_matches_oracle(B, act_fn, hidden):
+    """Rollout batch sizes take the one-launch forward (mlp_rows.cu: 64-row blocks, activations resident in shared
+    memory): action, log-prob, mean and std against critic_oracle.policy_action -- a multiple of the block, a ragged
+    row count, and other widths / activation / depth."""
+    import mirl_b200
+    from oracle import critic_oracle as co
+    pol = mirl_b200.B200GaussianPolicy(FakeEnv(), hidden_layers=hidden, activation=act_fn)
+    pW, pb = cases.mlp_params(93, 1, [cases.OBS] + hidden + [2 * cases.ACT])
+    pol.load_state_dict({k: T(v) for k, v in cases.policy_state_dict(pW, pb).items()})
+    pol = pol.to("cuda")
+    o, _ = cases.rollout_inputs(94, B)
+    eps = np.random.RandomState(95).standard_normal((B, cases.ACT)).astype(np.float32)
+    a, info = pol.action(T(o, "cuda"), return_log_prob=True, return_mean_std=True, noise=T(eps, "cuda"))
+    oa, olp, om, osd = co.policy_action([T(x) for x in pW], [T(x) for x in pb], T(o), T(eps), activation=act_fn)
+    assert_close(a, oa, what="action")
+    assert_close(info["mean"], om, what="mean")
+    assert_close(info["std"], osd, what="std")
+    assert_close(info["log_prob"], olp, what="log_prob")
+    with pol.deterministic_(True):
+        a, _ = pol.action(T(o, "cuda"))
+    assert_close(a, torch.tanh(om), what="deterministic action")
+
+
 # ---- N1: policy action -------------------------------------------------------------------------------
 def test_gaussian_policy_action_matches_reference():
     """B200GaussianPolicy.action against the reference GaussianPolicy (17 -> 256 -> 256 -> 12 relu, tanh-squashed):
