@@ -230,3 +230,36 @@ def test_sharded_pool_index_space_is_the_replicated_pools():
         assert np.array_equal(owner, np.asarray(owner_ref)[g]) and np.array_equal(local, np.asarray(local_ref)[g])
     with pytest.raises(RuntimeError):
         pools[0].reserve(20_000, counts=[20_000, 0, 0])
+
+
+def test_actor_trainer_reduction_options():
+    """B200ActorTrainer maps current_v_pi_kwargs onto the kernel's reduction like EnsembleQValue.value does
+    (ensemble_value.py:65-96): all members, a batch-wise drawn subset from NumPy's global generator, and the options
+    the chain does not cover raise instead of silently computing something else.  No GPU needed."""
+    import numpy as np
+    import mirl_b200
+    from mirl_b200 import _lib
+    from tests.helpers_gpu import FakeEnv
+    env = FakeEnv()
+    pol = mirl_b200.B200GaussianPolicy(env, hidden_layers=[32, 32], activation="relu")
+    qf = mirl_b200.B200EnsembleQValue(env, ensemble_size=10, hidden_layers=[32, 32], activation="relu")
+
+    def mk(kw):
+        return mirl_b200.B200ActorTrainer(pol, qf, current_v_pi_kwargs=kw)
+    assert mk({"sample_number": None, "mode": "mean"})._reduction() == (_lib.REDUCE["mean"], None)
+    assert mk({"sample_number": 10})._reduction() == (_lib.REDUCE["min"], None)          # value()'s default mode
+    np.random.seed(3)
+    want = np.random.choice(10, 3, replace=False)
+    np.random.seed(3)
+    mode, members = mk({"sample_number": 3, "batchwise_sample": True, "mode": "max"})._reduction()
+    assert mode == _lib.REDUCE["max"] and list(members) == list(want)
+    with pytest.raises(NotImplementedError):
+        mk({"sample_number": 2})._reduction()                                             # per-row draw
+    with pytest.raises(NotImplementedError):
+        mk({"mode": "sample", "sample_number": None})._reduction()
+    tq = mirl_b200.B200TQCQValue(env, ensemble_size=5, number_head=25, hidden_layers=[32], activation="relu")
+    assert mirl_b200.B200ActorTrainer(pol, tq, current_v_pi_kwargs={"number_drop": 0})._reduction() == \
+        (_lib.REDUCE["mean"], None)
+    with pytest.raises(NotImplementedError):
+        mirl_b200.B200ActorTrainer(pol, tq, current_v_pi_kwargs={"number_drop": 5})._reduction()
+    assert mirl_b200.B200ActorTrainer(pol, qf).target_entropy == -float(env.action_space.shape[0])   # sac_agent.py:55
