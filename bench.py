@@ -399,7 +399,8 @@ def secondary_metrics(dev, world, rank, timed):
         ms = timed(lambda: col.imagine(0), 5, 1) / 5
         out["imagine"]["depth_%d" % depth] = {
             "transitions_per_s": world * 100_000 * depth / (ms * 1e-3), "ms_per_call": ms,
-            "launches_per_horizon_step": "policy: 3 layer kernels + head; model: member draw or host draw, bucket, rollout"}
+            "launches_per_horizon_step": "policy: weight pack + one whole-network kernel + head; model: member draw on the "
+                                         "device, bucket, rollout with the pool insert; one host read (any terminal?)"}
     out["imagine"]["config"] = ("B200MBPOCollector.imagine: 1e5 start states, B200GaussianPolicy 17-256-256-12, "
                                 "transitions inserted into a B200DevicePool by the rollout kernel; per GPU replica")
     return out
