@@ -29,10 +29,16 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kT = kWarps * 32;
 constexpr int kIssuer = kWarps - 1;
-constexpr int kBlockRows = 64;     // rows per CTA pass: four M tiles share every weight fragment
+#ifndef MB_ROWS_BLOCK
+#define MB_ROWS_BLOCK 64
+#endif
+#ifndef MB_ROWS_STAGES
+#define MB_ROWS_STAGES 2
+#endif
+constexpr int kBlockRows = MB_ROWS_BLOCK;     // rows per CTA pass: its M tiles share every weight fragment
 constexpr int kMT = kBlockRows / 16;
 constexpr int kWChunk = 32;        // weight rows per streamed chunk (two k-steps)
-constexpr int kStages = 2;         // ring depth.  16-row chunks in a 4-stage ring (three copies in flight) measured 30 % SLOWER:
+constexpr int kStages = MB_ROWS_STAGES;   // ring depth.  16-row chunks in a 4-stage ring (three copies in flight) measured 30 % SLOWER:
                                    // several bulk copies in flight per SM cost more than the latency they hide
 constexpr int kNT = 4;             // n-tiles per warp: widths up to 8 * kWarps * kNT = 256
 
@@ -61,6 +67,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = pack_bf16x2(a - ha, b - hb);
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 
 struct RowsLayer {
     int K, N;        // fan-in, fan-out
