@@ -224,9 +224,50 @@ def cpu_secondary(threads=None):
             for _ in range(n):
                 fn()
             out[name] = 256 * n / (time.perf_counter() - t0)
+    out["sac_updates_per_s"] = time_ref_sac(20)               # SACAgent.train_from_torch_batch, REDQ settings
     out["kind"] = "reference"
     out["cores"] = threads or os.cpu_count()
     return out
+
+
+def ref_sac_agent():
+    """The unmodified reference SACAgent with configs/redq.json's settings (10 critics 2x256 relu, policy 2x256 relu)
+    on whatever device ptu currently selects; the update step timed by the CPU and eager-GPU arms."""
+    import contextlib
+    import tempfile
+    shim = _reference()
+    from mirl.agents.sac_agent import SACAgent
+    from mirl.policies.gaussian_policy import GaussianPolicy
+    from mirl.utils.logger import logger
+    from mirl.values.ensemble_value import EnsembleQValue
+    import mirl.torch_modules.utils as ptu
+    with contextlib.redirect_stdout(sys.stderr):
+        logger.set_snapshot_dir(tempfile.mkdtemp())
+    env = shim.FakeEnv()
+    pol = GaussianPolicy(env, hidden_layers=[256, 256], activation="relu").to(ptu.device)
+    qf = EnsembleQValue(env, ensemble_size=10, hidden_layers=[256, 256], activation="relu").to(ptu.device)
+    qt = EnsembleQValue(env, ensemble_size=10, hidden_layers=[256, 256], activation="relu").to(ptu.device)
+    return SACAgent(env, pol, qf, qt, policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3, use_automatic_entropy_tuning=True,
+                    alpha_if_not_automatic=0, policy_update_freq=20, target_entropy=-1,
+                    current_v_pi_kwargs={"sample_number": None, "mode": "mean"},
+                    next_v_pi_kwargs={"batchwise_sample": True}, tb_log_freq=-1), ptu
+
+
+def time_ref_sac(n_updates):
+    """Updates per second of the reference agent's train_from_torch_batch (20 critic updates per actor update)."""
+    from tests.golden import cases
+    agent, ptu = ref_sac_agent()
+    batch = {k: torch.from_numpy(v).to(ptu.device) for k, v in cases.sac_batch(1200, 256).items()}
+    for _ in range(3):
+        agent.train_from_torch_batch(batch)
+    if torch.cuda.is_available() and str(ptu.device) != "cpu":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_updates):
+        agent.train_from_torch_batch(batch)
+    if torch.cuda.is_available() and str(ptu.device) != "cpu":
+        torch.cuda.synchronize()
+    return n_updates / (time.perf_counter() - t0)
 
 
 def torch_eager_arm(dev):
@@ -270,6 +311,7 @@ def torch_eager_arm(dev):
             tr.train_from_torch_batch(bt)
         torch.cuda.synchronize()
         out["model_train_samples_per_s"] = 7 * 256 * 50 / (time.perf_counter() - t0)
+        out["sac_updates_per_s"] = time_ref_sac(100)
     except Exception as exc:                                # the reference's GPU path is not ours to fix
         out["error"] = "%s: %s" % (type(exc).__name__, str(exc)[:200])
     finally:
@@ -351,6 +393,17 @@ def secondary_metrics(dev, world, rank, timed):
                            "config": "REDQ: policy 17-256-256-12 relu through the mean of 10 critics 2x256, batch 256: policy "
                                      "forward + sample + alpha step + critics forward + input-gradient chain + policy "
                                      "backward + Adam"}
+    # the whole agent update (target + critic update, actor + alpha every 20th): B200SACUpdater, train_info read back
+    # to the host after every update like the reference does
+    qt2, _ = make_critic("redq", 172, device=dev)
+    up = mirl_b200.B200SACUpdater(pol, q, qt2, policy_update_freq=20, target_entropy=-1, alpha_if_not_automatic=0,
+                                  current_v_pi_kwargs={"sample_number": None, "mode": "mean"},
+                                  next_v_pi_kwargs={"batchwise_sample": True})
+    sb = {k: T(v, dev) for k, v in cases.sac_batch(1200, B).items()}
+    ms = timed(lambda: up.train_from_torch_batch(sb), 100, 20) / 100
+    out["sac_update"] = {"updates_per_s": 1e3 / ms, "kernel_ms": ms, "bound": "latency / host (three device->host reads per update)",
+                         "config": "SACAgent.train_from_torch_batch with configs/redq.json's settings on B200SACUpdater: policy "
+                                   "sample + min-of-2 TD target, fused critic update, actor + alpha every 20th update"}
     ms = timed(lambda: q.q_target(o, a, r, d, lp, alpha=0.2, sample_number=2, batchwise_sample=True), 200, 20) / 200
     tf = 2 * 2 * cm * B / (ms * 1e-3) / 1e12                                             # 2 drawn members
     out["redq_target"] = {"targets_per_s": world * B / (ms * 1e-3), "kernel_ms": ms, "achieved": tf, "peak": pk["tensor"],
