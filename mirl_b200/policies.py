@@ -169,6 +169,7 @@ class B200ActorTrainer(object):
         self.alpha_state = torch.tensor([float(init_log_alpha), 0.0, 0.0], device=dev)
         self.num_updates = 0
         self._ws = None
+        self._alpha_host = None
 
     @property
     def log_alpha(self):
@@ -176,9 +177,13 @@ class B200ActorTrainer(object):
 
     def get_alpha(self):
         """``SACAgent._get_alpha`` (sac_agent.py:66-72)."""
-        if self.use_automatic_entropy_tuning:
-            return float(self.alpha_state[0].exp().item())
-        return self.alpha_if_not_automatic
+        if not self.use_automatic_entropy_tuning:
+            return self.alpha_if_not_automatic
+        # log_alpha only changes in update_async: one device read per actor update, not one per critic update
+        # (REDQ runs 20 critic updates, each needing alpha for its TD target, per actor update)
+        if self._alpha_host is None:
+            self._alpha_host = float(self.alpha_state[0].exp().item())
+        return self._alpha_host
 
     def _reduction(self):
         import numpy as np
@@ -236,12 +241,15 @@ class B200ActorTrainer(object):
                 float(self.target_entropy), float(self.alpha_if_not_automatic), _lib.ptr(info), _lib.ptr(self._ws),
                 self._ws.numel(), _lib.stream(dev)))
         self.num_updates += 1
+        self._alpha_host = None
         pol.net.mark_weights_changed()
         return info
 
     def update(self, obs, noise=None):
         """-> the ``train_info`` entries of the reference (sac_agent.py:97-99,147-149), synchronising like it."""
         v = self.update_async(obs, noise).tolist()
+        if self.use_automatic_entropy_tuning:
+            self._alpha_host = v[5]                       # exp(log_alpha) after its step, as the kernel computed it
         out = {"policy/loss": v[0], "policy/q_pi": v[1], "policy/entropy": v[2]}
         if self.use_automatic_entropy_tuning:
             out.update({"alpha/value": v[3], "alpha/loss": v[4]})
