@@ -401,7 +401,12 @@ def secondary_metrics(dev, world, rank, timed):
                                   next_v_pi_kwargs={"batchwise_sample": True})
     sb = {k: T(v, dev) for k, v in cases.sac_batch(1200, B).items()}
     ms = timed(lambda: up.train_from_torch_batch(sb), 100, 20) / 100
-    out["sac_update"] = {"updates_per_s": 1e3 / ms, "kernel_ms": ms, "bound": "latency / host (three device->host reads per update)",
+    up.sync_info = False
+    ms_async = timed(lambda: up.train_from_torch_batch(sb), 100, 20) / 100
+    up.sync_info = True
+    out["sac_update"] = {"updates_per_s": 1e3 / ms, "kernel_ms": ms, "kernel_ms_no_host_read": ms_async,
+                         "bound": "latency / host (one device->host read per update; none between actor updates with "
+                                  "sync_info=False)",
                          "config": "SACAgent.train_from_torch_batch with configs/redq.json's settings on B200SACUpdater: policy "
                                    "sample + min-of-2 TD target, fused critic update, actor + alpha every 20th update"}
     ms = timed(lambda: q.q_target(o, a, r, d, lp, alpha=0.2, sample_number=2, batchwise_sample=True), 200, 20) / 200

@@ -21,12 +21,13 @@ from .values import B200CriticTrainer, B200TQCQValue
 class B200SACUpdater(object):
     """Arguments are those of ``SACAgent`` / ``DDPGAgent`` (sac_agent.py:17-37, ddpg_agent.py:40-60) /
     ``TQCAgent`` (tqc_agent.py:17-39).  ``noise_fn(shape) -> tensor`` replaces the device generator for the policy's
-    draws (tests replay the reference's CPU stream with it)."""
+    draws (tests replay the reference's CPU stream with it).  ``sync_info=False`` leaves ``qf/loss`` on the device (a
+    0-dim tensor), so that the critic updates between two actor updates run without a host read."""
 
     def __init__(self, policy, qf, qf_target, discount=0.99, policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3,
                  policy_update_freq=1, target_update_freq=1, clip_error=None, alpha_if_not_automatic=1e-2,
                  use_automatic_entropy_tuning=True, init_log_alpha=0, target_entropy=None, next_v_pi_kwargs=None,
-                 current_v_pi_kwargs=None, optimizer_class="Adam", optimizer_kwargs={}, noise_fn=None):
+                 current_v_pi_kwargs=None, optimizer_class="Adam", optimizer_kwargs={}, noise_fn=None, sync_info=True):
         self.policy, self.qf, self.qf_target = policy, qf, qf_target
         self.tqc = isinstance(qf, B200TQCQValue)
         if next_v_pi_kwargs is None:                      # tqc_agent.py:23-28 defaults
@@ -48,6 +49,7 @@ class B200SACUpdater(object):
                                       init_log_alpha=init_log_alpha, target_entropy=target_entropy,
                                       current_v_pi_kwargs=current_v_pi_kwargs, optimizer_class=optimizer_class,
                                       optimizer_kwargs=optimizer_kwargs)
+        self.sync_info = sync_info
         self.num_train_steps = 0
 
     def _noise(self, B):
@@ -76,7 +78,10 @@ class B200SACUpdater(object):
             # (ddpg_agent.py:139): the reference draws -- and discards -- a per-row member sample there
             # (ensemble_value.py:80-90).  Consume the same numbers, so that a run stays on the reference's NumPy stream.
             self.qf._draw_subset(obs.shape[0], (1,), 2, False)
-        info = dict(self.critic.update(obs, actions, q_target))
+        if self.sync_info:
+            info = dict(self.critic.update(obs, actions, q_target))
+        else:                                      # no host read: the loss stays a 0-dim device tensor
+            info = {"qf/loss": self.critic.update_async(obs, actions, q_target)[0]}
         if self.num_train_steps % self.policy_update_freq == 0:
             info.update(self.actor.update(obs, noise=self._noise(obs.shape[0])))
         self.num_train_steps += 1
