@@ -175,6 +175,11 @@ class B200ActorTrainer(object):
     def log_alpha(self):
         return self.alpha_state[0:1]
 
+    def set_log_alpha(self, value):
+        """Restore ``log_alpha`` (e.g. from a checkpoint); its Adam moments are kept."""
+        self.alpha_state[0] = float(value)
+        self._alpha_host = None
+
     def get_alpha(self):
         """``SACAgent._get_alpha`` (sac_agent.py:66-72)."""
         if not self.use_automatic_entropy_tuning:
